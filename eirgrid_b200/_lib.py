@@ -1,0 +1,288 @@
+"""ctypes binding of libeirgrid_b200.so (the C ABI declared in include/eirgrid_b200.h).
+
+The library is built in-tree by `python -m eirgrid_b200.build`. There is no Python or CPU fallback: if the
+shared object is missing this module raises, and every compute call fails with EG_ERR_NO_DEVICE without a GPU.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libeirgrid_b200.so")
+
+EXPORTS = [
+    "eg_init", "eg_destroy", "eg_last_error", "eg_sync", "eg_kernel_launches", "eg_map_load", "eg_map_set",
+    "eg_map_info", "eg_map_site_tables", "eg_map_site_static", "eg_weights_new", "eg_weights_free",
+    "eg_weights_clone", "eg_weights_load_json", "eg_weights_save_json", "eg_weights_merge", "eg_weights_get_table",
+    "eg_weights_set_table", "eg_weights_get_best", "eg_deficit_key_action", "eg_rollout_batch", "eg_weights_upload",
+    "eg_rollout_batch_device", "eg_replay_batch", "eg_replay_batch_device", "eg_update", "eg_update_stats_device",
+    "eg_update_apply_stats", "eg_location_analysis",
+]
+
+
+class EirgridError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("eirgrid_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: run `python -m eirgrid_b200.build` (needs nvcc). "
+                          "eirgrid_b200 has no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i64 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int64
+    L.eg_last_error.restype = C.c_char_p
+    L.eg_init.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    L.eg_destroy.argtypes = [vp]
+    L.eg_destroy.restype = None
+    L.eg_sync.argtypes = [vp]
+    L.eg_kernel_launches.argtypes = [vp]
+    L.eg_kernel_launches.restype = u64
+    L.eg_map_load.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p]
+    L.eg_map_set.argtypes = [vp, C.POINTER(_abi.MapDesc)]
+    L.eg_map_info.argtypes = [vp, C.POINTER(u32)]
+    L.eg_map_site_tables.argtypes = [vp, u32, u32, u32, vp, vp, vp]
+    L.eg_map_site_static.argtypes = [vp, vp, vp]
+    L.eg_weights_new.argtypes = [C.POINTER(vp)]
+    L.eg_weights_free.argtypes = [vp]
+    L.eg_weights_free.restype = None
+    L.eg_weights_clone.argtypes = [vp, C.POINTER(vp)]
+    L.eg_weights_load_json.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.eg_weights_save_json.argtypes = [vp, C.c_char_p]
+    L.eg_weights_merge.argtypes = [vp, vp]
+    L.eg_weights_get_table.argtypes = [vp, C.POINTER(_abi.WeightsTable)]
+    L.eg_weights_set_table.argtypes = [vp, C.POINTER(_abi.WeightsTable)]
+    L.eg_weights_get_best.argtypes = [vp, vp, vp, vp, vp]
+    L.eg_deficit_key_action.argtypes = [u32]
+    L.eg_deficit_key_action.restype = C.c_uint8
+    L.eg_rollout_batch.argtypes = [vp, vp, C.POINTER(_abi.RunCfg), u64, u64, u32, vp, vp, vp, vp]
+    L.eg_weights_upload.argtypes = [vp, vp]
+    L.eg_rollout_batch_device.argtypes = [vp, C.POINTER(_abi.RunCfg), u64, u64, u32, vp, vp, vp, vp]
+    L.eg_replay_batch.argtypes = [vp, C.POINTER(_abi.RunCfg), vp, u32, vp, vp, vp]
+    L.eg_replay_batch_device.argtypes = [vp, C.POINTER(_abi.RunCfg), vp, u32, vp, vp, vp]
+    L.eg_update.argtypes = [vp, vp, vp, u32, u32, u64, C.POINTER(_abi.UpdateStats)]
+    L.eg_update_stats_device.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp]
+    L.eg_update_apply_stats.argtypes = [vp, vp, u64, vp, vp, i64, C.POINTER(_abi.UpdateStats)]
+    L.eg_location_analysis.argtypes = [vp, C.c_int, C.c_int32, C.c_double, vp, u32, u32]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc < 0:
+        raise EirgridError(rc, lib().eg_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def _dev_ptr(t):
+    """Device pointer of a torch tensor (or None / int passthrough)."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    return t.data_ptr()
+
+
+class Weights:
+    """The policy table == reference ActionWeights (ai/learning/weights/mod.rs:49-107)."""
+
+    def __init__(self, handle=None):
+        self.L = lib()
+        if handle is None:
+            h = C.c_void_p()
+            check(self.L.eg_weights_new(C.byref(h)))  # ActionWeights::new
+            handle = h
+        self.h = handle
+
+    @classmethod
+    def load_from_file(cls, path):  # ActionWeights::load_from_file
+        h = C.c_void_p()
+        check(lib().eg_weights_load_json(os.fsencode(path), C.byref(h)))
+        return cls(h)
+
+    def save_to_file(self, path):  # ActionWeights::save_to_file
+        parent = os.path.dirname(path)
+        if parent:
+            os.makedirs(parent, exist_ok=True)
+        check(self.L.eg_weights_save_json(self.h, os.fsencode(path)))
+
+    def clone(self):
+        h = C.c_void_p()
+        check(self.L.eg_weights_clone(self.h, C.byref(h)))
+        return Weights(h)
+
+    def update_weights_from(self, other):  # ActionWeights::update_weights_from
+        check(self.L.eg_weights_merge(self.h, other.h))
+
+    def table(self):
+        t = _abi.WeightsTable()
+        check(self.L.eg_weights_get_table(self.h, C.byref(t)))
+        return t
+
+    def set_table(self, t):
+        check(self.L.eg_weights_set_table(self.h, C.byref(t)))
+
+    def best(self):
+        """(has_best, n_best[26], best[26,80], n_best_deficit[26], best_deficit[26,40])"""
+        nb = np.zeros(26, np.uint8)
+        b = np.zeros((26, 2 * _abi.MAX_ACTIONS_PER_YEAR), np.uint8)
+        nd = np.zeros(26, np.uint8)
+        d = np.zeros((26, _abi.MAX_ACTIONS_PER_YEAR), np.uint8)
+        has = check(self.L.eg_weights_get_best(self.h, _abi.ptr(nb), _abi.ptr(b), _abi.ptr(nd), _abi.ptr(d)))
+        return bool(has), nb, b, nd, d
+
+    def has_best_actions(self):  # ActionWeights::has_best_actions
+        return bool(self.table().has_best)
+
+    def update(self, results, trajs, replay_best=False, rng_seed=0):
+        """The write-lock section of multi_simulation.rs:494-508 for a batch, in episode order (host arrays)."""
+        results = np.ascontiguousarray(results)
+        trajs = np.ascontiguousarray(trajs)
+        assert results.dtype == _abi.RESULT_DTYPE and trajs.dtype == _abi.TRAJ_DTYPE and len(results) == len(trajs)
+        st = _abi.UpdateStats()
+        check(self.L.eg_update(self.h, _abi.ptr(results), _abi.ptr(trajs), len(results), int(replay_best), rng_seed,
+                               C.byref(st)))
+        return st
+
+    def apply_stats(self, stats, n_total, best_result, best_traj, best_index):
+        stats = np.ascontiguousarray(stats, dtype=np.int64)
+        assert stats.size == _abi.STATS_WORDS
+        st = _abi.UpdateStats()
+        br = np.ascontiguousarray(best_result) if best_result is not None else None
+        bt = np.ascontiguousarray(best_traj) if best_traj is not None else None
+        check(self.L.eg_update_apply_stats(self.h, _abi.ptr(stats), int(n_total), _abi.ptr(br), _abi.ptr(bt),
+                                           int(best_index), C.byref(st)))
+        return st
+
+    def __del__(self):
+        try:
+            self.L.eg_weights_free(self.h)
+        except Exception:
+            pass
+
+
+class Context:
+    """One device context per process/GPU (eg_ctx)."""
+
+    def __init__(self, device=0, stream=None):
+        self.L = lib()
+        h = C.c_void_p()
+        check(self.L.eg_init(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.L.eg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- map ----
+    def map_load(self, settlements_json, generators_csv, coastline_json):
+        check(self.L.eg_map_load(self.h, os.fsencode(settlements_json), os.fsencode(generators_csv),
+                                 os.fsencode(coastline_json)))
+
+    def map_load_dir(self, asset_dir):
+        """asset_dir holds settlements.json, ireland_generators.csv, coastline_points.json (aiSimulator/assets layout)."""
+        self.map_load(os.path.join(asset_dir, "settlements.json"), os.path.join(asset_dir, "ireland_generators.csv"),
+                      os.path.join(asset_dir, "coastline_points.json"))
+
+    def map_set(self, sx, sy, spop, ex, ey, etype, ecap, cx, cy, grid_n, grid_step):
+        f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        sx, sy, ex, ey, ecap, cx, cy = map(f8, (sx, sy, ex, ey, ecap, cx, cy))
+        spop = np.ascontiguousarray(spop, dtype=np.uint32)
+        etype = np.ascontiguousarray(etype, dtype=np.uint8)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        d = _abi.MapDesc(len(sx), dp(sx), dp(sy), spop.ctypes.data_as(C.POINTER(C.c_uint32)), len(ex), dp(ex), dp(ey),
+                         etype.ctypes.data_as(C.POINTER(C.c_uint8)), dp(ecap), len(cx), dp(cx), dp(cy), int(grid_n),
+                         float(grid_step))
+        check(self.L.eg_map_set(self.h, C.byref(d)))
+
+    def map_info(self):
+        out = (C.c_uint32 * 4)()
+        check(self.L.eg_map_info(self.h, out))
+        return dict(n_settlements=out[0], n_existing=out[1], n_coast=out[2], grid_n=out[3])
+
+    def site_tables(self, year_index, rclass, pclass):
+        ns = self.map_info()["grid_n"] ** 2
+        pref, stat, order = np.zeros(ns), np.zeros(ns), np.zeros(ns, np.uint32)
+        check(self.L.eg_map_site_tables(self.h, year_index, rclass, pclass, _abi.ptr(pref), _abi.ptr(stat), _abi.ptr(order)))
+        return pref, stat, order
+
+    def site_static(self):
+        ns = self.map_info()["grid_n"] ** 2
+        c, o = np.zeros(ns), np.zeros(ns)
+        check(self.L.eg_map_site_static(self.h, _abi.ptr(c), _abi.ptr(o)))
+        return c, o
+
+    # ---- hot path, host buffers ----
+    def rollout(self, weights, n, seed=1, first_episode=0, cfg=None, want_traj=True, want_sites=False,
+                want_yearly=False, out=None):
+        cfg = cfg or _abi.RunCfg()
+        out = out or {}
+        res = out.get("results") if out.get("results") is not None else np.zeros(n, _abi.RESULT_DTYPE)
+        traj = (out.get("traj") if out.get("traj") is not None else np.zeros(n, _abi.TRAJ_DTYPE)) if want_traj else None
+        sites = np.zeros(n, _abi.SITES_DTYPE) if want_sites else None
+        yearly = np.zeros(n, _abi.YEARLY_DTYPE) if want_yearly else None
+        check(self.L.eg_rollout_batch(self.h, weights.h, C.byref(cfg), seed, first_episode, n, _abi.ptr(res),
+                                      _abi.ptr(traj), _abi.ptr(sites), _abi.ptr(yearly)))
+        return res, traj, sites, yearly
+
+    def replay(self, traj_in, cfg=None, want_sites=True, want_yearly=True):
+        cfg = cfg or _abi.RunCfg()
+        traj_in = np.ascontiguousarray(traj_in)
+        assert traj_in.dtype == _abi.TRAJ_DTYPE
+        n = len(traj_in)
+        res = np.zeros(n, _abi.RESULT_DTYPE)
+        sites = np.zeros(n, _abi.SITES_DTYPE) if want_sites else None
+        yearly = np.zeros(n, _abi.YEARLY_DTYPE) if want_yearly else None
+        check(self.L.eg_replay_batch(self.h, C.byref(cfg), _abi.ptr(traj_in), n, _abi.ptr(res), _abi.ptr(sites),
+                                     _abi.ptr(yearly)))
+        return res, sites, yearly
+
+    # ---- hot path, device buffers (torch uint8 tensors sized by the dtypes in _abi) ----
+    def weights_upload(self, weights):
+        check(self.L.eg_weights_upload(self.h, weights.h))
+
+    def rollout_device(self, n, seed, first_episode, d_results, d_traj=None, d_sites=None, d_yearly=None, cfg=None):
+        cfg = cfg or _abi.RunCfg()
+        check(self.L.eg_rollout_batch_device(self.h, C.byref(cfg), seed, first_episode, n, _dev_ptr(d_results),
+                                             _dev_ptr(d_traj), _dev_ptr(d_sites), _dev_ptr(d_yearly)))
+
+    def replay_device(self, n, d_traj_in, d_results, d_sites=None, d_yearly=None, cfg=None):
+        cfg = cfg or _abi.RunCfg()
+        check(self.L.eg_replay_batch_device(self.h, C.byref(cfg), _dev_ptr(d_traj_in), n, _dev_ptr(d_results),
+                                            _dev_ptr(d_sites), _dev_ptr(d_yearly)))
+
+    def update_stats_device(self, weights, n, d_results, d_traj, d_stats, d_best_score, d_best_index):
+        check(self.L.eg_update_stats_device(self.h, weights.h, _dev_ptr(d_results), _dev_ptr(d_traj), n,
+                                            _dev_ptr(d_stats), _dev_ptr(d_best_score), _dev_ptr(d_best_index)))
+
+    def location_analysis(self, use_loaded_map, half_steps=25, step=2000.0, first_point=0, n_points=None):
+        side = 2 * half_steps + 1
+        n = side * side - first_point if n_points is None else n_points
+        out = np.zeros((n, _abi.N_GEN_TYPES))
+        check(self.L.eg_location_analysis(self.h, int(use_loaded_map), half_steps, step, _abi.ptr(out), first_point, n))
+        return out
+
+    def sync(self):
+        check(self.L.eg_sync(self.h))
+
+    def kernel_launches(self):
+        return int(self.L.eg_kernel_launches(self.h))

@@ -1,0 +1,417 @@
+// engine.cu — device context and the C-ABI entry points of include/eirgrid_b200.h.
+// There is no CPU fallback: every compute entry point needs a CUDA device and fails with
+// EG_ERR_NO_DEVICE / EG_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "common.hpp"
+#include "episode.cuh"
+#include "host_tables.hpp"
+#include "site_tables.cuh"
+#include "stats.cuh"
+#include "suitability.cuh"
+#include "weights.hpp"
+
+static thread_local std::string g_last_error;
+int eg_fail(int code, const std::string& message) {
+  g_last_error = message;
+  return code;
+}
+
+#define EG_CUDA(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t err__ = (expr);                                                                         \
+    if (err__ != cudaSuccess)                                                                           \
+      return eg_fail(EG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));               \
+  } while (0)
+
+struct eg_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  uint64_t launches = 0;
+  bool map_ready = false;
+  bool policy_ready = false;
+  EgHostMap hmap;
+  EgHostTables htab;
+  // device memory
+  EgSmallTables* d_small = nullptr;
+  double* d_op_cost = nullptr;
+  double* d_site_opinion = nullptr;
+  double* d_coast = nullptr;
+  double* d_prefix = nullptr;          // [6][26][ns]
+  double* d_static_unsorted = nullptr; // [7][26][ns]
+  uint16_t* d_order = nullptr;
+  double* d_static_sorted = nullptr;
+  double* d_prefix_sorted = nullptr;
+  double* d_near = nullptr;
+  double *d_sx = nullptr, *d_sy = nullptr, *d_ex = nullptr, *d_ey = nullptr, *d_cx = nullptr, *d_cy = nullptr;
+  uint32_t* d_pop = nullptr;
+  EgPolicyDevice* d_policy = nullptr;
+  EgDeviceMap dmap{};
+  // scratch for the host-buffer entry points
+  size_t cap = 0;
+  eg_result* s_out = nullptr;
+  eg_traj* s_traj = nullptr;
+  eg_traj* s_traj_in = nullptr;
+  eg_sites* s_sites = nullptr;
+  eg_yearly* s_yearly = nullptr;
+  size_t cap_yearly = 0, cap_sites = 0, cap_traj_in = 0;
+};
+
+namespace {
+
+void free_map(eg_ctx* c) {
+  void* ptrs[] = {c->d_small, c->d_op_cost, c->d_site_opinion, c->d_coast, c->d_prefix, c->d_static_unsorted, c->d_order,
+                  c->d_static_sorted, c->d_prefix_sorted, c->d_near, c->d_sx, c->d_sy, c->d_ex, c->d_ey, c->d_cx, c->d_cy, c->d_pop};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  c->d_small = nullptr; c->d_op_cost = nullptr; c->d_site_opinion = nullptr; c->d_coast = nullptr; c->d_prefix = nullptr;
+  c->d_static_unsorted = nullptr; c->d_order = nullptr; c->d_static_sorted = nullptr; c->d_prefix_sorted = nullptr;
+  c->d_near = nullptr; c->d_sx = c->d_sy = c->d_ex = c->d_ey = c->d_cx = c->d_cy = nullptr; c->d_pop = nullptr;
+  c->map_ready = false;
+}
+
+template <typename T>
+int upload(T** dst, const T* src, size_t n, cudaStream_t s) {
+  EG_CUDA(cudaMalloc((void**)dst, std::max<size_t>(n, 1) * sizeof(T)));
+  if (n) EG_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+  return EG_OK;
+}
+
+int build_device_map(eg_ctx* c) {
+  int rc = eg_host_map_validate(c->hmap);
+  if (rc) return rc;
+  EG_CUDA(cudaSetDevice(c->device));
+  free_map(c);
+  eg_host_build_tables(c->hmap, &c->htab);
+  const EgHostMap& m = c->hmap;
+  const int ns = m.grid_n * m.grid_n;
+  cudaStream_t s = c->stream;
+  if ((rc = upload(&c->d_small, &c->htab.small, 1, s))) return rc;
+  if ((rc = upload(&c->d_op_cost, c->htab.op_cost.data(), c->htab.op_cost.size(), s))) return rc;
+  if ((rc = upload(&c->d_near, c->htab.near_factor.data(), c->htab.near_factor.size(), s))) return rc;
+  if ((rc = upload(&c->d_sx, m.sx.data(), m.sx.size(), s))) return rc;
+  if ((rc = upload(&c->d_sy, m.sy.data(), m.sy.size(), s))) return rc;
+  if ((rc = upload(&c->d_ex, m.ex.data(), m.ex.size(), s))) return rc;
+  if ((rc = upload(&c->d_ey, m.ey.data(), m.ey.size(), s))) return rc;
+  if ((rc = upload(&c->d_cx, m.cx.data(), m.cx.size(), s))) return rc;
+  if ((rc = upload(&c->d_cy, m.cy.data(), m.cy.size(), s))) return rc;
+  if ((rc = upload(&c->d_pop, c->htab.pop.data(), c->htab.pop.size(), s))) return rc;
+  EG_CUDA(cudaMalloc((void**)&c->d_site_opinion, ns * sizeof(double)));
+  EG_CUDA(cudaMalloc((void**)&c->d_coast, ns * sizeof(double)));
+  EG_CUDA(cudaMalloc((void**)&c->d_prefix, (size_t)EG_N_RCLASS * EG_NY * ns * sizeof(double)));
+  EG_CUDA(cudaMalloc((void**)&c->d_static_unsorted, (size_t)EG_N_PCLASS * EG_NY * ns * sizeof(double)));
+  EG_CUDA(cudaMalloc((void**)&c->d_order, (size_t)EG_N_PCLASS * EG_NY * ns * sizeof(uint16_t)));
+  EG_CUDA(cudaMalloc((void**)&c->d_static_sorted, (size_t)EG_N_PCLASS * EG_NY * ns * sizeof(double)));
+  EG_CUDA(cudaMalloc((void**)&c->d_prefix_sorted, (size_t)EG_N_PCLASS * EG_NY * ns * sizeof(double)));
+  EgSiteBuildParams bp{};
+  bp.grid_n = m.grid_n; bp.n_sites = ns; bp.step = m.step;
+  bp.n_settlements = (int)m.sx.size(); bp.sx = c->d_sx; bp.sy = c->d_sy; bp.pop = c->d_pop;
+  bp.n_existing = (int)m.ex.size(); bp.ex = c->d_ex; bp.ey = c->d_ey;
+  bp.n_coast = (int)m.cx.size(); bp.cx = c->d_cx; bp.cy = c->d_cy;
+  bp.size_factor = c->htab.small.size_factor;
+  bp.prefix = c->d_prefix; bp.coast_factor = c->d_coast; bp.site_opinion = c->d_site_opinion;
+  bp.static_unsorted = c->d_static_unsorted; bp.order = c->d_order; bp.static_sorted = c->d_static_sorted;
+  bp.prefix_sorted = c->d_prefix_sorted;
+  int launches = 0;
+  EG_CUDA(eg_build_site_tables(bp, s, &launches));
+  c->launches += (uint64_t)launches;
+  EG_CUDA(cudaStreamSynchronize(s));
+  c->dmap.small = c->d_small;
+  c->dmap.op_cost = c->d_op_cost;
+  c->dmap.site_opinion = c->d_site_opinion;
+  c->dmap.coast_factor = c->d_coast;
+  c->dmap.order = c->d_order;
+  c->dmap.static_score = c->d_static_sorted;
+  c->dmap.prefix_score = c->d_prefix_sorted;
+  c->dmap.near_factor = c->d_near;
+  c->dmap.n_sites = ns;
+  c->dmap.grid_n = m.grid_n;
+  c->dmap.kmax = c->htab.kmax;
+  c->map_ready = true;
+  return EG_OK;
+}
+
+int ensure_scratch(eg_ctx* c, size_t n, bool sites, bool yearly, bool traj_in) {
+  if (n > c->cap) {
+    if (c->s_out) cudaFree(c->s_out);
+    if (c->s_traj) cudaFree(c->s_traj);
+    c->s_out = nullptr; c->s_traj = nullptr; c->cap = 0;
+    EG_CUDA(cudaMalloc((void**)&c->s_out, n * sizeof(eg_result)));
+    EG_CUDA(cudaMalloc((void**)&c->s_traj, n * sizeof(eg_traj)));
+    c->cap = n;
+  }
+  if (sites && n > c->cap_sites) {
+    if (c->s_sites) cudaFree(c->s_sites);
+    c->s_sites = nullptr; c->cap_sites = 0;
+    EG_CUDA(cudaMalloc((void**)&c->s_sites, n * sizeof(eg_sites)));
+    c->cap_sites = n;
+  }
+  if (yearly && n > c->cap_yearly) {
+    if (c->s_yearly) cudaFree(c->s_yearly);
+    c->s_yearly = nullptr; c->cap_yearly = 0;
+    EG_CUDA(cudaMalloc((void**)&c->s_yearly, n * sizeof(eg_yearly)));
+    c->cap_yearly = n;
+  }
+  if (traj_in && n > c->cap_traj_in) {
+    if (c->s_traj_in) cudaFree(c->s_traj_in);
+    c->s_traj_in = nullptr; c->cap_traj_in = 0;
+    EG_CUDA(cudaMalloc((void**)&c->s_traj_in, n * sizeof(eg_traj)));
+    c->cap_traj_in = n;
+  }
+  return EG_OK;
+}
+
+int check_cfg(const eg_ctx* c, const eg_run_cfg* cfg) {
+  if (!c) return eg_fail(EG_ERR_INVALID, "ctx is NULL");
+  if (!cfg) return eg_fail(EG_ERR_INVALID, "cfg is NULL");
+  if (!c->map_ready) return eg_fail(EG_ERR_STATE, "no map loaded: call eg_map_load or eg_map_set first");
+  if (cfg->enable_construction_delays)
+    return eg_fail(EG_ERR_INVALID, "enable_construction_delays=1 is not implemented on the device path (SURVEY.md §8(f) N1)");
+  return EG_OK;
+}
+
+EgEpisodeParams make_params(const eg_ctx* c, const eg_run_cfg* cfg, uint64_t seed, uint64_t first, uint32_t n) {
+  EgEpisodeParams p{};
+  p.map = c->dmap;
+  p.policy = c->d_policy;
+  p.seed = seed;
+  p.first_episode = first;
+  p.n = n;
+  p.cost_only = cfg->cost_only;
+  p.energy_sales = cfg->enable_energy_sales;
+  p.same_stream = cfg->same_stream_all_episodes;
+  p.replay_best = cfg->replay_best;
+  p.ln100 = std::log(50000000000.0 * 100.0 / 50000000000.0);
+  return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* eg_last_error(void) { return g_last_error.c_str(); }
+
+int eg_init(int device, void* cuda_stream, eg_ctx** out) {
+  if (!out) return eg_fail(EG_ERR_INVALID, "eg_init: out is NULL");
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0)
+    return eg_fail(EG_ERR_NO_DEVICE, std::string("no CUDA device (") + cudaGetErrorString(err) + "); eirgrid_b200 has no CPU fallback");
+  if (device < 0 || device >= count) return eg_fail(EG_ERR_INVALID, "eg_init: device index out of range");
+  EG_CUDA(cudaSetDevice(device));
+  eg_ctx* c = new eg_ctx();
+  c->device = device;
+  if (cuda_stream) {
+    c->stream = (cudaStream_t)cuda_stream;
+  } else {
+    cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e2 != cudaSuccess) { delete c; return eg_fail(EG_ERR_CUDA, cudaGetErrorString(e2)); }
+    c->own_stream = true;
+  }
+  *out = c;
+  return EG_OK;
+}
+
+void eg_destroy(eg_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_map(c);
+  void* ptrs[] = {c->d_policy, c->s_out, c->s_traj, c->s_traj_in, c->s_sites, c->s_yearly};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int eg_sync(eg_ctx* c) {
+  if (!c) return eg_fail(EG_ERR_INVALID, "ctx is NULL");
+  EG_CUDA(cudaStreamSynchronize(c->stream));
+  return EG_OK;
+}
+
+uint64_t eg_kernel_launches(const eg_ctx* c) { return c ? c->launches : 0; }
+
+int eg_map_load(eg_ctx* c, const char* settlements_json, const char* generators_csv, const char* coastline_json) {
+  if (!c || !settlements_json || !generators_csv || !coastline_json) return eg_fail(EG_ERR_INVALID, "eg_map_load: NULL argument");
+  int rc = eg_host_map_load(&c->hmap, settlements_json, generators_csv, coastline_json);
+  if (rc) return rc;
+  return build_device_map(c);
+}
+
+int eg_map_set(eg_ctx* c, const eg_map_desc* desc) {
+  if (!c) return eg_fail(EG_ERR_INVALID, "eg_map_set: ctx is NULL");
+  int rc = eg_host_map_set(&c->hmap, desc);
+  if (rc) return rc;
+  return build_device_map(c);
+}
+
+int eg_map_info(const eg_ctx* c, uint32_t out[4]) {
+  if (!c || !out) return eg_fail(EG_ERR_INVALID, "eg_map_info: NULL argument");
+  if (!c->map_ready) return eg_fail(EG_ERR_STATE, "no map loaded");
+  out[0] = (uint32_t)c->hmap.sx.size();
+  out[1] = (uint32_t)c->hmap.ex.size();
+  out[2] = (uint32_t)c->hmap.cx.size();
+  out[3] = (uint32_t)c->hmap.grid_n;
+  return EG_OK;
+}
+
+int eg_map_site_tables(eg_ctx* c, uint32_t year_index, uint32_t rclass, uint32_t pclass, double* prefix_score,
+                       double* static_score_sorted, uint32_t* order_sorted) {
+  if (!c) return eg_fail(EG_ERR_INVALID, "ctx is NULL");
+  if (!c->map_ready) return eg_fail(EG_ERR_STATE, "no map loaded");
+  if (year_index >= EG_NY || rclass >= EG_N_RCLASS || pclass >= EG_N_PCLASS) return eg_fail(EG_ERR_INVALID, "index out of range");
+  const size_t ns = (size_t)c->dmap.n_sites;
+  EG_CUDA(cudaSetDevice(c->device));
+  if (prefix_score)
+    EG_CUDA(cudaMemcpyAsync(prefix_score, c->d_prefix + ((size_t)rclass * EG_NY + year_index) * ns, ns * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (static_score_sorted)
+    EG_CUDA(cudaMemcpyAsync(static_score_sorted, c->d_static_sorted + ((size_t)pclass * EG_NY + year_index) * ns, ns * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  std::vector<uint16_t> tmp;
+  if (order_sorted) {
+    tmp.resize(ns);
+    EG_CUDA(cudaMemcpyAsync(tmp.data(), c->d_order + ((size_t)pclass * EG_NY + year_index) * ns, ns * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+  }
+  EG_CUDA(cudaStreamSynchronize(c->stream));
+  if (order_sorted)
+    for (size_t i = 0; i < ns; i++) order_sorted[i] = tmp[i];
+  return EG_OK;
+}
+
+int eg_map_site_static(eg_ctx* c, double* coast_factor, double* site_opinion) {
+  if (!c) return eg_fail(EG_ERR_INVALID, "ctx is NULL");
+  if (!c->map_ready) return eg_fail(EG_ERR_STATE, "no map loaded");
+  const size_t ns = (size_t)c->dmap.n_sites;
+  EG_CUDA(cudaSetDevice(c->device));
+  if (coast_factor) EG_CUDA(cudaMemcpyAsync(coast_factor, c->d_coast, ns * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (site_opinion) EG_CUDA(cudaMemcpyAsync(site_opinion, c->d_site_opinion, ns * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  EG_CUDA(cudaStreamSynchronize(c->stream));
+  return EG_OK;
+}
+
+int eg_weights_upload(eg_ctx* c, const eg_weights* w) {
+  if (!c || !w) return eg_fail(EG_ERR_INVALID, "eg_weights_upload: NULL argument");
+  EG_CUDA(cudaSetDevice(c->device));
+  if (!c->d_policy) EG_CUDA(cudaMalloc((void**)&c->d_policy, sizeof(EgPolicyDevice)));
+  EgPolicyDevice pol;
+  eg_weights_fill_policy(*w, &pol);
+  // pageable source: the copy is staged before the call returns, so `pol` may go out of scope
+  EG_CUDA(cudaMemcpyAsync(c->d_policy, &pol, sizeof(pol), cudaMemcpyHostToDevice, c->stream));
+  EG_CUDA(cudaStreamSynchronize(c->stream));
+  c->policy_ready = true;
+  return EG_OK;
+}
+
+int eg_rollout_batch_device(eg_ctx* c, const eg_run_cfg* cfg, uint64_t seed, uint64_t first_episode, uint32_t n,
+                            eg_result* d_out, eg_traj* d_traj, eg_sites* d_sites, eg_yearly* d_yearly) {
+  int rc = check_cfg(c, cfg);
+  if (rc) return rc;
+  if (!c->policy_ready) return eg_fail(EG_ERR_STATE, "no weights uploaded: call eg_weights_upload first");
+  if (!d_out) return eg_fail(EG_ERR_INVALID, "eg_rollout_batch_device: d_out is NULL");
+  if (cfg->replay_best) return eg_fail(EG_ERR_INVALID, "replay_best=1 is not implemented on the device path yet");
+  EG_CUDA(cudaSetDevice(c->device));
+  EgEpisodeParams p = make_params(c, cfg, seed, first_episode, n);
+  p.out = d_out; p.traj = d_traj; p.sites = d_sites; p.yearly = d_yearly;
+  EG_CUDA(eg_launch_rollout(p, c->stream));
+  if (n) c->launches++;
+  return EG_OK;
+}
+
+int eg_rollout_batch(eg_ctx* c, const eg_weights* w, const eg_run_cfg* cfg, uint64_t seed, uint64_t first_episode,
+                     uint32_t n, eg_result* out, eg_traj* traj_out, eg_sites* sites_out, eg_yearly* yearly_out) {
+  int rc = check_cfg(c, cfg);
+  if (rc) return rc;
+  if (!w || !out) return eg_fail(EG_ERR_INVALID, "eg_rollout_batch: NULL argument");
+  if ((rc = eg_weights_upload(c, w))) return rc;
+  if ((rc = ensure_scratch(c, n, sites_out != nullptr, yearly_out != nullptr, false))) return rc;
+  rc = eg_rollout_batch_device(c, cfg, seed, first_episode, n, c->s_out, traj_out ? c->s_traj : nullptr,
+                               sites_out ? c->s_sites : nullptr, yearly_out ? c->s_yearly : nullptr);
+  if (rc) return rc;
+  EG_CUDA(cudaMemcpyAsync(out, c->s_out, (size_t)n * sizeof(eg_result), cudaMemcpyDeviceToHost, c->stream));
+  if (traj_out) EG_CUDA(cudaMemcpyAsync(traj_out, c->s_traj, (size_t)n * sizeof(eg_traj), cudaMemcpyDeviceToHost, c->stream));
+  if (sites_out) EG_CUDA(cudaMemcpyAsync(sites_out, c->s_sites, (size_t)n * sizeof(eg_sites), cudaMemcpyDeviceToHost, c->stream));
+  if (yearly_out) EG_CUDA(cudaMemcpyAsync(yearly_out, c->s_yearly, (size_t)n * sizeof(eg_yearly), cudaMemcpyDeviceToHost, c->stream));
+  EG_CUDA(cudaStreamSynchronize(c->stream));
+  return EG_OK;
+}
+
+int eg_replay_batch_device(eg_ctx* c, const eg_run_cfg* cfg, const eg_traj* d_in, uint32_t n, eg_result* d_out,
+                           eg_sites* d_sites, eg_yearly* d_yearly) {
+  int rc = check_cfg(c, cfg);
+  if (rc) return rc;
+  if (!d_in || !d_out) return eg_fail(EG_ERR_INVALID, "eg_replay_batch_device: NULL argument");
+  EG_CUDA(cudaSetDevice(c->device));
+  EgEpisodeParams p = make_params(c, cfg, 0, 0, n);
+  p.policy = nullptr;
+  p.replay_in = d_in;
+  p.out = d_out; p.traj = nullptr; p.sites = d_sites; p.yearly = d_yearly;
+  EG_CUDA(eg_launch_replay(p, c->stream));
+  if (n) c->launches++;
+  return EG_OK;
+}
+
+int eg_replay_batch(eg_ctx* c, const eg_run_cfg* cfg, const eg_traj* in, uint32_t n, eg_result* out, eg_sites* sites_out,
+                    eg_yearly* yearly_out) {
+  int rc = check_cfg(c, cfg);
+  if (rc) return rc;
+  if (!in || !out) return eg_fail(EG_ERR_INVALID, "eg_replay_batch: NULL argument");
+  if ((rc = ensure_scratch(c, n, sites_out != nullptr, yearly_out != nullptr, true))) return rc;
+  EG_CUDA(cudaMemcpyAsync(c->s_traj_in, in, (size_t)n * sizeof(eg_traj), cudaMemcpyHostToDevice, c->stream));
+  rc = eg_replay_batch_device(c, cfg, c->s_traj_in, n, c->s_out, sites_out ? c->s_sites : nullptr, yearly_out ? c->s_yearly : nullptr);
+  if (rc) return rc;
+  EG_CUDA(cudaMemcpyAsync(out, c->s_out, (size_t)n * sizeof(eg_result), cudaMemcpyDeviceToHost, c->stream));
+  if (sites_out) EG_CUDA(cudaMemcpyAsync(sites_out, c->s_sites, (size_t)n * sizeof(eg_sites), cudaMemcpyDeviceToHost, c->stream));
+  if (yearly_out) EG_CUDA(cudaMemcpyAsync(yearly_out, c->s_yearly, (size_t)n * sizeof(eg_yearly), cudaMemcpyDeviceToHost, c->stream));
+  EG_CUDA(cudaStreamSynchronize(c->stream));
+  return EG_OK;
+}
+
+int eg_update_stats_device(eg_ctx* c, const eg_weights* w, const eg_result* d_results, const eg_traj* d_trajs, uint32_t n,
+                           int64_t* d_stats, double* d_best_score, unsigned long long* d_best_index) {
+  if (!c || !w || !d_results || !d_trajs || !d_stats || !d_best_score || !d_best_index)
+    return eg_fail(EG_ERR_INVALID, "eg_update_stats_device: NULL argument");
+  if (!c->policy_ready) return eg_fail(EG_ERR_STATE, "no weights uploaded: call eg_weights_upload first");
+  EG_CUDA(cudaSetDevice(c->device));
+  EgStatsParams p{};
+  p.consts = eg_contrast_consts(*w);
+  p.policy = c->d_policy;
+  p.results = d_results; p.trajs = d_trajs; p.n = n;
+  p.stats = d_stats; p.best_score = d_best_score; p.best_index = d_best_index;
+  p.ln100 = std::log(50000000000.0 * 100.0 / 50000000000.0);
+  EG_CUDA(eg_launch_stats(p, c->stream));
+  if (n) c->launches++;
+  return EG_OK;
+}
+
+int eg_location_analysis(eg_ctx* c, int use_loaded_map, int32_t half_steps, double step, double* scores_out,
+                         uint32_t first_point, uint32_t n_points) {
+  if (!c || !scores_out) return eg_fail(EG_ERR_INVALID, "eg_location_analysis: NULL argument");
+  if (!c->map_ready) return eg_fail(EG_ERR_STATE, "no map loaded (the coastline polygon is needed)");
+  if (half_steps < 0 || half_steps > 1000) return eg_fail(EG_ERR_INVALID, "half_steps out of range");
+  const uint32_t side = (uint32_t)(2 * half_steps + 1);
+  if ((uint64_t)first_point + n_points > (uint64_t)side * side) return eg_fail(EG_ERR_INVALID, "point range exceeds the analysis grid");
+  EG_CUDA(cudaSetDevice(c->device));
+  double* d_scores = nullptr;
+  EG_CUDA(cudaMalloc((void**)&d_scores, std::max<size_t>((size_t)n_points * EG_NT, 1) * sizeof(double)));
+  EgSuitabilityParams p{};
+  p.half = half_steps; p.step = step; p.first = first_point; p.n = n_points;
+  p.n_settlements = use_loaded_map ? (int)c->hmap.sx.size() : 0;
+  p.sx = c->d_sx; p.sy = c->d_sy; p.pop = c->d_pop;  // pop[0][s] = 2025 populations
+  p.n_generators = use_loaded_map ? (int)c->hmap.ex.size() : 0;
+  p.gx = c->d_ex; p.gy = c->d_ey;
+  p.n_coast = (int)c->hmap.cx.size(); p.cx = c->d_cx; p.cy = c->d_cy;
+  p.scores = d_scores;
+  cudaError_t err = eg_launch_suitability(p, c->stream);
+  if (err == cudaSuccess && n_points) c->launches++;
+  if (err == cudaSuccess) err = cudaMemcpyAsync(scores_out, d_scores, (size_t)n_points * EG_NT * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
+  cudaFree(d_scores);
+  if (err != cudaSuccess) return eg_fail(EG_ERR_CUDA, cudaGetErrorString(err));
+  return EG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,28 @@
+// host_tables.hpp — host-side map (as loaded) and the small host-built tables.
+#pragma once
+#include <cstdint>
+#include <vector>
+#include "tables.h"
+
+struct EgHostMap {
+  std::vector<double> sx, sy;      // settlements, grid metres
+  std::vector<uint32_t> spop;      // 2025 population
+  std::vector<double> ex, ey, ecap;  // plants existing before the simulation
+  std::vector<uint8_t> etype;
+  std::vector<double> cx, cy;      // coastline polygon
+  int grid_n = 0;
+  double step = 0;
+};
+
+struct EgHostTables {
+  EgSmallTables small;
+  std::vector<double> op_cost;       // [EG_OPC_SIZE]
+  std::vector<uint32_t> pop;         // [26][S]
+  std::vector<double> near_factor;   // [6][kmax][kmax]
+  int kmax = 0;
+};
+
+int eg_host_map_load(EgHostMap* m, const char* settlements_json, const char* generators_csv, const char* coastline_json);
+int eg_host_map_set(EgHostMap* m, const eg_map_desc* d);
+int eg_host_map_validate(const EgHostMap& m);
+void eg_host_build_tables(const EgHostMap& m, EgHostTables* out);

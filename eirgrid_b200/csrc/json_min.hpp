@@ -1,0 +1,164 @@
+// json_min.hpp — minimal JSON reader/writer for the three files the path touches:
+// settlements.json, coastline_points.json (inputs of the reference's loaders) and the weights
+// checkpoints (SerializableWeights, ai/learning/serialization.rs:37-51). Host-only.
+#pragma once
+#include <cstdlib>
+#include <cstring>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <utility>
+#include <stdexcept>
+
+namespace egjson {
+
+struct Value {
+  enum Kind { Null, Bool, Number, String, Array, Object } kind = Null;
+  bool b = false;
+  double num = 0;
+  std::string str;
+  std::vector<Value> arr;
+  std::vector<std::pair<std::string, Value>> obj;
+
+  const Value* get(const char* key) const {
+    if (kind != Object) return nullptr;
+    for (const auto& kv : obj)
+      if (kv.first == key) return &kv.second;
+    return nullptr;
+  }
+  bool is_null() const { return kind == Null; }
+};
+
+class Parser {
+ public:
+  explicit Parser(const std::string& text) : s_(text), i_(0) {}
+  Value parse() {
+    Value v = value();
+    ws();
+    if (i_ != s_.size()) fail("trailing characters");
+    return v;
+  }
+
+ private:
+  const std::string& s_;
+  size_t i_;
+  [[noreturn]] void fail(const char* what) const {
+    throw std::runtime_error(std::string("JSON parse error at byte ") + std::to_string(i_) + ": " + what);
+  }
+  void ws() {
+    while (i_ < s_.size() && (s_[i_] == ' ' || s_[i_] == '\n' || s_[i_] == '\t' || s_[i_] == '\r')) i_++;
+  }
+  Value value() {
+    ws();
+    if (i_ >= s_.size()) fail("unexpected end");
+    char c = s_[i_];
+    Value v;
+    if (c == '{') {
+      v.kind = Value::Object;
+      i_++;
+      ws();
+      if (i_ < s_.size() && s_[i_] == '}') { i_++; return v; }
+      for (;;) {
+        ws();
+        if (i_ >= s_.size() || s_[i_] != '"') fail("expected key");
+        std::string k = string();
+        ws();
+        if (i_ >= s_.size() || s_[i_] != ':') fail("expected ':'");
+        i_++;
+        v.obj.emplace_back(std::move(k), value());
+        ws();
+        if (i_ < s_.size() && s_[i_] == ',') { i_++; continue; }
+        if (i_ < s_.size() && s_[i_] == '}') { i_++; break; }
+        fail("expected ',' or '}'");
+      }
+    } else if (c == '[') {
+      v.kind = Value::Array;
+      i_++;
+      ws();
+      if (i_ < s_.size() && s_[i_] == ']') { i_++; return v; }
+      for (;;) {
+        v.arr.push_back(value());
+        ws();
+        if (i_ < s_.size() && s_[i_] == ',') { i_++; continue; }
+        if (i_ < s_.size() && s_[i_] == ']') { i_++; break; }
+        fail("expected ',' or ']'");
+      }
+    } else if (c == '"') {
+      v.kind = Value::String;
+      v.str = string();
+    } else if (c == 't' && s_.compare(i_, 4, "true") == 0) {
+      v.kind = Value::Bool; v.b = true; i_ += 4;
+    } else if (c == 'f' && s_.compare(i_, 5, "false") == 0) {
+      v.kind = Value::Bool; v.b = false; i_ += 5;
+    } else if (c == 'n' && s_.compare(i_, 4, "null") == 0) {
+      i_ += 4;
+    } else {
+      const char* start = s_.c_str() + i_;
+      char* end = nullptr;
+      v.num = std::strtod(start, &end);  // correctly rounded
+      if (end == start) fail("expected value");
+      v.kind = Value::Number;
+      i_ += (size_t)(end - start);
+    }
+    return v;
+  }
+  std::string string() {
+    std::string out;
+    i_++;  // opening quote
+    while (i_ < s_.size() && s_[i_] != '"') {
+      char c = s_[i_++];
+      if (c == '\\') {
+        if (i_ >= s_.size()) fail("bad escape");
+        char e = s_[i_++];
+        switch (e) {
+          case 'n': out.push_back('\n'); break;
+          case 't': out.push_back('\t'); break;
+          case 'r': out.push_back('\r'); break;
+          case 'b': out.push_back('\b'); break;
+          case 'f': out.push_back('\f'); break;
+          case 'u': {
+            if (i_ + 4 > s_.size()) fail("bad \\u escape");
+            unsigned cp = (unsigned)std::strtoul(s_.substr(i_, 4).c_str(), nullptr, 16);
+            i_ += 4;
+            if (cp < 0x80) out.push_back((char)cp);
+            else if (cp < 0x800) { out.push_back((char)(0xC0 | (cp >> 6))); out.push_back((char)(0x80 | (cp & 0x3F))); }
+            else { out.push_back((char)(0xE0 | (cp >> 12))); out.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out.push_back((char)(0x80 | (cp & 0x3F))); }
+            break;
+          }
+          default: out.push_back(e); break;
+        }
+      } else {
+        out.push_back(c);
+      }
+    }
+    if (i_ >= s_.size()) fail("unterminated string");
+    i_++;  // closing quote
+    return out;
+  }
+};
+
+inline bool read_file(const char* path, std::string* out) {
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return false;
+  std::fseek(f, 0, SEEK_END);
+  long n = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  out->resize((size_t)(n > 0 ? n : 0));
+  size_t got = n > 0 ? std::fread(&(*out)[0], 1, (size_t)n, f) : 0;
+  std::fclose(f);
+  return got == (size_t)(n > 0 ? n : 0);
+}
+
+// shortest decimal text that parses back to exactly `v` (what serde_json's ryu output guarantees)
+inline std::string fmt_double(double v) {
+  char buf[40];
+  for (int prec = 1; prec <= 17; prec++) {
+    std::snprintf(buf, sizeof(buf), "%.*g", prec, v);
+    if (std::strtod(buf, nullptr) == v) break;
+  }
+  std::string s(buf);
+  if (s.find_first_of(".eEni") == std::string::npos) s += ".0";  // serde_json prints floats with a fraction
+  return s;
+}
+
+}  // namespace egjson

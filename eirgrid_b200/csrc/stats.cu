@@ -1,0 +1,120 @@
+// stats.cu — per-batch update statistics accumulated on the device (sm_100a).
+//
+// The reference applies apply_contrast_learning / apply_deficit_contrast_learning (weights/learning.rs:131-373)
+// one episode at a time under a write lock (core/multi_simulation.rs:494-508). For a batch sampled from one frozen
+// snapshot and sharded over GPUs, the per-episode effect on the weight table is summarised here as a small integer
+// table that ranks sum with one NCCL allreduce:
+//   header[0] episodes, header[1] episodes whose deterioration passed the contrast threshold
+//   per year: [0,61)    sum of ln(penalty_e)      over penalised occurrences of action k   (fixed point, 2^-24)
+//             [61,122)  sum of ln(mild_penalty_e) over mis-positioned occurrences of k      (fixed point)
+//             [122,183) occurrences of action k in current_run_actions
+//             [183,198) occurrences of deficit key k in current_deficit_actions
+// Integer sums make the result independent of the reduction order and of the number of GPUs.
+#include "stats.cuh"
+
+namespace {
+
+constexpr double kMaxAcceptableCost = 50000000000.0, kMaxAcceptableEmissions = 1000000.0;
+
+__device__ __forceinline__ double default_score(const eg_result& r, double ln100) {  // scoring.rs:18-44
+  if (r.net_emissions > 0.0) return 1.0 - fmin(r.net_emissions / kMaxAcceptableEmissions, 1.0);
+  const double normalized_cost = fmax(r.total_cost / kMaxAcceptableCost, 1.0);
+  const double cost_score = 1.0 - fmin(log(normalized_cost) / ln100, 1.0);
+  const double cost_weight = normalized_cost > 8.0 ? 0.8 : 0.5;
+  return 1.0 + (cost_score * cost_weight + r.public_opinion * (1.0 - cost_weight));
+}
+
+__device__ __forceinline__ int deficit_key_of_action(int code) {
+  if (code == EG_ACT_DO_NOTHING) return 14;
+  if (code >= 45 || code % 3) return -1;
+  switch (code / 3) {
+    case 8: return 0; case 7: return 1; case 12: return 2; case 11: return 3; case 9: return 4; case 0: return 5;
+    case 1: return 6; case 4: return 7; case 10: return 8; case 5: return 9; case 2: return 10; case 3: return 11;
+    case 13: return 12; case 14: return 13;
+  }
+  return -1;
+}
+
+__global__ void eg_stats_reset_kernel(double* best_score, unsigned long long* best_index) {
+  *best_score = -1.0;
+  *best_index = ~0ull;
+}
+
+__global__ void __launch_bounds__(256) eg_stats_kernel(const EgStatsParams p) {
+  __shared__ unsigned long long acc[EG_STATS_WORDS];
+  for (int i = threadIdx.x; i < EG_STATS_WORDS; i += blockDim.x) acc[i] = 0ull;
+  __syncthreads();
+  const uint32_t ep = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ep < p.n) {
+    const eg_result r = p.results[ep];
+    const eg_traj* t = p.trajs + ep;
+    const double score = default_score(r, p.ln100);
+    atomicMax((long long*)p.best_score, __double_as_longlong(score));  // scores are >= 0: bit order == value order
+    atomicAdd(&acc[0], 1ull);
+    bool pass = false;
+    long long log_pen = 0, log_mild = 0;
+    if (p.consts.has_best) {
+      const double det = p.consts.best_score > 0.0 ? (p.consts.best_score - score) / p.consts.best_score : 0.0;
+      pass = det > p.consts.threshold || p.consts.force;
+      if (pass) {
+        if (det < 0.0) {
+          // powf(negative, 0.3) is NaN and f64::max(NaN, MIN_WEIGHT) == MIN_WEIGHT (quirk Q9): collapse to the floor
+          log_pen = log_mild = -(1ll << 40);
+        } else {
+          const double combined = pow(det, 0.3) * p.consts.stagnation;
+          const double penalty = 1.0 / (1.0 + p.consts.alr * 1.5 * combined);
+          const double mild = 1.0 / (1.0 + p.consts.alr * combined * 0.5);
+          log_pen = llrint(log(penalty) * EG_STATS_FIXED_SCALE);
+          log_mild = llrint(log(mild) * EG_STATS_FIXED_SCALE);
+        }
+        atomicAdd(&acc[1], 1ull);
+      }
+    }
+    for (int y = 0; y < EG_NY; y++) {
+      unsigned long long* ys = acc + EG_STATS_HEADER + y * EG_STATS_YEAR_STRIDE;
+      const int nd = min((int)t->n_deficit[y], EG_MAX_ACTIONS_PER_YEAR);
+      const int na = min((int)t->n_additional[y], EG_MAX_ACTIONS_PER_YEAR - nd);
+      const int nrun = nd + na, ncur = nrun + nd;  // current_run_actions ++ current_deficit_actions
+      const int nb = p.policy->n_best[y], nbd = p.policy->n_best_deficit[y], nbest = nb + nbd;
+      for (int i = 0; i < ncur; i++) {
+        const int a = i < nrun ? t->actions[y][i] : t->actions[y][i - nrun];
+        if (i < nrun) atomicAdd(&ys[2 * EG_N_ACTIONS + a], 1ull);
+        else {
+          const int k = deficit_key_of_action(a);
+          if (k >= 0) atomicAdd(&ys[3 * EG_N_ACTIONS + k], 1ull);
+        }
+        if (!pass) continue;
+        bool in_best = false;
+        for (int b = 0; b < nb && !in_best; b++) in_best = p.policy->best[y][b] == a;
+        for (int b = 0; b < nbd && !in_best; b++) in_best = p.policy->best_deficit[y][b] == a;
+        if (!in_best) {
+          atomicAdd(&ys[a], (unsigned long long)log_pen);
+        } else if (i < nbest) {
+          const int bi = i < nb ? p.policy->best[y][i] : p.policy->best_deficit[y][i - nb];
+          if (bi != a) atomicAdd(&ys[EG_N_ACTIONS + a], (unsigned long long)log_mild);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < EG_STATS_WORDS; i += blockDim.x)
+    if (acc[i]) atomicAdd((unsigned long long*)&p.stats[i], acc[i]);
+}
+
+__global__ void __launch_bounds__(256) eg_stats_argbest_kernel(const EgStatsParams p) {
+  const uint32_t ep = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ep >= p.n) return;
+  const double score = default_score(p.results[ep], p.ln100);
+  if (score == *p.best_score) atomicMin(p.best_index, (unsigned long long)ep);
+}
+
+}  // namespace
+
+cudaError_t eg_launch_stats(const EgStatsParams& p, cudaStream_t stream) {
+  eg_stats_reset_kernel<<<1, 1, 0, stream>>>(p.best_score, p.best_index);
+  if (p.n == 0) return cudaGetLastError();
+  const uint32_t blocks = (p.n + 255) / 256;
+  eg_stats_kernel<<<blocks, 256, 0, stream>>>(p);
+  eg_stats_argbest_kernel<<<blocks, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}

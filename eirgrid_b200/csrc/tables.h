@@ -1,0 +1,88 @@
+// tables.h — layout of the static tables the episode kernels read (HBM-resident, built once per map).
+//
+// Everything that needs libm (pow/exp) is tabulated on the host from small integer arguments
+// (year offsets), so the device path needs only + - * / sqrt, which are IEEE-exact in CUDA when the
+// kernels are compiled with --fmad=false. That is what makes results bit-comparable with the
+// CPU restatement of the reference.
+#pragma once
+#include <stdint.h>
+#include "../../include/eirgrid_b200.h"
+
+#define EG_NY EG_N_YEARS
+#define EG_NT EG_N_GEN_TYPES
+#define EG_N_RCLASS 6   // placement penalty radii 3,5,6,7,8,12 km (gpu/metal_location_search.rs:139-146)
+#define EG_N_PCLASS 7   // (radius, needs-coast-factor) combinations that occur among the 15 types
+
+// generation accumulator a plant's output is added to (map_handler.rs:852-865)
+enum { EG_ACC_PLAIN = 0, EG_ACC_INTERMITTENT = 1, EG_ACC_STORAGE = 2 };
+
+struct EgYearRow {       // one per simulated year
+  double usage_total;    // calc_total_power_usage(year)                      map_handler.rs:819-827
+  double inflation;      // calc_inflation_factor(year)                       const_funcs.rs:13-15
+  double carbon_price;   // carbon_price(year)                                const_funcs.rs:186-203
+  // sequential accumulators after the existing plants (they come first in Map.generators)
+  double ex_gen[3];      // plain / intermittent / storage generation         map_handler.rs:852-865
+  double ex_co2;         // calc_total_co2_emissions prefix                   map_handler.rs:902-910
+  double ex_opinion_sum; // calculate_average_opinion prefix                  metrics_calculation.rs:7-30
+  uint32_t ex_active;    // active existing plants
+  uint32_t pop_total;    // calc_total_population                             map_handler.rs:813-817
+};
+
+struct EgSmallTables {   // ~35 KB, read-mostly, L1/L2 resident
+  EgYearRow year[EG_NY];
+  double net_mw[EG_NT];            // get_current_power_output of a new plant           generator.rs:523-554
+  double co2[EG_NT];               // get_co2_output of a new plant                     generator.rs:618-626
+  double loc_mod[EG_NT];           // location modifier used by get_current_cost        generator.rs:582-594
+  double mult[EG_N_MULTS];         // construction_cost_multiplier                      actions.rs:44-45
+  double base_cost[EG_NT][EG_NY];  // get_base_cost(build year)                         generator.rs:244-298
+  double tech[EG_NT][EG_NY];       // cost_evolution_rate^(year-2025)                   const_funcs.rs:33-34
+  double op_type[EG_NY][EG_NT];    // PUBLIC_OPINION_WEIGHT * calc_type_opinion         map_handler.rs:943-947
+  double off_amount[EG_N_OFFSET_TYPES];   // base_offset * capture_efficiency           carbon_offset.rs:212-232
+  double off_base_cost[EG_N_OFFSET_TYPES];
+  double maturity[EG_NY];          // clamp(1-exp(-0.1*d)) for d years since completion carbon_offset.rs:224-228
+  double size_factor;              // 1.0 - (size_penalty as f64 * 0.1)                 metal_location_search.rs:166
+  uint8_t acc_class[EG_NT];
+  uint8_t pclass[EG_NT];           // placement class of the type
+  uint8_t rclass_of_pclass[EG_N_PCLASS];
+  uint8_t water_of_pclass[EG_N_PCLASS];
+  uint8_t natural_offset[EG_N_OFFSET_TYPES];  // Forest/Wetland mature over time
+  uint8_t pad[3];
+};
+
+// CONSTRUCTION_COST_WEIGHT * calc_cost_opinion(get_current_cost(year), year), map_handler.rs:944-948
+// index [year][type][mult][build year]
+#define EG_OPC_INDEX(y, t, m, b) ((((y) * EG_NT + (t)) * EG_N_MULTS + (m)) * EG_NY + (b))
+#define EG_OPC_SIZE (EG_NY * EG_NT * EG_N_MULTS * EG_NY)
+
+struct EgDeviceMap {      // device pointers + sizes, passed by value to the kernels
+  const EgSmallTables* small;
+  const double* op_cost;          // [EG_OPC_SIZE]
+  const double* site_opinion;     // [n_sites] avg_settlement_opinion of a plant on the site  map_handler.rs:931-941
+  const double* coast_factor;     // [n_sites] 1/(1+min_coast_distance/5000)                  metal_location_search.rs:157-162
+  // placement lists, sorted by static score (descending, ties by scan order), per (pclass, year)
+  const uint16_t* order;          // [7][26][n_sites] site index
+  const double* static_score;     // [7][26][n_sites] score of the site when no simulation-built plant is in range
+  const double* prefix_score;     // [7][26][n_sites] score after settlements + existing plants (before new plants)
+  const double* near_factor;      // [6][kmax][kmax] distance/radius for cell offsets inside the radius, -1 outside
+  int n_sites;
+  int grid_n;
+  int kmax;
+};
+
+struct EgPolicyDevice {   // weights snapshot + the per-batch constants of update_weights (learning.rs:36-55)
+  double w[EG_NY][EG_N_ACTIONS];
+  double dw[EG_NY][EG_N_DEFICIT_KEYS];
+  double cw[EG_NY][EG_N_COUNT_KEYS];
+  double learning_rate;
+  double exploration_rate;
+  double relative_improvement;    // learning.rs:40-49 (0 whenever a best strategy with positive score exists)
+  uint32_t iwi;                   // iterations_without_improvement
+  uint32_t has_count_weights;
+  uint32_t noop_boost;            // learning.rs:82: best is net-zero but costs > 8 * MAX_ACCEPTABLE_COST
+  uint32_t has_best;
+  // best strategy for replay iterations (force_best_actions, sampling.rs:78-145,242-313)
+  uint8_t n_best[EG_NY];
+  uint8_t n_best_deficit[EG_NY];
+  uint8_t best[EG_NY][EG_MAX_ACTIONS_PER_YEAR * 2];
+  uint8_t best_deficit[EG_NY][EG_MAX_ACTIONS_PER_YEAR];
+};

@@ -1,0 +1,681 @@
+// weights.cpp — host side of the policy table: construction, JSON checkpoints, merge and the weight update.
+//
+// Replaces ActionWeights::new (ai/learning/weights/core.rs:25-250), save_to_file / load_from_file
+// (weights/serialization.rs:29-493, schema ai/learning/serialization.rs:37-51), update_weights_from
+// (weights/strategy.rs:281-311) and the write-lock section of the batch driver, core/multi_simulation.rs:494-508:
+// transfer_recorded_actions_from -> apply_contrast_learning -> update_best_strategy -> apply_deficit_contrast_learning
+// (weights/strategy.rs:313-342,19-258; weights/learning.rs:131-373).
+// HashMap<GridAction, f64> becomes a dense row in canonical key order (see include/eirgrid_b200.h).
+#include "weights.hpp"
+#include "json_min.hpp"
+#include "common.hpp"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <ctime>
+
+namespace {
+
+const double kMinWeight = 0.0001, kMaxWeight = 0.999;           // ai/learning/constants.rs:14-15
+const double kMaxCost = 50000000000.0, kMaxEmissions = 1000000.0;  // config/constants.rs:112-113
+
+const char* kGenNames[EG_NT] = {"OnshoreWind", "OffshoreWind", "DomesticSolar", "CommercialSolar", "UtilitySolar",
+                                "Nuclear", "CoalPlant", "GasCombinedCycle", "GasPeaker", "Biomass", "HydroDam",
+                                "PumpedStorage", "BatteryStorage", "TidalGenerator", "WaveEnergy"};
+const char* kOffsetNames[EG_N_OFFSET_TYPES] = {"Forest", "Wetland", "ActiveCapture", "CarbonCredit"};
+const int kMultPercent[EG_N_MULTS] = {100, 120, 150};
+const int kDeficitKeyType[14] = {8, 7, 12, 11, 9, 0, 1, 4, 10, 5, 2, 3, 13, 14};  // weights/core.rs:130-149
+
+int deficit_key_of_action(int code) {
+  if (code == EG_ACT_DO_NOTHING) return 14;
+  if (code < 45 && code % 3 == 0)
+    for (int k = 0; k < 14; k++)
+      if (kDeficitKeyType[k] == code / 3) return k;
+  return -1;
+}
+
+bool contains(const std::vector<uint8_t>& v, uint8_t a) { return std::find(v.begin(), v.end(), a) != v.end(); }
+
+// ---- JSON <-> action code ---------------------------------------------------------------------------------
+void write_action(std::string& o, int code, const std::string& ind) {
+  // SerializableAction, ai/actions/serializable_action.rs:6-13 (field order of the struct)
+  const char* type = "DoNothing";
+  std::string gen = "null", id = "null", pct = "null", off = "null", mult = "null";
+  if (code < 45) { type = "AddGenerator"; gen = std::string("\"") + kGenNames[code / 3] + "\""; mult = std::to_string(kMultPercent[code % 3]); }
+  else if (code < 57) { type = "AddCarbonOffset"; off = std::string("\"") + kOffsetNames[(code - 45) / 3] + "\""; mult = std::to_string(kMultPercent[(code - 45) % 3]); }
+  else if (code == EG_ACT_UPGRADE) { type = "UpgradeEfficiency"; id = "\"\""; }
+  else if (code == EG_ACT_ADJUST) { type = "AdjustOperation"; id = "\"\""; pct = "0"; }
+  else if (code == EG_ACT_CLOSE) { type = "CloseGenerator"; id = "\"\""; }
+  o += ind + "{\n";
+  o += ind + "  \"action_type\": \"" + type + "\",\n";
+  o += ind + "  \"generator_type\": " + gen + ",\n";
+  o += ind + "  \"generator_id\": " + id + ",\n";
+  o += ind + "  \"operation_percentage\": " + pct + ",\n";
+  o += ind + "  \"offset_type\": " + off + ",\n";
+  o += ind + "  \"cost_multiplier\": " + mult + "\n";
+  o += ind + "}";
+}
+
+// returns the action code or -1 for keys outside the closed key set (e.g. a 200 % multiplier)
+int read_action(const egjson::Value& v) {
+  const egjson::Value* type = v.get("action_type");
+  if (!type || type->kind != egjson::Value::String) return -1;
+  auto mult_index = [&]() {
+    const egjson::Value* m = v.get("cost_multiplier");
+    int pct = (m && m->kind == egjson::Value::Number) ? (int)m->num : 100;  // unwrap_or(DEFAULT_COST_MULTIPLIER)
+    for (int i = 0; i < EG_N_MULTS; i++)
+      if (kMultPercent[i] == pct) return i;
+    return -1;
+  };
+  if (type->str == "AddGenerator") {
+    const egjson::Value* g = v.get("generator_type");
+    int t = 8;  // GasPeaker when the type is missing (weights/serialization.rs:163)
+    if (g && g->kind == egjson::Value::String) {
+      t = -1;
+      for (int i = 0; i < EG_NT; i++)
+        if (g->str == kGenNames[i]) t = i;
+      if (t < 0) return -1;
+    }
+    int m = mult_index();
+    return m < 0 ? -1 : 3 * t + m;
+  }
+  if (type->str == "AddCarbonOffset") {
+    const egjson::Value* o = v.get("offset_type");
+    int ot = 0;  // Forest for unknown names (weights/serialization.rs:185)
+    if (o && o->kind == egjson::Value::String)
+      for (int i = 0; i < EG_N_OFFSET_TYPES; i++)
+        if (o->str == kOffsetNames[i]) ot = i;
+    int m = mult_index();
+    return m < 0 ? -1 : 45 + 3 * ot + m;
+  }
+  if (type->str == "UpgradeEfficiency") return EG_ACT_UPGRADE;
+  if (type->str == "AdjustOperation") return EG_ACT_ADJUST;
+  if (type->str == "CloseGenerator") return EG_ACT_CLOSE;
+  if (type->str == "DoNothing") return EG_ACT_DO_NOTHING;
+  return -2;  // unknown action type: load_from_file fails with InvalidData
+}
+
+void write_weight_map(std::string& o, const char* name, const double* rows, int n_keys, bool deficit, bool present) {
+  o += std::string("  \"") + name + "\": ";
+  if (!present) { o += "null"; return; }
+  o += "{\n";
+  for (int y = 0; y < EG_NY; y++) {
+    o += "    \"" + std::to_string(EG_BASE_YEAR + y) + "\": [\n";
+    for (int k = 0; k < n_keys; k++) {
+      int code = deficit ? (k < 14 ? 3 * kDeficitKeyType[k] : EG_ACT_DO_NOTHING) : k;
+      o += "      [\n";
+      write_action(o, code, "        ");
+      o += ",\n        " + egjson::fmt_double(rows[(size_t)y * n_keys + k]) + "\n      ]";
+      o += k + 1 < n_keys ? ",\n" : "\n";
+    }
+    o += y + 1 < EG_NY ? "    ],\n" : "    ]\n";
+  }
+  o += "  }";
+}
+
+void write_action_lists(std::string& o, const char* name, const std::vector<uint8_t>* lists, bool present) {
+  o += std::string("  \"") + name + "\": ";
+  if (!present) { o += "null"; return; }
+  o += "{\n";
+  for (int y = 0; y < EG_NY; y++) {
+    o += "    \"" + std::to_string(EG_BASE_YEAR + y) + "\": [";
+    if (!lists[y].empty()) {
+      o += "\n";
+      for (size_t i = 0; i < lists[y].size(); i++) {
+        write_action(o, lists[y][i], "      ");
+        o += i + 1 < lists[y].size() ? ",\n" : "\n";
+      }
+      o += "    ]";
+    } else {
+      o += "]";
+    }
+    o += y + 1 < EG_NY ? ",\n" : "\n";
+  }
+  o += "  }";
+}
+
+bool read_weight_map(const egjson::Value* v, double* rows, int n_keys, bool deficit, bool* any) {
+  if (!v || v->kind != egjson::Value::Object) return true;
+  for (const auto& kv : v->obj) {
+    int year = std::atoi(kv.first.c_str());
+    if (year < EG_BASE_YEAR || year > EG_END_YEAR || kv.second.kind != egjson::Value::Array) continue;
+    for (const egjson::Value& entry : kv.second.arr) {
+      if (entry.kind != egjson::Value::Array || entry.arr.size() != 2) continue;
+      int code = read_action(entry.arr[0]);
+      if (code == -2 && !deficit) return false;
+      if (code < 0) continue;
+      int k = deficit ? deficit_key_of_action(code) : code;
+      if (k < 0 || k >= n_keys) continue;
+      rows[(size_t)(year - EG_BASE_YEAR) * n_keys + k] = entry.arr[1].num;
+      if (any) *any = true;
+    }
+  }
+  return true;
+}
+
+void read_action_lists(const egjson::Value* v, std::vector<uint8_t>* lists) {
+  if (!v || v->kind != egjson::Value::Object) return;
+  for (const auto& kv : v->obj) {
+    int year = std::atoi(kv.first.c_str());
+    if (year < EG_BASE_YEAR || year > EG_END_YEAR || kv.second.kind != egjson::Value::Array) continue;
+    for (const egjson::Value& a : kv.second.arr) {
+      int code = read_action(a);
+      if (code >= 0) lists[year - EG_BASE_YEAR].push_back((uint8_t)code);
+    }
+  }
+}
+
+// the episode's recorded lists as the shared weights see them after transfer_recorded_actions_from
+struct Recorded {
+  std::vector<uint8_t> run[EG_NY], deficit[EG_NY];
+  void from_traj(const eg_traj& t, bool replay) {
+    for (int y = 0; y < EG_NY; y++) {
+      run[y].clear();
+      deficit[y].clear();
+      int nd = std::min<int>(t.n_deficit[y], EG_MAX_ACTIONS_PER_YEAR);
+      int na = std::min<int>(t.n_additional[y], EG_MAX_ACTIONS_PER_YEAR - nd);
+      // replay iterations record every sampled action twice (sampling.rs:97-99,262-264 + simulation.rs:197,406-409; quirk Q10)
+      for (int i = 0; i < nd; i++) {
+        run[y].push_back(t.actions[y][i]);
+        deficit[y].push_back(t.actions[y][i]);
+        if (replay && i < 4) deficit[y].push_back(t.actions[y][i]);
+      }
+      for (int i = nd; i < nd + na; i++) {
+        run[y].push_back(t.actions[y][i]);
+        if (replay) run[y].push_back(t.actions[y][i]);
+      }
+    }
+  }
+};
+
+struct UpdateRng {  // Philox4x32-10 stream for the randomisation branch (learning.rs:267-280,358-370)
+  uint32_t k0, k1, c0, draw;
+  double f64() {
+    uint32_t a0 = c0, a1 = 0u, a2 = draw++, a3 = 0x55504454u, x0 = k0, x1 = k1;  // counter = (iteration, 0, draw, "UPDT")
+    for (int r = 0; r < 10; r++) {
+      uint64_t p0 = (uint64_t)0xD2511F53u * a0, p1 = (uint64_t)0xCD9E8D57u * a2;
+      uint32_t n0 = (uint32_t)(p1 >> 32) ^ a1 ^ x0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ a3 ^ x1, n3 = (uint32_t)p0;
+      a0 = n0; a1 = n1; a2 = n2; a3 = n3;
+      x0 += 0x9E3779B9u; x1 += 0xBB67AE85u;
+    }
+    uint64_t u = (uint64_t)a0 | ((uint64_t)a1 << 32);
+    return (double)(u >> 11) * (1.0 / 9007199254740992.0);
+  }
+};
+
+void contrast(eg_weights& W, const Recorded& rec, const double metrics[4], UpdateRng* rng, uint32_t* applied) {  // learning.rs:131-283
+  if (!W.has_best) return;
+  const double best_score = eg_score_default(W.best_metrics);
+  const double current_score = eg_score_default(metrics);
+  const double deterioration = best_score > 0.0 ? (best_score - current_score) / best_score : 0.0;
+  const double iterations = (double)W.iwi;
+  const double threshold = 0.1 * std::max(std::exp(-iterations / 500.0), 0.00001 / 0.1);
+  const bool force = W.iwi > 800;
+  if (!(deterioration > threshold || force)) return;
+  if (applied) (*applied)++;
+  const double stagnation = 1.0 + (0.2 * std::pow((double)W.iwi / 10.0, 1.8));
+  const double combined = std::pow(deterioration, 0.3) * stagnation;
+  const double alr = W.learning_rate * (1.0 + 0.1 * (double)W.iwi);
+  const double penalty = 1.0 / (1.0 + alr * 1.5 * combined);
+  const double boost = 1.0 + (alr * 2.0 * stagnation);
+  for (int y = 0; y < EG_NY; y++) {
+    std::vector<uint8_t> cur = rec.run[y];
+    cur.insert(cur.end(), rec.deficit[y].begin(), rec.deficit[y].end());
+    std::vector<uint8_t> best = W.best_actions[y];
+    best.insert(best.end(), W.best_deficit_actions[y].begin(), W.best_deficit_actions[y].end());
+    double* row = W.w[y];
+    for (uint8_t a : best) row[a] = std::min(row[a] * boost, kMaxWeight);
+    for (size_t i = 0; i < cur.size(); i++) {
+      const uint8_t a = cur[i];
+      if (!contains(best, a)) {
+        row[a] = std::fmax(row[a] * penalty, kMinWeight);  // NaN penalty collapses to MIN_WEIGHT like f64::max (quirk Q9)
+      } else if (i < best.size() && a != best[i]) {
+        const double mild = 1.0 / (1.0 + alr * combined * 0.5);
+        row[a] = std::fmax(row[a] * mild, kMinWeight);
+      }
+    }
+  }
+  if (W.iwi > 1200 && rng)
+    for (int y = 0; y < EG_NY; y++)
+      for (int k = 0; k < EG_N_ACTIONS; k++) {
+        const double f = 1.0 + 0.25 * (rng->f64() * 2.0 - 1.0);
+        W.w[y][k] = std::min(std::max(W.w[y][k] * f, kMinWeight), kMaxWeight);
+      }
+}
+
+std::string now_string() {
+  char buf[32];
+  std::time_t t = std::time(nullptr);
+  std::tm tmv;
+  localtime_r(&t, &tmv);
+  std::strftime(buf, sizeof(buf), "%Y-%m-%d %H:%M:%S", &tmv);
+  return buf;
+}
+
+bool best_strategy(eg_weights& W, const Recorded& rec, const double metrics[4]) {  // strategy.rs:19-258
+  const double current_score = eg_score_default(metrics);
+  W.iteration_count += 1;
+  const bool should_update = !W.has_best || current_score > eg_score_default(W.best_metrics);
+  if (should_update) {
+    W.history.push_back({W.iteration_count, current_score, metrics[0], metrics[2], metrics[1], metrics[3], now_string()});
+    std::memcpy(W.best_metrics, metrics, sizeof(W.best_metrics));
+    W.has_best = true;
+    W.best_weights.assign(&W.w[0][0], &W.w[0][0] + EG_NY * EG_N_ACTIONS);
+    for (int y = 0; y < EG_NY; y++) {
+      W.best_actions[y] = rec.run[y];
+      W.best_deficit_actions[y] = rec.deficit[y];
+    }
+    W.iwi = 0;
+  } else {
+    W.iwi += 1;
+  }
+  return should_update;
+}
+
+void deficit_contrast(eg_weights& W, const Recorded& rec, UpdateRng* rng) {  // learning.rs:285-373
+  if (!W.has_best) return;
+  const double deterioration = (double)W.iwi / 10.0;
+  const double threshold = 0.05 * std::max(std::exp(-(double)W.iwi / 400.0), 0.00001 / 0.05);
+  const bool force = W.iwi > 800;
+  if (!(deterioration > threshold || force)) return;
+  const double stagnation = 1.0 + (0.2 * std::pow((double)W.iwi / 10.0, 1.8));
+  const double combined = std::pow(deterioration, 0.3) * stagnation;
+  const double alr = W.learning_rate * (1.0 + 0.1 * (double)W.iwi);
+  const double penalty = 1.0 / (1.0 + alr * 1.5 * combined);
+  const double boost = 1.0 + (alr * 2.0 * stagnation * 1.5);
+  for (int y = 0; y < EG_NY; y++) {
+    const std::vector<uint8_t>& best = W.best_deficit_actions[y];
+    double* row = W.dw[y];
+    for (uint8_t a : best) {
+      int k = deficit_key_of_action(a);
+      if (k >= 0) row[k] = std::min(row[k] * boost, kMaxWeight);
+    }
+    for (uint8_t a : rec.deficit[y])
+      if (!contains(best, a)) {
+        int k = deficit_key_of_action(a);
+        if (k >= 0) row[k] = std::fmax(row[k] * penalty, kMinWeight);
+      }
+  }
+  if (W.iwi > 1200 && rng)
+    for (int y = 0; y < EG_NY; y++)
+      for (int k = 0; k < EG_N_DEFICIT_KEYS; k++) {
+        const double f = 1.0 + 0.25 * (rng->f64() * 2.0 - 1.0);
+        W.dw[y][k] = std::min(std::max(W.dw[y][k] * f, kMinWeight), kMaxWeight);
+      }
+}
+
+}  // namespace
+
+double eg_score(const double m[4], bool cost_only) {  // ai/metrics/scoring.rs:5-45
+  const double normalized_cost = std::max(m[2] / kMaxCost, 1.0);
+  const double log_cost = std::log(normalized_cost);
+  const double max_expected_log_cost = std::log(kMaxCost * 100.0 / kMaxCost);
+  if (cost_only) return 2.0 - std::min(log_cost / max_expected_log_cost, 1.0);
+  if (m[0] > 0.0) return 1.0 - std::min(m[0] / kMaxEmissions, 1.0);
+  const double cost_score = 1.0 - std::min(log_cost / max_expected_log_cost, 1.0);
+  const double cost_weight = normalized_cost > 8.0 ? 0.8 : 0.5;
+  const double opinion_weight = 1.0 - cost_weight;
+  return 1.0 + (cost_score * cost_weight + m[1] * opinion_weight);
+}
+double eg_score_default(const double m[4]) { return eg_score(m, false); }
+
+eg_weights::eg_weights() {  // ActionWeights::new, weights/core.rs:25-250
+  static const double gw[EG_NT] = {0.08, 0.08, 0.05, 0.05, 0.08, 0.03, 0.04, 0.06, 0.02, 0.04, 0.06, 0.06, 0.07, 0.05, 0.05};
+  static const double dk[EG_N_DEFICIT_KEYS] = {0.15, 0.15, 0.15, 0.10, 0.10, 0.07, 0.07, 0.06, 0.06, 0.05, 0.01, 0.01, 0.01, 0.01, 0.001};
+  for (int y = 0; y < EG_NY; y++) {
+    for (int t = 0; t < EG_NT; t++) {
+      w[y][3 * t] = gw[t];
+      w[y][3 * t + 1] = gw[t] * 0.5;
+      w[y][3 * t + 2] = gw[t] * 0.25;
+    }
+    for (int o = 0; o < EG_N_OFFSET_TYPES; o++) {
+      w[y][45 + 3 * o] = 0.02;
+      w[y][45 + 3 * o + 1] = 0.02 * 0.5;
+      w[y][45 + 3 * o + 2] = 0.02 * 0.25;
+    }
+    w[y][EG_ACT_UPGRADE] = 0.04;
+    w[y][EG_ACT_ADJUST] = 0.04;
+    w[y][EG_ACT_CLOSE] = 0.02;
+    w[y][EG_ACT_DO_NOTHING] = 0.1;
+    for (int k = 0; k < EG_N_DEFICIT_KEYS; k++) dw[y][k] = dk[k];
+    double total = 0.0;
+    for (int c = 0; c < EG_N_COUNT_KEYS; c++) {
+      const double base = std::exp(-0.8 * (double)c);
+      const double bias = c == 0 ? 4.0 : c == 1 ? 3.5 : c == 2 ? 3.0 : c == 3 ? 2.5 : c == 4 ? 2.0 : c == 5 ? 1.5 : 1.0;
+      cw[y][c] = base * bias;
+      total += cw[y][c];
+    }
+    for (int c = 0; c < EG_N_COUNT_KEYS; c++) cw[y][c] /= total;
+  }
+}
+
+void eg_weights_fill_policy(const eg_weights& W, EgPolicyDevice* out) {
+  std::memset(out, 0, sizeof(*out));
+  std::memcpy(out->w, W.w, sizeof(W.w));
+  std::memcpy(out->dw, W.dw, sizeof(W.dw));
+  std::memcpy(out->cw, W.cw, sizeof(W.cw));
+  out->learning_rate = W.learning_rate;
+  out->exploration_rate = W.exploration_rate;
+  // update_weights (learning.rs:36-49): final_impact_score and best_score are both score(best_metrics)
+  double rel = 0.0;
+  if (W.has_best) {
+    const double best_score = eg_score(W.best_metrics, !W.optimization_mode.empty() && W.optimization_mode == "cost_only");
+    rel = best_score > 0.0 ? (best_score - best_score) / best_score : best_score;
+  }
+  out->relative_improvement = rel;
+  out->iwi = W.iwi;
+  out->has_count_weights = W.has_count_weights ? 1 : 0;
+  out->noop_boost = (W.has_best && W.best_metrics[0] <= 0.0 && W.best_metrics[2] > kMaxCost * 8.0) ? 1 : 0;
+  out->has_best = W.has_best ? 1 : 0;
+  for (int y = 0; y < EG_NY; y++) {
+    out->n_best[y] = (uint8_t)std::min<size_t>(W.best_actions[y].size(), EG_MAX_ACTIONS_PER_YEAR * 2);
+    for (int i = 0; i < out->n_best[y]; i++) out->best[y][i] = W.best_actions[y][i];
+    out->n_best_deficit[y] = (uint8_t)std::min<size_t>(W.best_deficit_actions[y].size(), EG_MAX_ACTIONS_PER_YEAR);
+    for (int i = 0; i < out->n_best_deficit[y]; i++) out->best_deficit[y][i] = W.best_deficit_actions[y][i];
+  }
+}
+
+EgContrastConsts eg_contrast_consts(const eg_weights& W) {
+  EgContrastConsts c;
+  c.has_best = W.has_best ? 1 : 0;
+  c.force = W.iwi > 800 ? 1 : 0;
+  c.best_score = W.has_best ? eg_score_default(W.best_metrics) : 0.0;
+  c.threshold = 0.1 * std::max(std::exp(-(double)W.iwi / 500.0), 0.00001 / 0.1);
+  c.stagnation = 1.0 + (0.2 * std::pow((double)W.iwi / 10.0, 1.8));
+  c.alr = W.learning_rate * (1.0 + 0.1 * (double)W.iwi);
+  c.boost = 1.0 + (c.alr * 2.0 * c.stagnation);
+  return c;
+}
+
+extern "C" {
+
+uint8_t eg_deficit_key_action(uint32_t k) { return k < 14 ? (uint8_t)(3 * kDeficitKeyType[k]) : (uint8_t)EG_ACT_DO_NOTHING; }
+
+int eg_weights_new(eg_weights** out) {
+  if (!out) return eg_fail(EG_ERR_INVALID, "eg_weights_new: out is NULL");
+  *out = new eg_weights();
+  return EG_OK;
+}
+void eg_weights_free(eg_weights* w) { delete w; }
+int eg_weights_clone(const eg_weights* src, eg_weights** out) {
+  if (!src || !out) return eg_fail(EG_ERR_INVALID, "eg_weights_clone: NULL argument");
+  *out = new eg_weights(*src);
+  return EG_OK;
+}
+
+int eg_weights_get_table(const eg_weights* w, eg_weights_table* t) {
+  if (!w || !t) return eg_fail(EG_ERR_INVALID, "eg_weights_get_table: NULL argument");
+  std::memset(t, 0, sizeof(*t));
+  std::memcpy(t->weights, w->w, sizeof(w->w));
+  std::memcpy(t->deficit_weights, w->dw, sizeof(w->dw));
+  std::memcpy(t->count_weights, w->cw, sizeof(w->cw));
+  t->learning_rate = w->learning_rate;
+  t->exploration_rate = w->exploration_rate;
+  std::memcpy(t->best_metrics, w->best_metrics, sizeof(t->best_metrics));
+  t->has_count_weights = w->has_count_weights;
+  t->has_best = w->has_best;
+  t->iteration_count = w->iteration_count;
+  t->iterations_without_improvement = w->iwi;
+  return EG_OK;
+}
+int eg_weights_set_table(eg_weights* w, const eg_weights_table* t) {
+  if (!w || !t) return eg_fail(EG_ERR_INVALID, "eg_weights_set_table: NULL argument");
+  std::memcpy(w->w, t->weights, sizeof(w->w));
+  std::memcpy(w->dw, t->deficit_weights, sizeof(w->dw));
+  std::memcpy(w->cw, t->count_weights, sizeof(w->cw));
+  w->learning_rate = t->learning_rate;
+  w->exploration_rate = t->exploration_rate;
+  w->has_count_weights = t->has_count_weights != 0;
+  w->iteration_count = t->iteration_count;
+  w->iwi = t->iterations_without_improvement;
+  return EG_OK;
+}
+int eg_weights_get_best(const eg_weights* w, uint8_t n_best[EG_N_YEARS], uint8_t best[EG_N_YEARS][EG_MAX_ACTIONS_PER_YEAR * 2],
+                        uint8_t n_best_deficit[EG_N_YEARS], uint8_t best_deficit[EG_N_YEARS][EG_MAX_ACTIONS_PER_YEAR]) {
+  if (!w) return eg_fail(EG_ERR_INVALID, "eg_weights_get_best: NULL argument");
+  for (int y = 0; y < EG_NY; y++) {
+    n_best[y] = (uint8_t)std::min<size_t>(w->best_actions[y].size(), EG_MAX_ACTIONS_PER_YEAR * 2);
+    for (int i = 0; i < n_best[y]; i++) best[y][i] = w->best_actions[y][i];
+    n_best_deficit[y] = (uint8_t)std::min<size_t>(w->best_deficit_actions[y].size(), EG_MAX_ACTIONS_PER_YEAR);
+    for (int i = 0; i < n_best_deficit[y]; i++) best_deficit[y][i] = w->best_deficit_actions[y][i];
+  }
+  return w->has_best ? 1 : 0;
+}
+
+int eg_weights_save_json(const eg_weights* w, const char* path) {  // save_to_file, weights/serialization.rs:29-139
+  if (!w || !path) return eg_fail(EG_ERR_INVALID, "eg_weights_save_json: NULL argument");
+  std::string o = "{\n";
+  write_weight_map(o, "weights", &w->w[0][0], EG_N_ACTIONS, false, true);
+  o += ",\n  \"learning_rate\": " + egjson::fmt_double(w->learning_rate) + ",\n";
+  if (w->has_best) {
+    o += "  \"best_metrics\": {\n";
+    o += "    \"final_net_emissions\": " + egjson::fmt_double(w->best_metrics[0]) + ",\n";
+    o += "    \"average_public_opinion\": " + egjson::fmt_double(w->best_metrics[1]) + ",\n";
+    o += "    \"total_cost\": " + egjson::fmt_double(w->best_metrics[2]) + ",\n";
+    o += "    \"power_reliability\": " + egjson::fmt_double(w->best_metrics[3]) + "\n  },\n";
+  } else {
+    o += "  \"best_metrics\": null,\n";
+  }
+  write_weight_map(o, "best_weights", w->best_weights.data(), EG_N_ACTIONS, false, w->has_best && !w->best_weights.empty());
+  o += ",\n";
+  write_action_lists(o, "best_actions", w->best_actions, w->has_best);
+  o += ",\n  \"iteration_count\": " + std::to_string(w->iteration_count) + ",\n";
+  o += "  \"iterations_without_improvement\": " + std::to_string(w->iwi) + ",\n";
+  o += "  \"exploration_rate\": " + egjson::fmt_double(w->exploration_rate) + ",\n";
+  write_weight_map(o, "deficit_weights", &w->dw[0][0], EG_N_DEFICIT_KEYS, true, true);
+  o += ",\n";
+  write_action_lists(o, "best_deficit_actions", w->best_deficit_actions, w->has_best);
+  o += ",\n  \"optimization_mode\": " + (w->optimization_mode.empty() ? std::string("null") : "\"" + w->optimization_mode + "\"") + ",\n";
+  if (w->history.empty()) {
+    o += "  \"improvement_history\": null\n";
+  } else {
+    o += "  \"improvement_history\": [\n";
+    for (size_t i = 0; i < w->history.size(); i++) {
+      const EgImprovement& h = w->history[i];
+      o += "    {\n      \"iteration\": " + std::to_string(h.iteration) + ",\n";
+      o += "      \"score\": " + egjson::fmt_double(h.score) + ",\n";
+      o += "      \"net_emissions\": " + egjson::fmt_double(h.net_emissions) + ",\n";
+      o += "      \"total_cost\": " + egjson::fmt_double(h.total_cost) + ",\n";
+      o += "      \"public_opinion\": " + egjson::fmt_double(h.public_opinion) + ",\n";
+      o += "      \"power_reliability\": " + egjson::fmt_double(h.power_reliability) + ",\n";
+      o += "      \"timestamp\": \"" + h.timestamp + "\"\n    }";
+      o += i + 1 < w->history.size() ? ",\n" : "\n";
+    }
+    o += "  ]\n";
+  }
+  o += "}";
+  std::string tmp = std::string(path) + ".tmp";
+  FILE* f = std::fopen(tmp.c_str(), "wb");
+  if (!f) return eg_fail(EG_ERR_IO, std::string("cannot write ") + path);
+  size_t n = std::fwrite(o.data(), 1, o.size(), f);
+  std::fclose(f);
+  if (n != o.size() || std::rename(tmp.c_str(), path) != 0) return eg_fail(EG_ERR_IO, std::string("cannot write ") + path);
+  return EG_OK;
+}
+
+int eg_weights_load_json(const char* path, eg_weights** out) {  // load_from_file, weights/serialization.rs:141-493
+  if (!path || !out) return eg_fail(EG_ERR_INVALID, "eg_weights_load_json: NULL argument");
+  std::string text;
+  if (!egjson::read_file(path, &text)) return eg_fail(EG_ERR_IO, std::string("cannot read ") + path);
+  egjson::Value root;
+  try {
+    root = egjson::Parser(text).parse();
+  } catch (const std::exception& ex) {
+    return eg_fail(EG_ERR_IO, std::string(path) + ": " + ex.what());
+  }
+  if (root.kind != egjson::Value::Object || !root.get("weights")) return eg_fail(EG_ERR_IO, std::string(path) + ": not a weights file");
+  eg_weights* W = new eg_weights();
+  if (!read_weight_map(root.get("weights"), &W->w[0][0], EG_N_ACTIONS, false, nullptr)) {
+    delete W;
+    return eg_fail(EG_ERR_IO, std::string(path) + ": unknown action type");
+  }
+  // deficit weights default to the initial table when the file has none (weights/serialization.rs:266-283)
+  read_weight_map(root.get("deficit_weights"), &W->dw[0][0], EG_N_DEFICIT_KEYS, true, nullptr);
+  if (const egjson::Value* v = root.get("learning_rate")) W->learning_rate = v->num;
+  if (const egjson::Value* v = root.get("exploration_rate")) W->exploration_rate = v->num;
+  if (const egjson::Value* v = root.get("iteration_count")) W->iteration_count = (uint32_t)v->num;
+  if (const egjson::Value* v = root.get("iterations_without_improvement")) W->iwi = (uint32_t)v->num;
+  if (const egjson::Value* v = root.get("optimization_mode"))
+    if (v->kind == egjson::Value::String) W->optimization_mode = v->str;
+  const egjson::Value* bm = root.get("best_metrics");
+  if (bm && bm->kind == egjson::Value::Object) {
+    W->has_best = true;
+    if (const egjson::Value* v = bm->get("final_net_emissions")) W->best_metrics[0] = v->num;
+    if (const egjson::Value* v = bm->get("average_public_opinion")) W->best_metrics[1] = v->num;
+    if (const egjson::Value* v = bm->get("total_cost")) W->best_metrics[2] = v->num;
+    if (const egjson::Value* v = bm->get("power_reliability")) W->best_metrics[3] = v->num;
+    W->best_weights.assign(&W->w[0][0], &W->w[0][0] + EG_NY * EG_N_ACTIONS);
+    // unknown keys are skipped here instead of failing (weights/serialization.rs:286-360)
+    const egjson::Value* bw = root.get("best_weights");
+    if (bw && bw->kind == egjson::Value::Object)
+      for (const auto& kv : bw->obj) {
+        int year = std::atoi(kv.first.c_str());
+        if (year < EG_BASE_YEAR || year > EG_END_YEAR || kv.second.kind != egjson::Value::Array) continue;
+        for (const egjson::Value& entry : kv.second.arr) {
+          if (entry.kind != egjson::Value::Array || entry.arr.size() != 2) continue;
+          int code = read_action(entry.arr[0]);
+          if (code >= 0) W->best_weights[(size_t)(year - EG_BASE_YEAR) * EG_N_ACTIONS + code] = entry.arr[1].num;
+        }
+      }
+    read_action_lists(root.get("best_actions"), W->best_actions);
+    read_action_lists(root.get("best_deficit_actions"), W->best_deficit_actions);
+  }
+  const egjson::Value* hist = root.get("improvement_history");
+  if (hist && hist->kind == egjson::Value::Array)
+    for (const egjson::Value& h : hist->arr) {
+      EgImprovement r{};
+      if (const egjson::Value* v = h.get("iteration")) r.iteration = (uint32_t)v->num;
+      if (const egjson::Value* v = h.get("score")) r.score = v->num;
+      if (const egjson::Value* v = h.get("net_emissions")) r.net_emissions = v->num;
+      if (const egjson::Value* v = h.get("total_cost")) r.total_cost = v->num;
+      if (const egjson::Value* v = h.get("public_opinion")) r.public_opinion = v->num;
+      if (const egjson::Value* v = h.get("power_reliability")) r.power_reliability = v->num;
+      if (const egjson::Value* v = h.get("timestamp")) r.timestamp = v->str;
+      W->history.push_back(r);
+    }
+  // action_count_weights are not part of the file: empty after load -> heuristic count sampler
+  // (weights/serialization.rs:474, sampling.rs:423-442)
+  W->has_count_weights = false;
+  *out = W;
+  return EG_OK;
+}
+
+int eg_weights_merge(eg_weights* dst, const eg_weights* other) {  // update_weights_from, strategy.rs:281-311
+  if (!dst || !other) return eg_fail(EG_ERR_INVALID, "eg_weights_merge: NULL argument");
+  std::memcpy(dst->w, other->w, sizeof(dst->w));
+  std::memcpy(dst->dw, other->dw, sizeof(dst->dw));
+  if (other->has_count_weights) {
+    std::memcpy(dst->cw, other->cw, sizeof(dst->cw));
+    dst->has_count_weights = true;
+  }
+  dst->iteration_count = std::max(dst->iteration_count, other->iteration_count);
+  return EG_OK;
+}
+
+int eg_update(eg_weights* w, const eg_result* results, const eg_traj* trajs, uint32_t n, uint32_t replay_best,
+              uint64_t rng_seed, eg_update_stats* stats_out) {
+  if (!w || (n && (!results || !trajs))) return eg_fail(EG_ERR_INVALID, "eg_update: NULL argument");
+  eg_update_stats st;
+  std::memset(&st, 0, sizeof(st));
+  st.n_episodes = n;
+  st.batch_best_episode = -1;
+  Recorded rec;
+  for (uint32_t i = 0; i < n; i++) {
+    const double m[4] = {results[i].net_emissions, results[i].public_opinion, results[i].total_cost, results[i].power_reliability};
+    rec.from_traj(trajs[i], replay_best != 0);              // transfer_recorded_actions_from
+    UpdateRng rng{(uint32_t)rng_seed, (uint32_t)(rng_seed >> 32), w->iteration_count, 0};
+    contrast(*w, rec, m, &rng, &st.n_contrast_applied);    // apply_contrast_learning
+    if (best_strategy(*w, rec, m)) st.n_improvements++;    // update_best_strategy
+    deficit_contrast(*w, rec, &rng);                       // apply_deficit_contrast_learning
+    const double sc = eg_score_default(m);
+    if (st.batch_best_episode < 0 || sc > st.batch_best_score) { st.batch_best_score = sc; st.batch_best_episode = i; }
+  }
+  st.iterations_without_improvement = w->iwi;
+  st.best_score = w->has_best ? eg_score_default(w->best_metrics) : 0.0;
+  if (stats_out) *stats_out = st;
+  return EG_OK;
+}
+
+// Batch-synchronous rule: the statistics were accumulated against the snapshot `w` (frozen
+// best strategy and iterations_without_improvement) by eg_update_stats_device and summed over ranks.
+int eg_update_apply_stats(eg_weights* w, const int64_t* stats, uint64_t n_total, const eg_result* best_result,
+                          const eg_traj* best_traj, int64_t best_index, eg_update_stats* stats_out) {
+  if (!w || !stats) return eg_fail(EG_ERR_INVALID, "eg_update_apply_stats: NULL argument");
+  eg_update_stats st;
+  std::memset(&st, 0, sizeof(st));
+  st.n_episodes = (uint32_t)n_total;
+  st.batch_best_episode = best_index;
+  const EgContrastConsts c = eg_contrast_consts(*w);
+  const int64_t n_pass = stats[1];
+  st.n_contrast_applied = (uint32_t)n_pass;
+  if (w->has_best && n_pass > 0) {
+    for (int y = 0; y < EG_NY; y++) {
+      const int64_t* ys = stats + EG_STATS_HEADER + (size_t)y * EG_STATS_YEAR_STRIDE;
+      int occ[EG_N_ACTIONS] = {0};
+      for (uint8_t a : w->best_actions[y]) occ[a]++;
+      for (uint8_t a : w->best_deficit_actions[y]) occ[a]++;
+      for (int k = 0; k < EG_N_ACTIONS; k++) {
+        double v = w->w[y][k];
+        if (occ[k]) v = std::min(v * std::pow(c.boost, (double)n_pass * (double)occ[k]), kMaxWeight);
+        const double lg = ((double)ys[k] + (double)ys[EG_N_ACTIONS + k]) / EG_STATS_FIXED_SCALE;
+        if (lg != 0.0) v = std::fmax(v * std::exp(lg), kMinWeight);
+        w->w[y][k] = v;
+      }
+    }
+  }
+  // best bookkeeping with the batch winner
+  bool improved = false;
+  if (best_result && best_traj && n_total > 0) {
+    const double m[4] = {best_result->net_emissions, best_result->public_opinion, best_result->total_cost, best_result->power_reliability};
+    const double sc = eg_score_default(m);
+    st.batch_best_score = sc;
+    improved = !w->has_best || sc > eg_score_default(w->best_metrics);
+    if (improved) {
+      Recorded rec;
+      rec.from_traj(*best_traj, false);
+      w->history.push_back({w->iteration_count + (uint32_t)best_index + 1, sc, m[0], m[2], m[1], m[3], now_string()});
+      std::memcpy(w->best_metrics, m, sizeof(w->best_metrics));
+      w->has_best = true;
+      w->best_weights.assign(&w->w[0][0], &w->w[0][0] + EG_NY * EG_N_ACTIONS);
+      for (int y = 0; y < EG_NY; y++) {
+        w->best_actions[y] = rec.run[y];
+        w->best_deficit_actions[y] = rec.deficit[y];
+      }
+      st.n_improvements = 1;
+    }
+  }
+  w->iteration_count += (uint32_t)n_total;
+  w->iwi = improved ? (uint32_t)(n_total - 1 - (uint64_t)best_index) : w->iwi + (uint32_t)n_total;
+  // deficit contrast against the (possibly new) best, with the post-update stagnation counter
+  if (w->has_best) {
+    const double deterioration = (double)w->iwi / 10.0;
+    const double threshold = 0.05 * std::max(std::exp(-(double)w->iwi / 400.0), 0.00001 / 0.05);
+    if (deterioration > threshold || w->iwi > 800) {
+      const double stagnation = 1.0 + (0.2 * std::pow((double)w->iwi / 10.0, 1.8));
+      const double combined = std::pow(deterioration, 0.3) * stagnation;
+      const double alr = w->learning_rate * (1.0 + 0.1 * (double)w->iwi);
+      const double penalty = 1.0 / (1.0 + alr * 1.5 * combined);
+      const double boost = 1.0 + (alr * 2.0 * stagnation * 1.5);
+      for (int y = 0; y < EG_NY; y++) {
+        const int64_t* hist = stats + EG_STATS_HEADER + (size_t)y * EG_STATS_YEAR_STRIDE + 3 * EG_N_ACTIONS;
+        int occ[EG_N_DEFICIT_KEYS] = {0};
+        for (uint8_t a : w->best_deficit_actions[y]) {
+          int k = deficit_key_of_action(a);
+          if (k >= 0) occ[k]++;
+        }
+        for (int k = 0; k < EG_N_DEFICIT_KEYS; k++) {
+          double v = w->dw[y][k];
+          if (occ[k]) v = std::min(v * std::pow(boost, (double)n_total * (double)occ[k]), kMaxWeight);
+          else if (hist[k] > 0) v = std::fmax(v * std::pow(penalty, (double)hist[k]), kMinWeight);
+          w->dw[y][k] = v;
+        }
+      }
+    }
+  }
+  st.iterations_without_improvement = w->iwi;
+  st.best_score = w->has_best ? eg_score_default(w->best_metrics) : 0.0;
+  if (stats_out) *stats_out = st;
+  return EG_OK;
+}
+
+}  // extern "C"

@@ -203,6 +203,9 @@ int eg_map_info(const eg_ctx* ctx, uint32_t out[4]);
 int eg_map_site_tables(eg_ctx* ctx, uint32_t year_index, uint32_t rclass, uint32_t pclass,
                        double* prefix_score, double* static_score_sorted, uint32_t* order_sorted);
 
+/* per-site static factors: 1/(1+min_coast_distance/5000) and the average settlement opinion of a plant on the site */
+int eg_map_site_static(eg_ctx* ctx, double* coast_factor, double* site_opinion);
+
 /* ---- policy table: replaces ActionWeights::new (weights/core.rs:25-250), load_from_file /
  * save_to_file (weights/serialization.rs:29-493), update_weights_from (strategy.rs:281-311) ------- */
 int eg_weights_new(eg_weights** out);
@@ -247,23 +250,24 @@ int eg_replay_batch_device(eg_ctx* ctx, const eg_run_cfg* cfg, const eg_traj* d_
 /* ---- weight update: replaces the write-lock section multi_simulation.rs:494-508
  * (transfer_recorded_actions_from → apply_contrast_learning → update_best_strategy →
  *  apply_deficit_contrast_learning; learning.rs:131-373, strategy.rs:19-258,313-342), applied for the
- * n episodes of a batch in episode-index order. HOST buffers. `rng_seed` feeds the randomisation
+ * n episodes of a batch in episode-index order. HOST buffers. `replay_best` = the batch ran with
+ * eg_run_cfg.replay_best (its doubled action records are rebuilt, quirk Q10); `rng_seed` feeds the randomisation
  * branch (iterations_without_improvement > 1200). */
 int eg_update(eg_weights* w, const eg_result* results, const eg_traj* trajs, uint32_t n,
-              uint64_t rng_seed, eg_update_stats* stats_out);
+              uint32_t replay_best, uint64_t rng_seed, eg_update_stats* stats_out);
 
 /* Batch-synchronous update for sharded episodes: statistics are accumulated on the
  * device by eg_update_stats_device into a table of EG_STATS_WORDS int64 words that the caller sums
  * across ranks (NCCL allreduce SUM), then eg_update_apply_stats applies the identical update on every
  * rank. `best_*` of the batch winner travel with the MAX-loc step done by the caller. */
 #define EG_STATS_WORDS (8 + EG_N_YEARS * (3 * EG_N_ACTIONS + EG_N_DEFICIT_KEYS))
-int eg_update_stats_device(eg_ctx* ctx, const eg_result* d_results, const eg_traj* d_trajs, uint32_t n,
+int eg_update_stats_device(eg_ctx* ctx, const eg_weights* w, const eg_result* d_results, const eg_traj* d_trajs, uint32_t n,
                            int64_t* d_stats /* EG_STATS_WORDS, accumulated (not cleared) */,
                            double* d_best_score /* [1] max score of the shard */,
                            unsigned long long* d_best_index /* [1] lowest index with that score */);
 int eg_update_apply_stats(eg_weights* w, const int64_t* stats, uint64_t n_total,
                           const eg_result* batch_best_result, const eg_traj* batch_best_traj,
-                          eg_update_stats* stats_out);
+                          int64_t batch_best_index, eg_update_stats* stats_out);
 
 /* ---- location suitability analysis (BASELINE config 5): replaces Map::analyze_locations →
  * LocationAnalysis::analyze_map (map_handler.rs:61-142) and calculate_generator_suitability
