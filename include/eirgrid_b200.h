@@ -63,8 +63,8 @@ typedef enum {
 #define EG_FLAG_OFFSET_OVERFLOW 2u  /* more than EG_MAX_OFFSETS offsets */
 #define EG_FLAG_YEAR_OVERFLOW 4u    /* more than EG_MAX_ACTIONS_PER_YEAR actions in one year */
 #define EG_FLAG_NO_SITE 8u          /* placement search found no site with score > 0 (reference falls back; we flag) */
-#define EG_MAX_NEW_GENERATORS 192
-#define EG_MAX_OFFSETS 96
+#define EG_MAX_NEW_GENERATORS 560
+#define EG_MAX_OFFSETS 520
 
 typedef struct eg_ctx eg_ctx;         /* device context: stream, static map tables in HBM */
 typedef struct eg_weights eg_weights; /* host object == reference ActionWeights (weights/mod.rs:49-107) */
