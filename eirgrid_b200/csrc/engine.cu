@@ -14,6 +14,7 @@
 #include "suitability.cuh"
 #include "weights.hpp"
 
+static_assert(sizeof(EgPolicyDevice) == 23392, "bench.py and eirgrid_b200/_abi.py quote this size");
 static thread_local std::string g_last_error;
 int eg_fail(int code, const std::string& message) {
   g_last_error = message;
@@ -383,7 +384,7 @@ int eg_update_stats_device(eg_ctx* c, const eg_weights* w, const eg_result* d_re
   p.stats = d_stats; p.best_score = d_best_score; p.best_index = d_best_index;
   p.ln100 = std::log(50000000000.0 * 100.0 / 50000000000.0);
   EG_CUDA(eg_launch_stats(p, c->stream));
-  if (n) c->launches++;
+  c->launches += n ? 3 : 1;  // reset + accumulate + arg-best kernels
   return EG_OK;
 }
 

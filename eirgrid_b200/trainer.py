@@ -1,0 +1,141 @@
+"""Batch training loop: the B200 replacement of the reference's rayon loop (core/multi_simulation.rs:425-611).
+
+One process per GPU. Each step every rank
+  1. uploads the shared weights snapshot        (== local_weights = shared.read().clone(), :457-460)
+  2. rolls out `episodes_per_gpu` episodes       (== run_iteration for its shard of iteration ids, :472)
+  3. accumulates the update statistics on the GPU (== the write-lock section :494-508, batch-synchronous form)
+  4. sums the statistics table over ranks        (one NCCL allreduce, int64) and gathers each rank's best episode
+  5. applies the identical update on every rank  (eg_update_apply_stats)
+
+PyTorch is used for device buffers, streams and torch.distributed only.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi, _lib
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class BatchTrainer:
+    def __init__(self, episodes_per_gpu, seed=1, device=None, cfg=None, weights=None, asset_dir=None, map_arrays=None,
+                 distributed=None, want_sites=False):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.EirgridError(-4, "no CUDA device; eirgrid_b200 has no CPU fallback")
+        import torch.distributed as dist
+        self.dist = dist if (distributed if distributed is not None else dist.is_initialized()) else None
+        self.rank = self.dist.get_rank() if self.dist else 0
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.device_index = int(os.environ.get("LOCAL_RANK", 0)) if device is None else int(device)
+        torch.cuda.set_device(self.device_index)
+        self.device = torch.device("cuda", self.device_index)
+        # a dedicated (non-default) stream shared by the library's kernels, the torch copies and the collectives
+        self.stream = torch.cuda.Stream(self.device)
+        self.ctx = _lib.Context(self.device_index, self.stream.cuda_stream)
+        assert self.stream.cuda_stream != 0
+        if map_arrays is not None:
+            self.ctx.map_set(*map_arrays)
+        else:
+            self.ctx.map_load_dir(asset_dir)
+        self.n = int(episodes_per_gpu)
+        self.seed = int(seed)
+        self.cfg = cfg or _abi.RunCfg()
+        self.weights = weights or _lib.Weights()
+        self.next_episode = 0  # global id of the first episode of the next batch
+        u8 = torch.uint8
+        self.d_results = torch.empty(self.n * _abi.RESULT_DTYPE.itemsize, dtype=u8, device=self.device)
+        self.d_traj = torch.empty(self.n * _abi.TRAJ_DTYPE.itemsize, dtype=u8, device=self.device)
+        self.d_sites = torch.empty(self.n * _abi.SITES_DTYPE.itemsize, dtype=u8, device=self.device) if want_sites else None
+        self.d_stats = torch.zeros(_abi.STATS_WORDS, dtype=torch.int64, device=self.device)
+        self.d_best_score = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.d_best_index = torch.zeros(1, dtype=torch.int64, device=self.device)
+        # per-rank candidate record: [score f64 | global index i64 | eg_result | eg_traj]
+        self.rec_bytes = 16 + _abi.RESULT_DTYPE.itemsize + _abi.TRAJ_DTYPE.itemsize
+        self.d_rec = torch.zeros(self.rec_bytes, dtype=u8, device=self.device)
+        self.d_all_rec = torch.zeros(self.world * self.rec_bytes, dtype=u8, device=self.device)
+        self.h_stats = torch.zeros(_abi.STATS_WORDS, dtype=torch.int64).pin_memory()
+        self.h_all_rec = torch.zeros(self.world * self.rec_bytes, dtype=u8).pin_memory()
+        self.h2d_bytes_per_step = 0
+        self.d2h_bytes_per_step = self.h_stats.numel() * 8 + self.h_all_rec.numel()
+        self.last_stats = None
+        torch.cuda.synchronize(self.device)  # allocations above ran on the default stream
+
+    # -- pieces (also used by bench.py to time the device-resident part alone) --
+    def upload_weights(self):
+        self.ctx.weights_upload(self.weights)
+
+    def launch_rollout(self, first_episode=None):
+        first = self.next_episode + self.rank * self.n if first_episode is None else first_episode
+        self.ctx.rollout_device(self.n, self.seed, first, self.d_results, self.d_traj, self.d_sites, None, self.cfg)
+
+    def launch_stats(self):
+        with _torch().cuda.stream(self.stream):
+            self.d_stats.zero_()
+        self.ctx.update_stats_device(self.weights, self.n, self.d_results, self.d_traj, self.d_stats, self.d_best_score,
+                                     self.d_best_index)
+
+    def _pack_best(self):
+        torch = _torch()
+        rb, tb = _abi.RESULT_DTYPE.itemsize, _abi.TRAJ_DTYPE.itemsize
+        with torch.cuda.stream(self.stream):
+            idx = self.d_best_index.clamp(0, self.n - 1)
+            gidx = idx + (self.next_episode + self.rank * self.n)
+            self.d_rec[0:8] = self.d_best_score.view(torch.uint8)
+            self.d_rec[8:16] = gidx.view(torch.uint8)
+            self.d_rec[16:16 + rb] = self.d_results.view(self.n, rb).index_select(0, idx).view(-1)
+            self.d_rec[16 + rb:] = self.d_traj.view(self.n, tb).index_select(0, idx).view(-1)
+
+    def reduce_stats(self):
+        """Sum the statistics table over ranks (the path's only exchange step)."""
+        if self.dist and self.world > 1:
+            with _torch().cuda.stream(self.stream):
+                self.dist.all_reduce(self.d_stats, op=self.dist.ReduceOp.SUM)
+
+    def step(self):
+        """One training batch through the public path: weights in from the host, update statistics back."""
+        torch = _torch()
+        self.upload_weights()
+        self.launch_rollout()
+        self.launch_stats()
+        self._pack_best()
+        self.reduce_stats()
+        with torch.cuda.stream(self.stream):
+            if self.dist and self.world > 1:
+                self.dist.all_gather_into_tensor(self.d_all_rec, self.d_rec)
+            else:
+                self.d_all_rec.copy_(self.d_rec)
+            self.h_stats.copy_(self.d_stats, non_blocking=True)
+            self.h_all_rec.copy_(self.d_all_rec, non_blocking=True)
+        self.stream.synchronize()
+        rec = self.h_all_rec.numpy().reshape(self.world, self.rec_bytes)
+        scores = rec[:, 0:8].copy().view(np.float64).ravel()
+        gidx = rec[:, 8:16].copy().view(np.int64).ravel()
+        # batch winner: highest score, lowest episode id among ties (== first in episode order)
+        order = np.lexsort((gidx, -scores))
+        win = int(order[0])
+        rb = _abi.RESULT_DTYPE.itemsize
+        best_result = rec[win, 16:16 + rb].copy().view(_abi.RESULT_DTYPE)
+        best_traj = rec[win, 16 + rb:].copy().view(_abi.TRAJ_DTYPE)
+        n_total = self.n * self.world
+        st = self.weights.apply_stats(self.h_stats.numpy(), n_total, best_result, best_traj,
+                                      int(gidx[win] - self.next_episode))
+        self.next_episode += n_total
+        self.last_stats = st
+        return st
+
+    def fetch_results(self):
+        """Copy this rank's last batch to the host as structured arrays (results, trajectories)."""
+        self.stream.synchronize()
+        with _torch().cuda.stream(self.stream):
+            res = self.d_results.cpu().numpy().view(_abi.RESULT_DTYPE)
+            traj = self.d_traj.cpu().numpy().view(_abi.TRAJ_DTYPE)
+        return res, traj
+
+    def close(self):
+        self.ctx.close()

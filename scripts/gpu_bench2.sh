@@ -1,0 +1,13 @@
+#!/bin/bash
+# bench + ncu launch list + ncu full capture of the rollout kernel
+set -x
+mkdir -p gpurun_out
+python bench.py --steps 5 --warmup 3 2>gpurun_out/bench_err.log | tee gpurun_out/bench_r01.json
+tail -3 gpurun_out/bench_err.log
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_r01.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+python bench.py --steps 1 --warmup 3 --episodes 16384 --no-cpu-baseline > gpurun_out/plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:eg_episode_kernel -s 1 -c 1 -o gpurun_out/rollout_r01 \
+    python bench.py --steps 1 --warmup 3 --episodes 16384 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+ls -la gpurun_out
