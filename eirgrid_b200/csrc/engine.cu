@@ -14,7 +14,7 @@
 #include "suitability.cuh"
 #include "weights.hpp"
 
-static_assert(sizeof(EgPolicyDevice) == 23392, "bench.py and eirgrid_b200/_abi.py quote this size");
+static_assert(sizeof(EgPolicyDevice) == 37752, "bench.py and eirgrid_b200/_abi.py quote this size");
 static thread_local std::string g_last_error;
 int eg_fail(int code, const std::string& message) {
   g_last_error = message;
@@ -48,6 +48,7 @@ struct eg_ctx {
   double* d_static_sorted = nullptr;
   double* d_prefix_sorted = nullptr;
   double* d_near = nullptr;
+  int* d_r2_limit = nullptr;
   double *d_sx = nullptr, *d_sy = nullptr, *d_ex = nullptr, *d_ey = nullptr, *d_cx = nullptr, *d_cy = nullptr;
   uint32_t* d_pop = nullptr;
   EgPolicyDevice* d_policy = nullptr;
@@ -66,12 +67,12 @@ namespace {
 
 void free_map(eg_ctx* c) {
   void* ptrs[] = {c->d_small, c->d_op_cost, c->d_site_opinion, c->d_coast, c->d_prefix, c->d_static_unsorted, c->d_order,
-                  c->d_static_sorted, c->d_prefix_sorted, c->d_near, c->d_sx, c->d_sy, c->d_ex, c->d_ey, c->d_cx, c->d_cy, c->d_pop};
+                  c->d_static_sorted, c->d_prefix_sorted, c->d_near, c->d_r2_limit, c->d_sx, c->d_sy, c->d_ex, c->d_ey, c->d_cx, c->d_cy, c->d_pop};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   c->d_small = nullptr; c->d_op_cost = nullptr; c->d_site_opinion = nullptr; c->d_coast = nullptr; c->d_prefix = nullptr;
   c->d_static_unsorted = nullptr; c->d_order = nullptr; c->d_static_sorted = nullptr; c->d_prefix_sorted = nullptr;
-  c->d_near = nullptr; c->d_sx = c->d_sy = c->d_ex = c->d_ey = c->d_cx = c->d_cy = nullptr; c->d_pop = nullptr;
+  c->d_near = nullptr; c->d_r2_limit = nullptr; c->d_sx = c->d_sy = c->d_ex = c->d_ey = c->d_cx = c->d_cy = nullptr; c->d_pop = nullptr;
   c->map_ready = false;
 }
 
@@ -94,6 +95,7 @@ int build_device_map(eg_ctx* c) {
   if ((rc = upload(&c->d_small, &c->htab.small, 1, s))) return rc;
   if ((rc = upload(&c->d_op_cost, c->htab.op_cost.data(), c->htab.op_cost.size(), s))) return rc;
   if ((rc = upload(&c->d_near, c->htab.near_factor.data(), c->htab.near_factor.size(), s))) return rc;
+  if ((rc = upload(&c->d_r2_limit, c->htab.r2_limit, (size_t)EG_N_RCLASS, s))) return rc;
   if ((rc = upload(&c->d_sx, m.sx.data(), m.sx.size(), s))) return rc;
   if ((rc = upload(&c->d_sy, m.sy.data(), m.sy.size(), s))) return rc;
   if ((rc = upload(&c->d_ex, m.ex.data(), m.ex.size(), s))) return rc;
@@ -129,6 +131,8 @@ int build_device_map(eg_ctx* c) {
   c->dmap.static_score = c->d_static_sorted;
   c->dmap.prefix_score = c->d_prefix_sorted;
   c->dmap.near_factor = c->d_near;
+  c->dmap.r2_limit = c->d_r2_limit;
+  c->dmap.r2_stride = c->htab.r2_stride;
   c->dmap.n_sites = ns;
   c->dmap.grid_n = m.grid_n;
   c->dmap.kmax = c->htab.kmax;
@@ -313,7 +317,6 @@ int eg_rollout_batch_device(eg_ctx* c, const eg_run_cfg* cfg, uint64_t seed, uin
   if (rc) return rc;
   if (!c->policy_ready) return eg_fail(EG_ERR_STATE, "no weights uploaded: call eg_weights_upload first");
   if (!d_out) return eg_fail(EG_ERR_INVALID, "eg_rollout_batch_device: d_out is NULL");
-  if (cfg->replay_best) return eg_fail(EG_ERR_INVALID, "replay_best=1 is not implemented on the device path yet");
   EG_CUDA(cudaSetDevice(c->device));
   EgEpisodeParams p = make_params(c, cfg, seed, first_episode, n);
   p.out = d_out; p.traj = d_traj; p.sites = d_sites; p.yearly = d_yearly;

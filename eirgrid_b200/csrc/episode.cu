@@ -1,31 +1,52 @@
-// episode.cu — the batched 2025-2050 episode kernel (sm_100a), one episode per thread.
+// episode.cu — the batched 2025-2050 episode kernel (sm_100a), one episode per WARP.
 //
 // Replaces, for n episodes at once, the body of the reference's rayon closure up to the write lock:
 //   run_iteration / run_simulation / handle_power_deficit      core/iteration.rs:10-95, core/simulation.rs:22-522
 //   apply_action / Map::add_generator / add_carbon_offset       core/actions.rs:40-204, utils/map_handler.rs:553-811
 //   find_best_generator_location -> find_suitable_location      map_handler.rs:1084-1143, gpu/metal_location_search.rs:110-176
 //   Map totals, opinion, capital cost, yearly metrics           map_handler.rs:813-985, analysis/metrics_calculation.rs:7-175
-//   sample_action / sample_deficit_action / sample_additional   ai/learning/weights/sampling.rs:76-443
+//   sample_action / sample_deficit_action / sample_additional   ai/learning/weights/sampling.rs:76-528
 //   update_weights / update_deficit_weights (episode-local)     weights/learning.rs:21-88, weights/deficit.rs:82-135
 //   score_metrics                                               ai/metrics/scoring.rs:5-45
 //
-// Design: every float sum/product of the reference runs over Vec<Generator> in insertion
-// order, with the existing plants first. A thread therefore walks ITS episode's plants in the same order and
-// reproduces the reference's rounding exactly; the existing-plant prefix of every accumulator and everything that
-// needs pow/exp is tabulated per year on the host. Within a year a new plant extends each sequential sum by one
-// term, so the sums are carried incrementally and re-walked only when the year (and so every term) changes.
-// The 100x100 placement scan collapses to a walk down a per-(class, year) list of sites pre-sorted by their
-// static score: only sites within the penalty radius of a plant built in this episode can differ from it.
-// Compiled with --fmad=false: no contraction, so + - * / are the reference's IEEE operations.
+// Design.
+//  * Every float sum/product of the reference runs over Vec<Generator> in insertion order with the pre-existing
+//    plants first. The warp keeps the episode's scalar state replicated in every lane (uniform control flow, no
+//    broadcasts) and adds terms in that same order, so roundings are the reference's; the existing-plant prefix of
+//    each accumulator and everything needing pow/exp is tabulated per year on the host. Per-plant TERMS are computed
+//    32 at a time across the lanes and folded in sequentially by shuffle.
+//  * Episode state that is indexed dynamically lives in shared memory, one slice per warp: the list of plants and
+//    offsets built so far, this year's private copy of the weight rows, and a per-candidate-site map of the squared
+//    cell distance to the nearest plant built in this episode.
+//  * The 100x100 placement scan becomes a walk, 32 candidates per step, down a per-(class, year) list of sites sorted
+//    by static score. A site farther than the penalty radius from every new plant keeps its static score. A site in
+//    range can only lose score, and (static prefix) x (factor of its nearest new plant) is an exact upper bound of
+//    its score (rounding is monotone), so most in-range sites are rejected without touching the plant list; the few
+//    survivors multiply their factors in plant order. The walk stops once static scores fall below the best found.
+//  * Compiled with --fmad=false: + - * / sqrt are the reference's IEEE operations, no contraction.
 #include "episode.cuh"
 
 namespace {
 
-constexpr int kBattery100 = 3 * 12;  // AddGenerator(BatteryStorage, 100 %), simulation.rs:376
-constexpr int kGasPeaker100 = 3 * 8; // sampling fallbacks, sampling.rs:185,237,321,377
-constexpr double kMinWeight = 0.0001, kMaxWeight = 0.999;      // ai/learning/constants.rs:14-15
-constexpr double kMaxAcceptableCost = 50000000000.0;            // config/constants.rs:113
-constexpr double kMaxAcceptableEmissions = 1000000.0;           // config/constants.rs:112
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr int kBattery100 = 3 * 12;   // AddGenerator(BatteryStorage, 100 %), simulation.rs:376
+constexpr int kGasPeaker100 = 3 * 8;  // sampling fallbacks, sampling.rs:185,237,321,377
+constexpr double kMinWeight = 0.0001, kMaxWeight = 0.999;   // ai/learning/constants.rs:14-15
+constexpr double kMaxAcceptableCost = 50000000000.0;         // config/constants.rs:113
+constexpr double kMaxAcceptableEmissions = 1000000.0;        // config/constants.rs:112
+
+// ---- per-warp shared-memory slice --------------------------------------------------------------------------
+constexpr int kOffLw = 0;                                       // double[61]  this year's regular weights
+constexpr int kOffLdw = kOffLw + 8 * EG_N_ACTIONS;              // double[15]  this year's deficit weights
+constexpr int kOffScaled = kOffLdw + 8 * EG_N_DEFICIT_KEYS;     // double[61]  weights^power in sorted order
+constexpr int kOffGens = kOffScaled + 8 * EG_N_ACTIONS;         // uint32[EG_MAX_NEW_GENERATORS]
+constexpr int kOffOffs = kOffGens + 4 * EG_MAX_NEW_GENERATORS;  // uint16[EG_MAX_OFFSETS]
+constexpr int kOffYearSites = kOffOffs + 2 * EG_MAX_OFFSETS;    // uint16[40]
+constexpr int kOffYearActions = kOffYearSites + 2 * EG_MAX_ACTIONS_PER_YEAR;  // uint8[40]
+constexpr int kOffSortIdx = kOffYearActions + EG_MAX_ACTIONS_PER_YEAR;        // uint8[64]
+constexpr int kOffCounts = kOffSortIdx + 64;                    // uint8[26] deficit + uint8[26] additional
+constexpr int kOffNear = (kOffCounts + 2 * EG_NY + 15) & ~15;   // nearest-plant map, n_sites entries
+static_assert(kOffGens % 8 == 0 && kOffOffs % 4 == 0 && kOffYearSites % 4 == 0 && kOffYearActions % 4 == 0, "alignment");
 
 // ---- Philox4x32-10, counter = (episode lo, episode hi, draw, stream 0), key = seed ------------------------
 __device__ __forceinline__ unsigned long long philox_u64(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
@@ -62,39 +83,54 @@ __device__ __forceinline__ double action_impact(const State& cur, const State& n
   return cost_improvement * cost_weight + opinion_improvement * opinion_weight;
 }
 
+__device__ __forceinline__ double shfl_f64(double v, int src) { return __shfl_sync(kFull, v, src); }
+
 // packed plant: gi(8) gj(8) type(4) mult(2) build(5)
 __device__ __forceinline__ uint32_t pack_gen(int gi, int gj, int t, int m, int b) {
   return (uint32_t)gi | ((uint32_t)gj << 8) | ((uint32_t)t << 16) | ((uint32_t)m << 20) | ((uint32_t)b << 22);
 }
 
-struct Episode {
-  // sequential sums over the episode's fleet for the current year
-  double gen[3];
-  double co2;
-  double op_sum;
+template <bool REPLAY, typename NearT>
+struct Warp {
+  const EgEpisodeParams& p;
+  const EgSmallTables* __restrict__ T;
+  const int lane;
+  // shared-memory slice of this warp
+  double* lw;
+  double* ldw;
+  double* scaled;
+  uint32_t* gens;
+  uint16_t* offs;
+  uint16_t* year_sites;
+  uint8_t* year_actions;
+  uint8_t* sort_idx;
+  uint8_t* counts;
+  NearT* nearest;
+  // warp-uniform episode state (identical in every lane)
+  double gen0, gen1, gen2;    // plain / intermittent / storage generation accumulators
+  double co2, op_sum;
   double gcost, gcost_prev;   // capital cost of new plants re-priced at year / year-1 (map_handler.rs:955-958)
   double ocost, ocost_prev;   // same for offsets (map_handler.rs:960-962)
   double off_amount;          // calc_total_carbon_offset(year)
-  uint32_t n_gens, n_offs;
-  uint32_t flags;
-};
-
-template <bool REPLAY>
-struct Kernel {
-  const EgEpisodeParams& p;
-  const EgSmallTables* __restrict__ T;
-  Episode e;
-  uint32_t gens[EG_MAX_NEW_GENERATORS];
-  uint16_t offs[EG_MAX_OFFSETS];       // otype(2) mult(2) build(5)
-  double lw[EG_N_ACTIONS];             // episode-local copy of this year's weights once update_weights touched them
-  double ldw[EG_N_DEFICIT_KEYS];
-  bool lw_valid;
-  uint8_t year_actions[EG_MAX_ACTIONS_PER_YEAR];
-  uint16_t year_sites[EG_MAX_ACTIONS_PER_YEAR];
-  uint8_t n_def_year[EG_NY], n_add_year[EG_NY];
+  uint32_t n_gens, n_offs, flags;
+  bool lw_valid, sorted_valid;
   Rng rng;
 
-  __device__ Kernel(const EgEpisodeParams& p_) : p(p_), T(p_.map.small) {}
+  __device__ Warp(const EgEpisodeParams& p_, unsigned char* slice, int lane_)
+      : p(p_), T(p_.map.small), lane(lane_) {
+    lw = (double*)(slice + kOffLw);
+    ldw = (double*)(slice + kOffLdw);
+    scaled = (double*)(slice + kOffScaled);
+    gens = (uint32_t*)(slice + kOffGens);
+    offs = (uint16_t*)(slice + kOffOffs);
+    year_sites = (uint16_t*)(slice + kOffYearSites);
+    year_actions = (uint8_t*)(slice + kOffYearActions);
+    sort_idx = (uint8_t*)(slice + kOffSortIdx);
+    counts = (uint8_t*)(slice + kOffCounts);
+    nearest = (NearT*)(slice + kOffNear);
+  }
+
+  static constexpr NearT kFar = (NearT)~(NearT)0;
 
   __device__ __forceinline__ double gen_cost(int t, int m, int b, int y) const {
     // get_current_cost: base_cost * inflation * technology_factor * location_modifier, then * multiplier
@@ -109,115 +145,190 @@ struct Kernel {
     return 0.03 * __ldg(&p.map.site_opinion[site]) + __ldg(&T->op_type[y][t]) + __ldg(&p.map.op_cost[EG_OPC_INDEX(y, t, m, b)]);
   }
 
-  // Re-walk the fleet for a new year: every per-plant term depends on the year.
+  // Re-walk the fleet for a new year: every per-plant term depends on the year. Terms are computed one plant per
+  // lane, then folded into the accumulators in plant order (the order of the reference's iterator sums).
   __device__ void year_start(int y) {
     const EgYearRow& yr = T->year[y];
-    e.gen[0] = __ldg(&yr.ex_gen[0]); e.gen[1] = __ldg(&yr.ex_gen[1]); e.gen[2] = __ldg(&yr.ex_gen[2]);
-    e.co2 = __ldg(&yr.ex_co2);
-    e.op_sum = __ldg(&yr.ex_opinion_sum);
-    e.gcost = 0.0; e.gcost_prev = 0.0;
+    gen0 = __ldg(&yr.ex_gen[0]); gen1 = __ldg(&yr.ex_gen[1]); gen2 = __ldg(&yr.ex_gen[2]);
+    co2 = __ldg(&yr.ex_co2);
+    op_sum = __ldg(&yr.ex_opinion_sum);
+    gcost = 0.0; gcost_prev = 0.0;
     const int n = p.map.grid_n;
-    for (uint32_t i = 0; i < e.n_gens; i++) {
-      uint32_t g = gens[i];
-      int gi = g & 0xFF, gj = (g >> 8) & 0xFF, t = (g >> 16) & 0xF, m = (g >> 20) & 0x3, b = (g >> 22) & 0x1F;
-      e.gen[__ldg(&T->acc_class[t])] += __ldg(&T->net_mw[t]);
-      e.co2 += __ldg(&T->co2[t]);
-      e.op_sum += gen_opinion(gi * n + gj, t, m, b, y);
-      e.gcost += gen_cost(t, m, b, y);
-      if (y > 0) e.gcost_prev += gen_cost(t, m, b, y - 1);
+    for (uint32_t base = 0; base < n_gens; base += 32) {
+      const uint32_t i = base + lane;
+      double t_mw = 0.0, t_co2 = 0.0, t_op = 0.0, t_c = 0.0, t_cp = 0.0;
+      int cls = 0;
+      if (i < n_gens) {
+        const uint32_t g = gens[i];
+        const int gi = g & 0xFF, gj = (g >> 8) & 0xFF, t = (g >> 16) & 0xF, m = (g >> 20) & 0x3, b = (g >> 22) & 0x1F;
+        cls = __ldg(&T->acc_class[t]);
+        t_mw = __ldg(&T->net_mw[t]);
+        t_co2 = __ldg(&T->co2[t]);
+        t_op = gen_opinion(gi * n + gj, t, m, b, y);
+        t_c = gen_cost(t, m, b, y);
+        if (y > 0) t_cp = gen_cost(t, m, b, y - 1);
+      }
+      const int cnt = min(32u, n_gens - base);
+      for (int j = 0; j < cnt; j++) {
+        const double mw = shfl_f64(t_mw, j);
+        const int c = __shfl_sync(kFull, cls, j);
+        // adding +0.0 leaves the other two accumulators unchanged bit for bit
+        gen0 += c == EG_ACC_PLAIN ? mw : 0.0;
+        gen1 += c == EG_ACC_INTERMITTENT ? mw : 0.0;
+        gen2 += c == EG_ACC_STORAGE ? mw : 0.0;
+        co2 += shfl_f64(t_co2, j);
+        op_sum += shfl_f64(t_op, j);
+        gcost += shfl_f64(t_c, j);
+        if (y > 0) gcost_prev += shfl_f64(t_cp, j);
+      }
     }
-    e.ocost = 0.0; e.ocost_prev = 0.0; e.off_amount = 0.0;
-    for (uint32_t i = 0; i < e.n_offs; i++) {
-      uint32_t o = offs[i];
-      int ot = o & 3, m = (o >> 2) & 3, b = (o >> 4) & 0x1F;
-      double maturity = __ldg(&T->natural_offset[ot]) ? __ldg(&T->maturity[y - b]) : 1.0;
-      e.off_amount += __ldg(&T->off_amount[ot]) * maturity;
-      e.ocost += off_cost(ot, m, y);
-      if (y > 0) e.ocost_prev += off_cost(ot, m, y - 1);
+    ocost = 0.0; ocost_prev = 0.0; off_amount = 0.0;
+    for (uint32_t base = 0; base < n_offs; base += 32) {
+      const uint32_t i = base + lane;
+      double t_a = 0.0, t_c = 0.0, t_cp = 0.0;
+      if (i < n_offs) {
+        const uint32_t o = offs[i];
+        const int ot = o & 3, m = (o >> 2) & 3, b = (o >> 4) & 0x1F;
+        const double maturity = __ldg(&T->natural_offset[ot]) ? __ldg(&T->maturity[y - b]) : 1.0;
+        t_a = __ldg(&T->off_amount[ot]) * maturity;
+        t_c = off_cost(ot, m, y);
+        if (y > 0) t_cp = off_cost(ot, m, y - 1);
+      }
+      const int cnt = min(32u, n_offs - base);
+      for (int j = 0; j < cnt; j++) {
+        off_amount += shfl_f64(t_a, j);
+        ocost += shfl_f64(t_c, j);
+        if (y > 0) ocost_prev += shfl_f64(t_cp, j);
+      }
     }
   }
 
   __device__ __forceinline__ State state(int y) const {  // simulation.rs:122-135
     State s;
-    s.net = e.co2 - e.off_amount;
-    uint32_t cnt = __ldg(&T->year[y].ex_active) + e.n_gens;
-    s.opinion = cnt > 0 ? e.op_sum / (double)cnt : 1.0;
-    s.balance = (e.gen[0] + e.gen[1] + e.gen[2]) - __ldg(&T->year[y].usage_total);
-    s.cost = e.gcost + e.ocost;
+    s.net = co2 - off_amount;
+    const uint32_t cnt = __ldg(&T->year[y].ex_active) + n_gens;
+    s.opinion = cnt > 0 ? op_sum / (double)cnt : 1.0;
+    s.balance = (gen0 + gen1 + gen2) - __ldg(&T->year[y].usage_total);
+    s.cost = gcost + ocost;
     return s;
   }
 
-  // MetalLocationSearch::find_suitable_location (CPU branch) as a walk down the pre-sorted site list.
-  __device__ int place(int t, int y) const {
+  // MetalLocationSearch::find_suitable_location (CPU branch) as a 32-wide walk down the pre-sorted site list.
+  __device__ int place(int t, int y) {
     const int pc = __ldg(&T->pclass[t]);
     const int rc = __ldg(&T->rclass_of_pclass[pc]);
     const bool water = __ldg(&T->water_of_pclass[pc]) != 0;
-    const int ns = p.map.n_sites, n = p.map.grid_n, km = p.map.kmax;
+    const int ns = p.map.n_sites, n = p.map.grid_n;
+    const int r2lim = __ldg(&p.map.r2_limit[rc]);  // cell offsets with d2 < r2lim are inside the penalty radius
     const size_t base = ((size_t)pc * EG_NY + y) * ns;
     const uint16_t* __restrict__ order = p.map.order + base;
     const double* __restrict__ stat = p.map.static_score + base;
     const double* __restrict__ pref = p.map.prefix_score + base;
-    const double* __restrict__ nf = p.map.near_factor + (size_t)rc * km * km;
+    const double* __restrict__ nf = p.map.near_factor + (size_t)rc * p.map.r2_stride;  // distance/radius by squared cell distance
     const double size_factor = __ldg(&T->size_factor);
     double best_score = 0.0;
     int best_site = -1;
-    for (int k = 0; k < ns; k++) {
-      const double s_static = __ldg(&stat[k]);
-      // a site in range of new plants only loses score (factors < 1), so nothing below can beat the best so far
-      if (s_static < best_score || !(s_static > 0.0)) break;
-      const int site = __ldg(&order[k]);
-      const int si = site / n, sj = site - si * n;
-      double score = __ldg(&pref[k]);
-      bool affected = false;
-      for (uint32_t g = 0; g < e.n_gens; g++) {
-        const uint32_t pk = gens[g];
-        int di = si - (int)(pk & 0xFF), dj = sj - (int)((pk >> 8) & 0xFF);
-        di = di < 0 ? -di : di; dj = dj < 0 ? -dj : dj;
-        if (di < km && dj < km) {
-          const double f = __ldg(&nf[di * km + dj]);
-          if (f >= 0.0) { score *= f; affected = true; }   // score *= distance / penalty_radius
+    for (int k0 = 0; k0 < ns; k0 += 32) {
+      const int k = k0 + lane;
+      const double s_static = k < ns ? __ldg(&stat[k]) : 0.0;
+      const double s_first = shfl_f64(s_static, 0);
+      // the list is sorted: nothing from here on can beat the best so far, and zero scores never win
+      if (s_first < best_score || !(s_first > 0.0)) break;
+      bool live = k < ns && s_static > 0.0 && !(s_static < best_score);
+      double score = s_static;
+      int site = 0x7FFFFFFF;
+      if (live) {
+        site = __ldg(&order[k]);
+        const int d2n = nearest[site];
+        if (d2n < r2lim) {
+          // in range of at least one new plant: all factors are < 1 and rounding is monotone, so the product with
+          // the nearest plant's factor alone bounds the true score from above
+          const double pre = __ldg(&pref[k]);
+          double bound = pre * __ldg(&nf[d2n]);
+          if (water) bound *= __ldg(&p.map.coast_factor[site]);
+          bound *= size_factor;
+          if (bound < best_score) {
+            live = false;
+          } else {
+            const int si = site / n, sj = site - si * n;
+            double sc = pre;
+            for (uint32_t g = 0; g < n_gens; g++) {  // plant order == multiplication order of the reference
+              const uint32_t pk = gens[g];
+              const int di = si - (int)(pk & 0xFF), dj = sj - (int)((pk >> 8) & 0xFF);
+              const int d2 = di * di + dj * dj;
+              if (d2 < r2lim) sc *= __ldg(&nf[d2]);  // score *= distance / penalty_radius
+            }
+            if (water) sc *= __ldg(&p.map.coast_factor[site]);
+            sc *= size_factor;
+            score = sc;
+          }
         }
       }
-      if (affected) {
-        if (water) score *= __ldg(&p.map.coast_factor[site]);
-        score *= size_factor;
-      } else {
-        score = s_static;
-      }
-      // strict '>' in scan order (metal_location_search.rs:168): equal scores keep the lower site index
-      if (score > best_score || (score == best_score && best_site >= 0 && site < best_site)) {
-        best_score = score;
-        best_site = site;
+      // strict '>' in scan order (metal_location_search.rs:168): the maximum wins, equal scores keep the lower site
+      const bool better = live && (score > best_score || (score == best_score && best_site >= 0 && site < best_site));
+      if (__any_sync(kFull, better)) {
+        double c_score = better ? score : -1.0;
+        int c_site = better ? site : 0x7FFFFFFF;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double o_score = __shfl_xor_sync(kFull, c_score, o);
+          const int o_site = __shfl_xor_sync(kFull, c_site, o);
+          if (o_score > c_score || (o_score == c_score && o_site < c_site)) { c_score = o_score; c_site = o_site; }
+        }
+        best_score = c_score;
+        best_site = c_site;
       }
     }
     return best_site;
   }
 
-  __device__ __forceinline__ void add_generator(int site, int t, int m, int y) {
-    if (e.n_gens >= EG_MAX_NEW_GENERATORS) { e.flags |= EG_FLAG_GEN_OVERFLOW; return; }
+  __device__ void add_generator(int site, int t, int m, int y) {
+    if (n_gens >= EG_MAX_NEW_GENERATORS) { flags |= EG_FLAG_GEN_OVERFLOW; return; }
     const int n = p.map.grid_n;
-    gens[e.n_gens++] = pack_gen(site / n, site % n, t, m, y);
-    e.gen[__ldg(&T->acc_class[t])] += __ldg(&T->net_mw[t]);
-    e.co2 += __ldg(&T->co2[t]);
-    e.op_sum += gen_opinion(site, t, m, y, y);
-    e.gcost += gen_cost(t, m, y, y);
-    if (y > 0) e.gcost_prev += gen_cost(t, m, y, y - 1);
+    const int gi = site / n, gj = site - gi * n;
+    if (lane == 0) gens[n_gens] = pack_gen(gi, gj, t, m, y);
+    n_gens++;
+    // nearest-plant map: squared cell distance to the closest plant built in this episode
+    const int R = p.map.kmax - 1, side = 2 * R + 1, cells = side * side;
+    const int far = (int)kFar;
+    for (int c = lane; c < cells; c += 32) {
+      const int di = c / side - R, dj = c - (c / side) * side - R;
+      const int i = gi + di, j = gj + dj;
+      if (i >= 0 && i < n && j >= 0 && j < n) {
+        const int d2 = min(di * di + dj * dj, far);
+        NearT* cell = &nearest[i * n + j];
+        if (d2 < (int)*cell) *cell = (NearT)d2;
+      }
+    }
+    __syncwarp();
+    const int cls = __ldg(&T->acc_class[t]);
+    const double mw = __ldg(&T->net_mw[t]);
+    gen0 += cls == EG_ACC_PLAIN ? mw : 0.0;
+    gen1 += cls == EG_ACC_INTERMITTENT ? mw : 0.0;
+    gen2 += cls == EG_ACC_STORAGE ? mw : 0.0;
+    co2 += __ldg(&T->co2[t]);
+    op_sum += gen_opinion(site, t, m, y, y);
+    gcost += gen_cost(t, m, y, y);
+    if (y > 0) gcost_prev += gen_cost(t, m, y, y - 1);
   }
-  __device__ __forceinline__ void add_offset(int ot, int m, int y) {
-    if (e.n_offs >= EG_MAX_OFFSETS) { e.flags |= EG_FLAG_OFFSET_OVERFLOW; return; }
-    offs[e.n_offs++] = (uint16_t)(ot | (m << 2) | (y << 4));
-    double maturity = __ldg(&T->natural_offset[ot]) ? __ldg(&T->maturity[0]) : 1.0;
-    e.off_amount += __ldg(&T->off_amount[ot]) * maturity;
-    e.ocost += off_cost(ot, m, y);
-    if (y > 0) e.ocost_prev += off_cost(ot, m, y - 1);
+  __device__ void add_offset(int ot, int m, int y) {
+    if (n_offs >= EG_MAX_OFFSETS) { flags |= EG_FLAG_OFFSET_OVERFLOW; return; }
+    if (lane == 0) offs[n_offs] = (uint16_t)(ot | (m << 2) | (y << 4));
+    n_offs++;
+    __syncwarp();
+    const double maturity = __ldg(&T->natural_offset[ot]) ? __ldg(&T->maturity[0]) : 1.0;
+    off_amount += __ldg(&T->off_amount[ot]) * maturity;
+    ocost += off_cost(ot, m, y);
+    if (y > 0) ocost_prev += off_cost(ot, m, y - 1);
   }
 
   // ---- episode-local learning (the deficit handler edits this year's rows of its private weights) ----------
   __device__ void touch_local(int y) {
     if (lw_valid) return;
-    for (int k = 0; k < EG_N_ACTIONS; k++) lw[k] = __ldg(&p.policy->w[y][k]);
-    for (int k = 0; k < EG_N_DEFICIT_KEYS; k++) ldw[k] = __ldg(&p.policy->dw[y][k]);
+    for (int k = lane; k < EG_N_ACTIONS; k += 32) lw[k] = __ldg(&p.policy->w[y][k]);
+    if (lane < EG_N_DEFICIT_KEYS) ldw[lane] = __ldg(&p.policy->dw[y][lane]);
     lw_valid = true;
+    __syncwarp();
   }
   __device__ __forceinline__ double weight(int y, int k) const { return lw_valid ? lw[k] : __ldg(&p.policy->w[y][k]); }
   __device__ __forceinline__ double dweight(int y, int k) const { return lw_valid ? ldw[k] : __ldg(&p.policy->dw[y][k]); }
@@ -240,13 +351,13 @@ struct Kernel {
     if (key < 0 || action % 3 != 0) return;
     touch_local(y);
     const double lr = p.policy->learning_rate;
-    double adj = improvement > 0.0 ? 1.0 + (lr * improvement * 1.5) : 1.0 / (1.0 + (lr * fabs(improvement) * 1.5));
-    ldw[key] = fmin(fmax(ldw[key] * adj, kMinWeight), kMaxWeight);
-    if (improvement < 0.0) {
-      const double boost = 1.0 + (lr * 0.1);
-      for (int k = 0; k < 14; k++)
-        if (k != key) ldw[k] = fmin(ldw[k] * boost, kMaxWeight);
+    const double adj = improvement > 0.0 ? 1.0 + (lr * improvement * 1.5) : 1.0 / (1.0 + (lr * fabs(improvement) * 1.5));
+    const double boost = 1.0 + (lr * 0.1);
+    if (lane < 14) {
+      if (lane == key) ldw[lane] = fmin(fmax(ldw[lane] * adj, kMinWeight), kMaxWeight);
+      else if (improvement < 0.0) ldw[lane] = fmin(ldw[lane] * boost, kMaxWeight);
     }
+    __syncwarp();
   }
   __device__ void update_weights(int y, int action, double improvement) {  // learning.rs:21-88
     touch_local(y);
@@ -254,18 +365,50 @@ struct Kernel {
     const double rel = p.policy->relative_improvement;
     const double immediate = rel > 0.0 ? 0.7 : 0.3;
     const double combined = immediate * improvement + (1.0 - immediate) * rel;
-    double adj = combined > 0.0 ? 1.0 + (lr * combined) : 1.0 / (1.0 + (lr * fabs(combined)));
-    lw[action] = fmin(fmax(lw[action] * adj, kMinWeight), kMaxWeight);
-    if (combined < 0.0) {
-      const double boost = 1.0 + (lr * 0.1);
-      for (int k = 0; k < 45; k++)
-        if (k != action) lw[k] = fmin(lw[k] * boost, kMaxWeight);
-      if (p.policy->noop_boost) lw[EG_ACT_DO_NOTHING] = fmin(lw[EG_ACT_DO_NOTHING] * (1.0 + lr * 0.2), kMaxWeight);
+    const double adj = combined > 0.0 ? 1.0 + (lr * combined) : 1.0 / (1.0 + (lr * fabs(combined)));
+    const double boost = 1.0 + (lr * 0.1);
+    for (int k = lane; k < EG_N_ACTIONS; k += 32) {
+      if (k == action) lw[k] = fmin(fmax(lw[k] * adj, kMinWeight), kMaxWeight);
+      else if (combined < 0.0 && k < 45) lw[k] = fmin(lw[k] * boost, kMaxWeight);
+      else if (combined < 0.0 && k == EG_ACT_DO_NOTHING && p.policy->noop_boost) lw[k] = fmin(lw[k] * (1.0 + lr * 0.2), kMaxWeight);
     }
+    sorted_valid = false;
+    __syncwarp();
   }
 
   // ---- sampling (canonical key order replaces HashMap iteration order) ---------------------------------------
-  __device__ int sample_deficit_action(int y) {  // sampling.rs:315-378
+  __device__ int smart_fallback_action(int y) {  // sampling.rs:445-490
+    const int year = EG_BASE_YEAR + y;
+    const uint32_t storage = year < 2035 ? 10 : 20;
+    const uint32_t offset = year < 2035 ? 5 : (year < 2045 ? 15 : 25);
+    const uint32_t gas = year < 2035 ? 15 : (year < 2045 ? 10 : 5);
+    const int act[7] = {3 * 0, 3 * 1, 3 * 4, 3 * 12, 45 + 3 * 0, 45 + 3 * 2, 3 * 7};
+    const uint32_t wt[7] = {15, 10, 15, storage, offset, offset, gas};
+    uint32_t total = 0;
+    for (int i = 0; i < 7; i++) total += wt[i];
+    uint32_t choice = rng.index(total);
+    for (int i = 0; i < 7; i++) {
+      if (choice < wt[i]) return act[i];
+      choice -= wt[i];
+    }
+    return kBattery100;
+  }
+  __device__ int smart_deficit_fallback_action() {  // sampling.rs:492-528 ((0.07*0.5) as u32 == 0, (0.06*0.5*100) as u32 == 3)
+    const int act[6] = {3 * 8, 3 * 12, 3 * 7, 3 * 0, 3 * 1, 3 * 4};
+    const uint32_t wt[6] = {30, 30, 20, 10, 0, 3};
+    uint32_t choice = rng.index(93);
+    for (int i = 0; i < 6; i++) {
+      if (choice < wt[i]) return act[i];
+      choice -= wt[i];
+    }
+    return kBattery100;
+  }
+
+  __device__ int sample_deficit_action(int y, uint32_t* replay_pos) {  // sampling.rs:240-378
+    if (p.replay_best) {
+      if (p.policy->has_best && *replay_pos < p.policy->n_best_deficit[y]) return p.policy->best_deficit[y][(*replay_pos)++];
+      return smart_deficit_fallback_action();
+    }
     const bool explore = rng.f64() < p.policy->exploration_rate;
     if (explore) return deficit_key_action((int)rng.index(14));
     double total = 0.0;
@@ -293,13 +436,35 @@ struct Kernel {
       }
       return min(5u, max_possible);
     }
-    const double scaled = sqrt(p.policy->exploration_rate);  // powf(0.5) of a non-negative value
-    const uint32_t min_actions = (uint32_t)round(2.0 / scaled), max_actions = (uint32_t)round(12.0 / scaled);
+    const double scaled_eps = sqrt(p.policy->exploration_rate);  // powf(0.5) of a non-negative value
+    const uint32_t min_actions = (uint32_t)round(2.0 / scaled_eps), max_actions = (uint32_t)round(12.0 / scaled_eps);
     const uint32_t cmax = min(max_actions, max_possible), cmin = min(min_actions, cmax);
     if (cmin == cmax) return cmin;
     return cmin + rng.index(cmax - cmin + 1);
   }
-  __device__ int sample_action(int y) {  // sampling.rs:147-238
+
+  // stagnation branch of sample_action (sampling.rs:190-220) for rows edited in this episode: stable descending
+  // sort by rank counting and the powers, both spread over the lanes
+  __device__ void sort_local(double power) {
+    for (int k = lane; k < EG_N_ACTIONS; k += 32) {
+      const double wk = lw[k];
+      int rank = 0;
+      for (int j = 0; j < EG_N_ACTIONS; j++) {
+        const double wj = lw[j];
+        rank += (wj > wk) || (wj == wk && j < k);
+      }
+      sort_idx[rank] = (uint8_t)k;
+      scaled[rank] = pow(wk, power);
+    }
+    sorted_valid = true;
+    __syncwarp();
+  }
+
+  __device__ int sample_action(int y, uint32_t* replay_pos) {  // sampling.rs:76-238
+    if (p.replay_best) {
+      if (p.policy->has_best && *replay_pos < p.policy->n_best[y]) return p.policy->best[y][(*replay_pos)++];
+      return smart_fallback_action(y);
+    }
     const uint32_t iwi = p.policy->iwi;
     const double eps = p.policy->exploration_rate;
     const double cur_eps = iwi > 100 ? eps * (1.0 / (1.0 + 0.01 * (double)iwi)) : eps;
@@ -309,21 +474,19 @@ struct Kernel {
     for (int k = 0; k < EG_N_ACTIONS; k++) total += weight(y, k);
     if (total <= 0.0) return kGasPeaker100;
     if (iwi > 500) {
-      // stagnation branch: weights sorted descending (stable), raised to a power (sampling.rs:190-220)
-      uint8_t idx[EG_N_ACTIONS];
-      for (int k = 0; k < EG_N_ACTIONS; k++) {
-        const double wk = weight(y, k);
-        int j = k;
-        while (j > 0 && weight(y, idx[j - 1]) < wk) { idx[j] = idx[j - 1]; j--; }
-        idx[j] = (uint8_t)k;
+      const double* sc;
+      const uint8_t* idx;
+      if (lw_valid) {
+        if (!sorted_valid) sort_local(p.policy->stagnation_power);
+        sc = scaled; idx = sort_idx;
+      } else {
+        sc = p.policy->scaled_sorted[y]; idx = p.policy->sorted_idx[y];  // host libm, per snapshot
       }
-      const double sf = fmin((double)iwi / 1000.0, 3.0);
-      const double power = 1.0 + (2.0 * sf);
       double total_scaled = 0.0;
-      for (int k = 0; k < EG_N_ACTIONS; k++) total_scaled += pow(weight(y, idx[k]), power);
+      for (int k = 0; k < EG_N_ACTIONS; k++) total_scaled += sc[k];
       double rv = rng.f64() * total_scaled;
       for (int k = 0; k < EG_N_ACTIONS; k++) {
-        rv -= pow(weight(y, idx[k]), power);
+        rv -= sc[k];
         if (rv <= 0.0) return idx[k];
       }
       return idx[0];
@@ -337,16 +500,20 @@ struct Kernel {
   }
 
   __device__ __forceinline__ void record(int slot, int action, int site) {
-    if (slot >= EG_MAX_ACTIONS_PER_YEAR) { e.flags |= EG_FLAG_YEAR_OVERFLOW; return; }
-    year_actions[slot] = (uint8_t)action;
-    year_sites[slot] = site >= 0 ? (uint16_t)site : (uint16_t)EG_SITE_NONE;
+    if (slot >= EG_MAX_ACTIONS_PER_YEAR) { flags |= EG_FLAG_YEAR_OVERFLOW; return; }
+    if (lane == 0) {
+      year_actions[slot] = (uint8_t)action;
+      year_sites[slot] = site >= 0 ? (uint16_t)site : (uint16_t)EG_SITE_NONE;
+    }
   }
 
   __device__ void run(uint32_t ep) {
     const unsigned long long id = p.same_stream ? 0ull : p.first_episode + ep;
     rng.k0 = (uint32_t)p.seed; rng.k1 = (uint32_t)(p.seed >> 32);
     rng.e0 = (uint32_t)id; rng.e1 = (uint32_t)(id >> 32); rng.draw = 0;
-    e.n_gens = 0; e.n_offs = 0; e.flags = 0;
+    n_gens = 0; n_offs = 0; flags = 0;
+    for (int i = lane; i < p.map.n_sites; i += 32) nearest[i] = kFar;
+    __syncwarp();
     const eg_traj* in = REPLAY ? p.replay_in + ep : nullptr;
     double total_cost = 0.0, total_credit = 0.0, total_sales = 0.0;
     uint32_t n_def_total = 0, n_add_total = 0;
@@ -355,11 +522,12 @@ struct Kernel {
     for (int y = 0; y < EG_NY; y++) {
       year_start(y);
       lw_valid = false;
+      sorted_valid = false;
       State cur = state(y);
       bool deficit_mode = cur.balance < 0.0;                 // simulation.rs:137
       const State initial = cur;                             // simulation.rs:341-356
       double remaining = deficit_mode ? -cur.balance : 0.0;  // Map::handle_power_deficit returns it unchanged (Q2)
-      uint32_t attempts = 0, n_def = 0, n_add = 0, n_to_add = 0;
+      uint32_t attempts = 0, n_def = 0, n_add = 0, n_to_add = 0, replay_def = 0, replay_act = 0;
       bool counted = false;
       const uint32_t in_def = REPLAY ? in->n_deficit[y] : 0;
 
@@ -370,10 +538,10 @@ struct Kernel {
           if (remaining > 0.0) {                             // simulation.rs:358
             attempts++;
             if (REPLAY) action = n_def < in_def ? in->actions[y][n_def] : kBattery100;
-            else action = attempts < 5 ? sample_deficit_action(y) : kBattery100;
+            else action = attempts < 5 ? sample_deficit_action(y, &replay_def) : kBattery100;
             is_def = true;
           } else {                                           // simulation.rs:490-519
-            if (!REPLAY) {
+            if (!REPLAY && !p.replay_best) {
               const State fin = state(y);
               const double overall_success = action_impact(initial, fin);
               if (fin.balance >= 0.0 && overall_success > 0.0 && n_def > 0) {
@@ -385,7 +553,9 @@ struct Kernel {
             continue;
           }
         } else if (!counted) {                               // simulation.rs:144-187
-          n_to_add = REPLAY ? in->n_additional[y] : sample_additional_actions(y, n_def);
+          if (REPLAY) n_to_add = in->n_additional[y];
+          else if (p.replay_best) n_to_add = p.policy->has_best ? p.policy->n_best[y] : 0;
+          else n_to_add = sample_additional_actions(y, n_def);
           counted = true;
           continue;
         } else if (n_add < n_to_add) {                       // simulation.rs:189-198
@@ -393,7 +563,7 @@ struct Kernel {
             const uint32_t pos = in_def + n_add;
             action = pos < EG_MAX_ACTIONS_PER_YEAR ? in->actions[y][pos] : EG_ACT_DO_NOTHING;
           } else {
-            action = sample_action(y);
+            action = sample_action(y, &replay_act);
           }
           is_def = false;
         } else {
@@ -407,7 +577,7 @@ struct Kernel {
           const int t = action / 3, m = action - 3 * t;
           site = place(t, y);
           if (site >= 0) add_generator(site, t, m, y);
-          else e.flags |= EG_FLAG_NO_SITE;
+          else flags |= EG_FLAG_NO_SITE;
         } else if (action < 57) {                            // actions.rs:129-179
           const int a = action - 45;
           add_offset(a / 3, a % 3, y);
@@ -417,7 +587,7 @@ struct Kernel {
         if (is_def) {
           n_def++;
           const State after = state(y);                      // simulation.rs:412-427
-          if (!REPLAY) {
+          if (!REPLAY && !p.replay_best) {
             const double overall = action_impact(before, after);
             const double emis = after.net < before.net ? (before.net - after.net) / fmax(fabs(before.net), 1.0) : 0.0;
             double cost_imp = 0.0;
@@ -427,6 +597,7 @@ struct Kernel {
             }
             const double op_imp = after.cost < kMaxAcceptableCost * 8.0 ? (after.opinion - before.opinion) / fmax(1.0 - before.opinion, 0.1) : 0.0;
             const double combined = overall * 0.7 + emis * 0.15 + cost_imp * 0.1 + op_imp * 0.05;
+            __syncwarp();
             update_deficit_weights(y, action, combined);     // simulation.rs:479
             update_weights(y, action, overall * 0.5);        // simulation.rs:482
           }
@@ -435,38 +606,51 @@ struct Kernel {
           n_add++;
         }
       }
+      __syncwarp();
 
-      n_def_year[y] = (uint8_t)min(n_def, (uint32_t)EG_MAX_ACTIONS_PER_YEAR);
-      n_add_year[y] = (uint8_t)min(n_add, (uint32_t)EG_MAX_ACTIONS_PER_YEAR - n_def_year[y]);
+      const uint32_t nd_rec = min(n_def, (uint32_t)EG_MAX_ACTIONS_PER_YEAR);
+      const uint32_t na_rec = min(n_add, (uint32_t)EG_MAX_ACTIONS_PER_YEAR - nd_rec);
+      if (lane == 0) { counts[y] = (uint8_t)nd_rec; counts[EG_NY + y] = (uint8_t)na_rec; }
       n_def_total += n_def; n_add_total += n_add;
-      const uint32_t used = min(n_def + n_add, (uint32_t)EG_MAX_ACTIONS_PER_YEAR);
-      if (p.traj) {
-        uint8_t* row = p.traj[ep].actions[y];
-        for (uint32_t i = 0; i < used; i++) row[i] = year_actions[i];
-        for (uint32_t i = used; i < EG_MAX_ACTIONS_PER_YEAR; i++) row[i] = 0;
+      const uint32_t used = nd_rec + na_rec;
+      if (p.traj) {  // 40 B row, one 32-bit word per lane
+        if (lane < EG_MAX_ACTIONS_PER_YEAR / 4) {
+          uint32_t word = 0;
+          for (int b = 0; b < 4; b++) {
+            const uint32_t i = lane * 4 + b;
+            if (i < used) word |= (uint32_t)year_actions[i] << (8 * b);
+          }
+          ((uint32_t*)p.traj[ep].actions[y])[lane] = word;
+        }
       }
       if (p.sites) {
-        uint16_t* row = p.sites[ep].site[y];
-        for (uint32_t i = 0; i < used; i++) row[i] = year_sites[i];
-        for (uint32_t i = used; i < EG_MAX_ACTIONS_PER_YEAR; i++) row[i] = (uint16_t)EG_SITE_NONE;
+        if (lane < EG_MAX_ACTIONS_PER_YEAR / 2) {
+          uint32_t word = 0;
+          for (int b = 0; b < 2; b++) {
+            const uint32_t i = lane * 2 + b;
+            word |= (uint32_t)(i < used ? year_sites[i] : (uint16_t)EG_SITE_NONE) << (16 * b);
+          }
+          ((uint32_t*)p.sites[ep].site[y])[lane] = word;
+        }
       }
+      __syncwarp();
 
       // calculate_yearly_metrics, analysis/metrics_calculation.rs:32-175
       const EgYearRow& yr = T->year[y];
       const double usage = __ldg(&yr.usage_total);
-      const double generation = e.gen[0] + e.gen[1] + e.gen[2];
+      const double generation = gen0 + gen1 + gen2;
       const double balance = generation - usage;
-      const double net = e.co2 - e.off_amount;
+      const double net = co2 - off_amount;
       const double credit = net >= 0.0 ? 0.0 : (-net) * __ldg(&yr.carbon_price);
-      const uint32_t active = __ldg(&yr.ex_active) + e.n_gens;
-      const double opinion = active > 0 ? e.op_sum / (double)active : 1.0;
-      const double total_capital = e.gcost + e.ocost;
-      const double yearly_capital = y == 0 ? total_capital : total_capital - (e.gcost_prev + e.ocost_prev);
+      const uint32_t active = __ldg(&yr.ex_active) + n_gens;
+      const double opinion = active > 0 ? op_sum / (double)active : 1.0;
+      const double total_capital = gcost + ocost;
+      const double yearly_capital = y == 0 ? total_capital : total_capital - (gcost_prev + ocost_prev);
       const double sales = (p.energy_sales && balance > 0.0) ? (balance * 8.76) * 50000.0 : 0.0;
       const double yearly_total = yearly_capital + 0.0 + 0.0 - credit - (p.energy_sales ? sales : 0.0);
       if (y == 0) { total_cost = yearly_total; total_credit = credit; total_sales = sales; }
       else { total_cost = total_cost + yearly_total; total_credit = total_credit + credit; total_sales = total_sales + sales; }
-      if (p.yearly) {
+      if (p.yearly && lane == 0) {
         eg_year_metrics& m = p.yearly[ep].y[y];
         m.total_population = __ldg(&yr.pop_total);
         m.active_generators = active;
@@ -477,8 +661,8 @@ struct Kernel {
         m.yearly_capital_cost = yearly_capital;
         m.total_capital_cost = total_capital;
         m.inflation_factor = __ldg(&yr.inflation);
-        m.total_co2_emissions = e.co2;
-        m.total_carbon_offset = e.off_amount;
+        m.total_co2_emissions = co2;
+        m.total_carbon_offset = off_amount;
         m.net_co2_emissions = net;
         m.yearly_carbon_credit_revenue = credit;
         m.total_carbon_credit_revenue = total_credit;
@@ -509,39 +693,58 @@ struct Kernel {
         res.score = 1.0 + (cost_score * cost_weight + res.public_opinion * opinion_weight);
       }
     }
-    res.n_generators = e.n_gens;
-    res.n_offsets = e.n_offs;
+    res.n_generators = n_gens;
+    res.n_offsets = n_offs;
     res.n_deficit_actions = (uint16_t)n_def_total;
     res.n_additional_actions = (uint16_t)n_add_total;
-    res.flags = e.flags;
+    res.flags = flags;
     res.reserved = 0;
-    p.out[ep] = res;
+    if (lane == 0) p.out[ep] = res;
     if (p.traj) {
-      for (int y = 0; y < EG_NY; y++) { p.traj[ep].n_deficit[y] = n_def_year[y]; p.traj[ep].n_additional[y] = n_add_year[y]; }
+      __syncwarp();
+      uint8_t* dst = p.traj[ep].n_deficit;  // n_deficit[26] then n_additional[26] are contiguous
+      for (int i = lane; i < 2 * EG_NY; i += 32) dst[i] = counts[i];
     }
+    __syncwarp();
   }
 };
 
+template <bool REPLAY, typename NearT>
+__global__ void __launch_bounds__(32 * EG_EPISODE_WARPS) eg_episode_kernel(const __grid_constant__ EgEpisodeParams p, int slice_bytes) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ep = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (ep >= p.n) return;  // whole warps leave together
+  Warp<REPLAY, NearT> w(p, smem + (size_t)warp * slice_bytes, lane);
+  w.run(ep);
+}
+
 template <bool REPLAY>
-__global__ void __launch_bounds__(EG_EPISODE_BLOCK) eg_episode_kernel(const __grid_constant__ EgEpisodeParams p) {
-  const uint32_t ep = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ep >= p.n) return;
-  Kernel<REPLAY> k(p);
-  k.run(ep);
+cudaError_t launch(const EgEpisodeParams& p, cudaStream_t stream) {
+  if (p.n == 0) return cudaSuccess;
+  const bool wide = p.map.kmax > 12 + 1 || p.map.r2_stride > 255;  // squared cell distances do not fit a byte
+  const int near_bytes = p.map.n_sites * (wide ? 2 : 1);
+  const int slice = (kOffNear + near_bytes + 15) & ~15;
+  // as many warps per block as keep several blocks resident in the 227 KB of an SM
+  int warps = EG_EPISODE_WARPS;
+  while (warps > 1 && warps * slice > 100 * 1024) warps >>= 1;
+  const size_t smem = (size_t)warps * slice;
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  const uint32_t blocks = (p.n + warps - 1) / warps;
+  cudaError_t err;
+  if (wide) {
+    err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    eg_episode_kernel<REPLAY, uint16_t><<<blocks, 32 * warps, smem, stream>>>(p, slice);
+  } else {
+    err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    eg_episode_kernel<REPLAY, uint8_t><<<blocks, 32 * warps, smem, stream>>>(p, slice);
+  }
+  return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t eg_launch_rollout(const EgEpisodeParams& p, cudaStream_t stream) {
-  if (p.n == 0) return cudaSuccess;
-  const uint32_t blocks = (p.n + EG_EPISODE_BLOCK - 1) / EG_EPISODE_BLOCK;
-  eg_episode_kernel<false><<<blocks, EG_EPISODE_BLOCK, 0, stream>>>(p);
-  return cudaGetLastError();
-}
-
-cudaError_t eg_launch_replay(const EgEpisodeParams& p, cudaStream_t stream) {
-  if (p.n == 0) return cudaSuccess;
-  const uint32_t blocks = (p.n + EG_EPISODE_BLOCK - 1) / EG_EPISODE_BLOCK;
-  eg_episode_kernel<true><<<blocks, EG_EPISODE_BLOCK, 0, stream>>>(p);
-  return cudaGetLastError();
-}
+cudaError_t eg_launch_rollout(const EgEpisodeParams& p, cudaStream_t stream) { return launch<false>(p, stream); }
+cudaError_t eg_launch_replay(const EgEpisodeParams& p, cudaStream_t stream) { return launch<true>(p, stream); }

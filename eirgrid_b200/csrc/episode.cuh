@@ -21,7 +21,7 @@ struct EgEpisodeParams {
   double ln100;                  // ln(MAX_ACCEPTABLE_COST*100/MAX_ACCEPTABLE_COST), host libm (scoring.rs:13,32)
 };
 
-#define EG_EPISODE_BLOCK 128
+#define EG_EPISODE_WARPS 4   // episodes (warps) per block for the Irish map; fewer when the per-warp slice is large
 
 cudaError_t eg_launch_rollout(const EgEpisodeParams& p, cudaStream_t stream);
 cudaError_t eg_launch_replay(const EgEpisodeParams& p, cudaStream_t stream);

@@ -358,16 +358,23 @@ void eg_host_build_tables(const EgHostMap& m, EgHostTables* out) {
     }
   }
 
-  // ---- distance/radius factors between candidate sites (sites lie on an integer grid, so distances are exact)
+  // ---- distance/radius factors between candidate sites. Sites lie on an integer grid, so dx*dx + dy*dy of the
+  // reference's distance_to is exactly step^2 * d2 with d2 = di^2 + dj^2, and the factor is a function of d2 alone.
   const int kmax = (int)std::floor(12000.0 / m.step) + 1;
   out->kmax = kmax;
-  out->near_factor.assign((size_t)EG_N_RCLASS * kmax * kmax, -1.0);
+  int stride = 1;
+  for (int rc = 0; rc < EG_N_RCLASS; rc++) {
+    int d2 = 0;
+    while (std::sqrt((double)d2 * m.step * m.step) < kRadii[rc]) d2++;
+    out->r2_limit[rc] = d2;
+    stride = std::max(stride, d2);
+  }
+  out->r2_stride = stride;
+  out->near_factor.assign((size_t)EG_N_RCLASS * stride, 1.0);
   for (int rc = 0; rc < EG_N_RCLASS; rc++)
-    for (int di = 0; di < kmax; di++)
-      for (int dj = 0; dj < kmax; dj++) {
-        const double dx = (double)di * m.step, dy = (double)dj * m.step;
-        const double distance = std::sqrt(dx * dx + dy * dy);
-        if (distance < kRadii[rc]) out->near_factor[((size_t)rc * kmax + di) * kmax + dj] = distance / kRadii[rc];
-      }
+    for (int d2 = 0; d2 < out->r2_limit[rc]; d2++) {
+      const double distance = std::sqrt((double)d2 * m.step * m.step);
+      out->near_factor[(size_t)rc * stride + d2] = distance / kRadii[rc];
+    }
   (void)kRadius;
 }

@@ -18,7 +18,9 @@ struct EgHostTables {
   EgSmallTables small;
   std::vector<double> op_cost;       // [EG_OPC_SIZE]
   std::vector<uint32_t> pop;         // [26][S]
-  std::vector<double> near_factor;   // [6][kmax][kmax]
+  std::vector<double> near_factor;   // [6][r2_stride], by squared cell distance
+  int r2_limit[EG_N_RCLASS] = {0};
+  int r2_stride = 0;
   int kmax = 0;
 };
 

@@ -63,10 +63,12 @@ struct EgDeviceMap {      // device pointers + sizes, passed by value to the ker
   const uint16_t* order;          // [7][26][n_sites] site index
   const double* static_score;     // [7][26][n_sites] score of the site when no simulation-built plant is in range
   const double* prefix_score;     // [7][26][n_sites] score after settlements + existing plants (before new plants)
-  const double* near_factor;      // [6][kmax][kmax] distance/radius for cell offsets inside the radius, -1 outside
+  const double* near_factor;      // [6][r2_stride] distance/radius by squared cell distance d2 (valid for d2 < r2_limit[rc])
+  const int* r2_limit;            // [6] first squared cell distance that is NOT inside the penalty radius
+  int r2_stride;
   int n_sites;
   int grid_n;
-  int kmax;
+  int kmax;                       // plants farther than kmax-1 cells (in x or y) are outside every radius
 };
 
 struct EgPolicyDevice {   // weights snapshot + the per-batch constants of update_weights (learning.rs:36-55)
@@ -76,6 +78,9 @@ struct EgPolicyDevice {   // weights snapshot + the per-batch constants of updat
   double learning_rate;
   double exploration_rate;
   double relative_improvement;    // learning.rs:40-49 (0 whenever a best strategy with positive score exists)
+  // stagnation branch of sample_action (sampling.rs:190-220), evaluated per snapshot with the host libm
+  double stagnation_power;        // 1 + 2 * min(iwi / 1000, 3)
+  double scaled_sorted[EG_NY][EG_N_ACTIONS];  // weight^power in stable descending weight order
   uint32_t iwi;                   // iterations_without_improvement
   uint32_t has_count_weights;
   uint32_t noop_boost;            // learning.rs:82: best is net-zero but costs > 8 * MAX_ACCEPTABLE_COST
@@ -85,4 +90,5 @@ struct EgPolicyDevice {   // weights snapshot + the per-batch constants of updat
   uint8_t n_best_deficit[EG_NY];
   uint8_t best[EG_NY][EG_MAX_ACTIONS_PER_YEAR * 2];
   uint8_t best_deficit[EG_NY][EG_MAX_ACTIONS_PER_YEAR];
+  uint8_t sorted_idx[EG_NY][64];  // action code at each rank of scaled_sorted
 };

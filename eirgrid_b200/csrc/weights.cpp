@@ -363,6 +363,18 @@ void eg_weights_fill_policy(const eg_weights& W, EgPolicyDevice* out) {
     rel = best_score > 0.0 ? (best_score - best_score) / best_score : best_score;
   }
   out->relative_improvement = rel;
+  out->stagnation_power = 1.0 + (2.0 * std::min((double)W.iwi / 1000.0, 3.0));
+  if (W.iwi > 500) {
+    for (int y = 0; y < EG_NY; y++) {
+      int idx[EG_N_ACTIONS];
+      for (int k = 0; k < EG_N_ACTIONS; k++) idx[k] = k;
+      std::stable_sort(idx, idx + EG_N_ACTIONS, [&](int a, int b) { return W.w[y][a] > W.w[y][b]; });
+      for (int k = 0; k < EG_N_ACTIONS; k++) {
+        out->sorted_idx[y][k] = (uint8_t)idx[k];
+        out->scaled_sorted[y][k] = std::pow(W.w[y][idx[k]], out->stagnation_power);
+      }
+    }
+  }
   out->iwi = W.iwi;
   out->has_count_weights = W.has_count_weights ? 1 : 0;
   out->noop_boost = (W.has_best && W.best_metrics[0] <= 0.0 && W.best_metrics[2] > kMaxCost * 8.0) ? 1 : 0;
