@@ -14,7 +14,7 @@
 #include "suitability.cuh"
 #include "weights.hpp"
 
-static_assert(sizeof(EgPolicyDevice) == 37752, "bench.py and eirgrid_b200/_abi.py quote this size");
+static_assert(sizeof(EgPolicyDevice) == 38376, "bench.py and eirgrid_b200/_abi.py quote this size");
 static thread_local std::string g_last_error;
 int eg_fail(int code, const std::string& message) {
   g_last_error = message;
@@ -283,7 +283,7 @@ int eg_map_site_tables(eg_ctx* c, uint32_t year_index, uint32_t rclass, uint32_t
   }
   EG_CUDA(cudaStreamSynchronize(c->stream));
   if (order_sorted)
-    for (size_t i = 0; i < ns; i++) order_sorted[i] = tmp[i];
+    for (size_t i = 0; i < ns; i++) order_sorted[i] = (uint32_t)(tmp[i] >> 8) * (uint32_t)c->dmap.grid_n + (tmp[i] & 0xFFu);
   return EG_OK;
 }
 

@@ -113,7 +113,8 @@ struct Warp {
   double ocost, ocost_prev;   // same for offsets (map_handler.rs:960-962)
   double off_amount;          // calc_total_carbon_offset(year)
   uint32_t n_gens, n_offs, flags;
-  bool lw_valid, sorted_valid;
+  bool lw_valid, sorted_valid, total_valid;
+  double lw_total;
   Rng rng;
 
   __device__ Warp(const EgEpisodeParams& p_, unsigned char* slice, int lane_)
@@ -145,18 +146,26 @@ struct Warp {
     return 0.03 * __ldg(&p.map.site_opinion[site]) + __ldg(&T->op_type[y][t]) + __ldg(&p.map.op_cost[EG_OPC_INDEX(y, t, m, b)]);
   }
 
-  // Re-walk the fleet for a new year: every per-plant term depends on the year. Terms are computed one plant per
-  // lane, then folded into the accumulators in plant order (the order of the reference's iterator sums).
+  // Start of a year: re-fold the per-plant terms that depend on the year, in plant order (the order of the
+  // reference's iterator sums). Terms are computed one plant per lane and folded in sequentially by shuffle.
+  //  * capital cost re-priced at year-1 over this year's fleet continues last year's sum (the plants built this year
+  //    are appended to it), so it is carried, not recomputed;
+  //  * generation and CO2 of a simulation-built plant do not depend on the year: those sums are re-folded only when
+  //    the existing-plant prefix changed (the years the pre-existing fleet comes online, quirk Q1).
   __device__ void year_start(int y) {
     const EgYearRow& yr = T->year[y];
-    gen0 = __ldg(&yr.ex_gen[0]); gen1 = __ldg(&yr.ex_gen[1]); gen2 = __ldg(&yr.ex_gen[2]);
-    co2 = __ldg(&yr.ex_co2);
+    const bool refold = y == 0 || __ldg(&yr.prefix_changed) != 0;
+    if (refold) {
+      gen0 = __ldg(&yr.ex_gen[0]); gen1 = __ldg(&yr.ex_gen[1]); gen2 = __ldg(&yr.ex_gen[2]);
+      co2 = __ldg(&yr.ex_co2);
+    }
     op_sum = __ldg(&yr.ex_opinion_sum);
-    gcost = 0.0; gcost_prev = 0.0;
+    gcost_prev = gcost;
+    gcost = 0.0;
     const int n = p.map.grid_n;
     for (uint32_t base = 0; base < n_gens; base += 32) {
       const uint32_t i = base + lane;
-      double t_mw = 0.0, t_co2 = 0.0, t_op = 0.0, t_c = 0.0, t_cp = 0.0;
+      double t_mw = 0.0, t_co2 = 0.0, t_op = 0.0, t_c = 0.0;
       int cls = 0;
       if (i < n_gens) {
         const uint32_t g = gens[i];
@@ -166,39 +175,38 @@ struct Warp {
         t_co2 = __ldg(&T->co2[t]);
         t_op = gen_opinion(gi * n + gj, t, m, b, y);
         t_c = gen_cost(t, m, b, y);
-        if (y > 0) t_cp = gen_cost(t, m, b, y - 1);
       }
       const int cnt = min(32u, n_gens - base);
       for (int j = 0; j < cnt; j++) {
-        const double mw = shfl_f64(t_mw, j);
-        const int c = __shfl_sync(kFull, cls, j);
-        // adding +0.0 leaves the other two accumulators unchanged bit for bit
-        gen0 += c == EG_ACC_PLAIN ? mw : 0.0;
-        gen1 += c == EG_ACC_INTERMITTENT ? mw : 0.0;
-        gen2 += c == EG_ACC_STORAGE ? mw : 0.0;
-        co2 += shfl_f64(t_co2, j);
         op_sum += shfl_f64(t_op, j);
         gcost += shfl_f64(t_c, j);
-        if (y > 0) gcost_prev += shfl_f64(t_cp, j);
+        if (refold) {
+          const double mw = shfl_f64(t_mw, j);
+          const int c = __shfl_sync(kFull, cls, j);
+          // adding +0.0 leaves the other two accumulators unchanged bit for bit
+          gen0 += c == EG_ACC_PLAIN ? mw : 0.0;
+          gen1 += c == EG_ACC_INTERMITTENT ? mw : 0.0;
+          gen2 += c == EG_ACC_STORAGE ? mw : 0.0;
+          co2 += shfl_f64(t_co2, j);
+        }
       }
     }
-    ocost = 0.0; ocost_prev = 0.0; off_amount = 0.0;
+    ocost_prev = ocost;
+    ocost = 0.0; off_amount = 0.0;
     for (uint32_t base = 0; base < n_offs; base += 32) {
       const uint32_t i = base + lane;
-      double t_a = 0.0, t_c = 0.0, t_cp = 0.0;
+      double t_a = 0.0, t_c = 0.0;
       if (i < n_offs) {
         const uint32_t o = offs[i];
         const int ot = o & 3, m = (o >> 2) & 3, b = (o >> 4) & 0x1F;
         const double maturity = __ldg(&T->natural_offset[ot]) ? __ldg(&T->maturity[y - b]) : 1.0;
         t_a = __ldg(&T->off_amount[ot]) * maturity;
         t_c = off_cost(ot, m, y);
-        if (y > 0) t_cp = off_cost(ot, m, y - 1);
       }
       const int cnt = min(32u, n_offs - base);
       for (int j = 0; j < cnt; j++) {
         off_amount += shfl_f64(t_a, j);
         ocost += shfl_f64(t_c, j);
-        if (y > 0) ocost_prev += shfl_f64(t_cp, j);
       }
     }
   }
@@ -237,8 +245,11 @@ struct Warp {
       bool live = k < ns && s_static > 0.0 && !(s_static < best_score);
       double score = s_static;
       int site = 0x7FFFFFFF;
+      int si = 0, sj = 0;
       if (live) {
-        site = __ldg(&order[k]);
+        const int packed = __ldg(&order[k]);  // (i << 8) | j of the candidate site
+        si = packed >> 8; sj = packed & 0xFF;
+        site = si * n + sj;
         const int d2n = nearest[site];
         if (d2n < r2lim) {
           // in range of at least one new plant: all factors are < 1 and rounding is monotone, so the product with
@@ -250,7 +261,6 @@ struct Warp {
           if (bound < best_score) {
             live = false;
           } else {
-            const int si = site / n, sj = site - si * n;
             double sc = pre;
             for (uint32_t g = 0; g < n_gens; g++) {  // plant order == multiplication order of the reference
               const uint32_t pk = gens[g];
@@ -289,15 +299,18 @@ struct Warp {
     if (lane == 0) gens[n_gens] = pack_gen(gi, gj, t, m, y);
     n_gens++;
     // nearest-plant map: squared cell distance to the closest plant built in this episode
-    const int R = p.map.kmax - 1, side = 2 * R + 1, cells = side * side;
-    const int far = (int)kFar;
-    for (int c = lane; c < cells; c += 32) {
-      const int di = c / side - R, dj = c - (c / side) * side - R;
-      const int i = gi + di, j = gj + dj;
-      if (i >= 0 && i < n && j >= 0 && j < n) {
-        const int d2 = min(di * di + dj * dj, far);
-        NearT* cell = &nearest[i * n + j];
-        if (d2 < (int)*cell) *cell = (NearT)d2;
+    const int R = p.map.kmax - 1, r2max = p.map.r2_stride;
+    for (int dj0 = -R; dj0 <= R; dj0 += 32) {  // one row of the (2R+1)^2 neighbourhood per step, one cell per lane
+      const int dj = dj0 + lane, j = gj + dj;
+      const bool col_ok = dj <= R && j >= 0 && j < n;
+      for (int di = -R; di <= R; di++) {
+        const int i = gi + di;
+        if (i < 0 || i >= n) continue;
+        const int d2 = di * di + dj * dj;
+        if (col_ok && d2 < r2max) {  // only cells inside the largest penalty radius can matter
+          NearT* cell = &nearest[i * n + j];
+          if (d2 < (int)*cell) *cell = (NearT)d2;
+        }
       }
     }
     __syncwarp();
@@ -373,11 +386,12 @@ struct Warp {
       else if (combined < 0.0 && k == EG_ACT_DO_NOTHING && p.policy->noop_boost) lw[k] = fmin(lw[k] * (1.0 + lr * 0.2), kMaxWeight);
     }
     sorted_valid = false;
+    total_valid = false;
     __syncwarp();
   }
 
   // ---- sampling (canonical key order replaces HashMap iteration order) ---------------------------------------
-  __device__ int smart_fallback_action(int y) {  // sampling.rs:445-490
+  __device__ __noinline__ int smart_fallback_action(int y) {  // sampling.rs:445-490
     const int year = EG_BASE_YEAR + y;
     const uint32_t storage = year < 2035 ? 10 : 20;
     const uint32_t offset = year < 2035 ? 5 : (year < 2045 ? 15 : 25);
@@ -393,7 +407,7 @@ struct Warp {
     }
     return kBattery100;
   }
-  __device__ int smart_deficit_fallback_action() {  // sampling.rs:492-528 ((0.07*0.5) as u32 == 0, (0.06*0.5*100) as u32 == 3)
+  __device__ __noinline__ int smart_deficit_fallback_action() {  // sampling.rs:492-528 ((0.07*0.5) as u32 == 0, (0.06*0.5*100) as u32 == 3)
     const int act[6] = {3 * 8, 3 * 12, 3 * 7, 3 * 0, 3 * 1, 3 * 4};
     const uint32_t wt[6] = {30, 30, 20, 10, 0, 3};
     uint32_t choice = rng.index(93);
@@ -411,8 +425,13 @@ struct Warp {
     }
     const bool explore = rng.f64() < p.policy->exploration_rate;
     if (explore) return deficit_key_action((int)rng.index(14));
-    double total = 0.0;
-    for (int k = 0; k < 14; k++) total += dweight(y, k);
+    double total;
+    if (lw_valid) {
+      total = 0.0;
+      for (int k = 0; k < 14; k++) total += ldw[k];
+    } else {
+      total = __ldg(&p.policy->dw_total[y]);  // same left-to-right sum, done once per snapshot on the host
+    }
     if (total <= 0.0) return kGasPeaker100;
     double rv = rng.f64() * total;
     for (int k = 0; k < 14; k++) {
@@ -426,8 +445,7 @@ struct Warp {
     if (max_possible == 0) return 0;
     const double random_val = rng.f64();
     if (p.policy->has_count_weights) {
-      double total = 0.0;
-      for (int c = 0; c < EG_N_COUNT_KEYS; c++) total += __ldg(&p.policy->cw[y][c]);
+      const double total = __ldg(&p.policy->cw_total[y]);
       if (total <= 0.0) return 0;
       double rc = random_val * total;
       for (int c = 0; c < EG_N_COUNT_KEYS; c++) {
@@ -445,7 +463,7 @@ struct Warp {
 
   // stagnation branch of sample_action (sampling.rs:190-220) for rows edited in this episode: stable descending
   // sort by rank counting and the powers, both spread over the lanes
-  __device__ void sort_local(double power) {
+  __device__ __noinline__ void sort_local(double power) {
     for (int k = lane; k < EG_N_ACTIONS; k += 32) {
       const double wk = lw[k];
       int rank = 0;
@@ -470,8 +488,17 @@ struct Warp {
     const double cur_eps = iwi > 100 ? eps * (1.0 / (1.0 + 0.01 * (double)iwi)) : eps;
     const bool explore = rng.f64() < cur_eps;
     if (explore) return (int)rng.index(EG_N_ACTIONS);
-    double total = 0.0;
-    for (int k = 0; k < EG_N_ACTIONS; k++) total += weight(y, k);
+    double total;
+    if (lw_valid) {
+      if (!total_valid) {
+        lw_total = 0.0;
+        for (int k = 0; k < EG_N_ACTIONS; k++) lw_total += lw[k];
+        total_valid = true;
+      }
+      total = lw_total;
+    } else {
+      total = __ldg(&p.policy->w_total[y]);
+    }
     if (total <= 0.0) return kGasPeaker100;
     if (iwi > 500) {
       const double* sc;
@@ -512,6 +539,7 @@ struct Warp {
     rng.k0 = (uint32_t)p.seed; rng.k1 = (uint32_t)(p.seed >> 32);
     rng.e0 = (uint32_t)id; rng.e1 = (uint32_t)(id >> 32); rng.draw = 0;
     n_gens = 0; n_offs = 0; flags = 0;
+    gcost = 0.0; ocost = 0.0; gen0 = gen1 = gen2 = 0.0; co2 = 0.0;
     for (int i = lane; i < p.map.n_sites; i += 32) nearest[i] = kFar;
     __syncwarp();
     const eg_traj* in = REPLAY ? p.replay_in + ep : nullptr;
@@ -523,6 +551,7 @@ struct Warp {
       year_start(y);
       lw_valid = false;
       sorted_valid = false;
+      total_valid = false;
       State cur = state(y);
       bool deficit_mode = cur.balance < 0.0;                 // simulation.rs:137
       const State initial = cur;                             // simulation.rs:341-356
@@ -710,7 +739,7 @@ struct Warp {
 };
 
 template <bool REPLAY, typename NearT>
-__global__ void __launch_bounds__(32 * EG_EPISODE_WARPS) eg_episode_kernel(const __grid_constant__ EgEpisodeParams p, int slice_bytes) {
+__global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, 4) eg_episode_kernel(const __grid_constant__ EgEpisodeParams p, int slice_bytes) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ep = blockIdx.x * (blockDim.x >> 5) + warp;

@@ -356,6 +356,11 @@ void eg_host_build_tables(const EgHostMap& m, EgHostTables* out) {
       row.ex_opinion_sum += 0.03 * settle_op[g] + 0.12 * type_opinion(t, y) + 0.82 * cost_opinion(cost, y);
       row.ex_active++;
     }
+    row.prefix_changed = 1;
+    if (y > 0) {
+      const EgYearRow& prev = T.year[y - 1];
+      row.prefix_changed = std::memcmp(prev.ex_gen, row.ex_gen, sizeof(row.ex_gen)) != 0 || std::memcmp(&prev.ex_co2, &row.ex_co2, sizeof(double)) != 0;
+    }
   }
 
   // ---- distance/radius factors between candidate sites. Sites lie on an integer grid, so dx*dx + dy*dy of the

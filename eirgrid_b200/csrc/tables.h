@@ -26,6 +26,8 @@ struct EgYearRow {       // one per simulated year
   double ex_opinion_sum; // calculate_average_opinion prefix                  metrics_calculation.rs:7-30
   uint32_t ex_active;    // active existing plants
   uint32_t pop_total;    // calc_total_population                             map_handler.rs:813-817
+  uint32_t prefix_changed;  // ex_gen / ex_co2 differ from the previous year's (existing plants came online)
+  uint32_t pad;
 };
 
 struct EgSmallTables {   // ~35 KB, read-mostly, L1/L2 resident
@@ -60,7 +62,7 @@ struct EgDeviceMap {      // device pointers + sizes, passed by value to the ker
   const double* site_opinion;     // [n_sites] avg_settlement_opinion of a plant on the site  map_handler.rs:931-941
   const double* coast_factor;     // [n_sites] 1/(1+min_coast_distance/5000)                  metal_location_search.rs:157-162
   // placement lists, sorted by static score (descending, ties by scan order), per (pclass, year)
-  const uint16_t* order;          // [7][26][n_sites] site index
+  const uint16_t* order;          // [7][26][n_sites] candidate site as (i << 8) | j
   const double* static_score;     // [7][26][n_sites] score of the site when no simulation-built plant is in range
   const double* prefix_score;     // [7][26][n_sites] score after settlements + existing plants (before new plants)
   const double* near_factor;      // [6][r2_stride] distance/radius by squared cell distance d2 (valid for d2 < r2_limit[rc])
@@ -80,6 +82,9 @@ struct EgPolicyDevice {   // weights snapshot + the per-batch constants of updat
   double relative_improvement;    // learning.rs:40-49 (0 whenever a best strategy with positive score exists)
   // stagnation branch of sample_action (sampling.rs:190-220), evaluated per snapshot with the host libm
   double stagnation_power;        // 1 + 2 * min(iwi / 1000, 3)
+  double w_total[EG_NY];          // left-to-right sums of the rows, as sample_action / sample_deficit_action /
+  double dw_total[EG_NY];         // sample_additional_actions compute them (sampling.rs:182,352-355,406)
+  double cw_total[EG_NY];
   double scaled_sorted[EG_NY][EG_N_ACTIONS];  // weight^power in stable descending weight order
   uint32_t iwi;                   // iterations_without_improvement
   uint32_t has_count_weights;

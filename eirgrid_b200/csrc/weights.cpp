@@ -364,6 +364,13 @@ void eg_weights_fill_policy(const eg_weights& W, EgPolicyDevice* out) {
   }
   out->relative_improvement = rel;
   out->stagnation_power = 1.0 + (2.0 * std::min((double)W.iwi / 1000.0, 3.0));
+  for (int y = 0; y < EG_NY; y++) {
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int k = 0; k < EG_N_ACTIONS; k++) a += W.w[y][k];
+    for (int k = 0; k < 14; k++) b += W.dw[y][k];  // AddGenerator keys only (sampling.rs:352-355)
+    for (int k = 0; k < EG_N_COUNT_KEYS; k++) c += W.cw[y][k];
+    out->w_total[y] = a; out->dw_total[y] = b; out->cw_total[y] = c;
+  }
   if (W.iwi > 500) {
     for (int y = 0; y < EG_NY; y++) {
       int idx[EG_N_ACTIONS];
