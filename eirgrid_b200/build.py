@@ -11,10 +11,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libeirgrid_b200.so")
+LIB = os.path.join(HERE, os.environ.get("EIRGRID_LIB_NAME", "libeirgrid_b200.so"))
 SOURCES = ["engine.cu", "episode.cu", "site_tables.cu", "stats.cu", "suitability.cu", "weights.cpp", "host_tables.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
+EXTRA = os.environ.get("EIRGRID_NVCC_EXTRA", "").split()
+FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall", "-Xptxas", "-v"]
 
 
@@ -30,7 +31,7 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build", os.path.splitext(os.path.basename(LIB))[0])
     os.makedirs(objdir, exist_ok=True)
     objs = []
     log = []

@@ -25,8 +25,15 @@
 //    survivors multiply their factors in plant order. The walk stops once static scores fall below the best found.
 //  * Compiled with --fmad=false: + - * / sqrt are the reference's IEEE operations, no contraction.
 #include "episode.cuh"
+#include <algorithm>
 
 namespace {
+
+#ifdef EG_NOINLINE_HELPERS
+#define EG_HELPER_INLINE __noinline__
+#else
+#define EG_HELPER_INLINE __forceinline__
+#endif
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kBattery100 = 3 * 12;   // AddGenerator(BatteryStorage, 100 %), simulation.rs:376
@@ -49,7 +56,7 @@ constexpr int kOffNear = (kOffCounts + 2 * EG_NY + 15) & ~15;   // nearest-plant
 static_assert(kOffGens % 8 == 0 && kOffOffs % 4 == 0 && kOffYearSites % 4 == 0 && kOffYearActions % 4 == 0, "alignment");
 
 // ---- Philox4x32-10, counter = (episode lo, episode hi, draw, stream 0), key = seed ------------------------
-__device__ __forceinline__ unsigned long long philox_u64(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+__device__ EG_HELPER_INLINE unsigned long long philox_u64(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
 #pragma unroll
   for (int r = 0; r < 10; r++) {
     uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -73,7 +80,7 @@ struct State {  // ActionResult, ai/metrics/simulation_metrics.rs:14-19
 };
 
 // evaluate_action_impact(.., None), scoring.rs:60-84
-__device__ __forceinline__ double action_impact(const State& cur, const State& nw) {
+__device__ EG_HELPER_INLINE double action_impact(const State& cur, const State& nw) {
   if (cur.net > 0.0) return (cur.net - nw.net) / fmax(fabs(cur.net), 1.0);
   double cost_change = nw.cost - cur.cost;
   double cost_improvement = -cost_change / fmax(fabs(cur.cost), 1.0);
@@ -211,7 +218,7 @@ struct Warp {
     }
   }
 
-  __device__ __forceinline__ State state(int y) const {  // simulation.rs:122-135
+  __device__ EG_HELPER_INLINE State state(int y) const {  // simulation.rs:122-135
     State s;
     s.net = co2 - off_amount;
     const uint32_t cnt = __ldg(&T->year[y].ex_active) + n_gens;
@@ -355,8 +362,8 @@ struct Warp {
     return -1;  // CoalPlant has no deficit key
   }
   __device__ static int deficit_key_action(int k) {
-    const int type_of_key[14] = {8, 7, 12, 11, 9, 0, 1, 4, 10, 5, 2, 3, 13, 14};
-    return 3 * type_of_key[k];
+    // type of deficit key k (weights/core.rs:130-149), 4 bits each: {8,7,12,11,9,0,1,4,10,5,2,3,13,14}
+    return 3 * (int)((0xED325A4109BC78ull >> (4 * k)) & 0xF);
   }
 
   __device__ void update_deficit_weights(int y, int action, double improvement) {  // deficit.rs:82-135
@@ -739,7 +746,7 @@ struct Warp {
 };
 
 template <bool REPLAY, typename NearT>
-__global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, 4) eg_episode_kernel(const __grid_constant__ EgEpisodeParams p, int slice_bytes) {
+__global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) eg_episode_kernel(const __grid_constant__ EgEpisodeParams p, int slice_bytes) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ep = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -760,14 +767,19 @@ cudaError_t launch(const EgEpisodeParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)warps * slice;
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   const uint32_t blocks = (p.n + warps - 1) / warps;
+  // shared-memory carveout: room for as many blocks as the register budget allows, the rest stays L1
+  const int resident = (int)std::min<size_t>(EG_EPISODE_MIN_BLOCKS * (EG_EPISODE_WARPS / warps), (227 * 1024) / (smem + 1024));
+  const int carveout = std::min(100, (int)((resident * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
   cudaError_t err;
   if (wide) {
     err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
+    cudaFuncSetAttribute(eg_episode_kernel<REPLAY, uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
     eg_episode_kernel<REPLAY, uint16_t><<<blocks, 32 * warps, smem, stream>>>(p, slice);
   } else {
     err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
+    cudaFuncSetAttribute(eg_episode_kernel<REPLAY, uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
     eg_episode_kernel<REPLAY, uint8_t><<<blocks, 32 * warps, smem, stream>>>(p, slice);
   }
   return cudaGetLastError();

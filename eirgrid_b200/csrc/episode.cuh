@@ -21,7 +21,12 @@ struct EgEpisodeParams {
   double ln100;                  // ln(MAX_ACCEPTABLE_COST*100/MAX_ACCEPTABLE_COST), host libm (scoring.rs:13,32)
 };
 
+#ifndef EG_EPISODE_WARPS
 #define EG_EPISODE_WARPS 4   // episodes (warps) per block for the Irish map; fewer when the per-warp slice is large
+#endif
+#ifndef EG_EPISODE_MIN_BLOCKS
+#define EG_EPISODE_MIN_BLOCKS 7  // register cap 65536 / (128 threads * 7) = 72; measured best of 4..8 on B200
+#endif
 
 cudaError_t eg_launch_rollout(const EgEpisodeParams& p, cudaStream_t stream);
 cudaError_t eg_launch_replay(const EgEpisodeParams& p, cudaStream_t stream);
