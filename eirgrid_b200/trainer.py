@@ -22,6 +22,34 @@ def _torch():
     return torch
 
 
+REC_BYTES = 16 + _abi.RESULT_DTYPE.itemsize + _abi.TRAJ_DTYPE.itemsize  # [score f64 | global id i64 | eg_result | eg_traj]
+
+
+def pack_record(score, global_index, result, traj):
+    """Per-rank candidate for the batch winner as a flat uint8 array."""
+    rec = np.zeros(REC_BYTES, np.uint8)
+    rec[0:8] = np.frombuffer(np.float64(score).tobytes(), np.uint8)
+    rec[8:16] = np.frombuffer(np.int64(global_index).tobytes(), np.uint8)
+    rb = _abi.RESULT_DTYPE.itemsize
+    rec[16:16 + rb] = np.frombuffer(np.ascontiguousarray(result).tobytes(), np.uint8)
+    rec[16 + rb:] = np.frombuffer(np.ascontiguousarray(traj).tobytes(), np.uint8)
+    return rec
+
+
+def combine_and_apply(weights, stats_sum, all_records, n_total, first_episode):
+    """Host side of the exchange step, identical on every rank: pick the batch winner among the per-rank
+    candidates (highest score, lowest episode id) and apply the summed statistics to the weights.
+    stats_sum: int64[STATS_WORDS] already summed over ranks; all_records: uint8[world, REC_BYTES]."""
+    rec = np.ascontiguousarray(all_records).reshape(-1, REC_BYTES)
+    scores = rec[:, 0:8].copy().view(np.float64).ravel()
+    gidx = rec[:, 8:16].copy().view(np.int64).ravel()
+    win = int(np.lexsort((gidx, -scores))[0])
+    rb = _abi.RESULT_DTYPE.itemsize
+    best_result = rec[win, 16:16 + rb].copy().view(_abi.RESULT_DTYPE)
+    best_traj = rec[win, 16 + rb:].copy().view(_abi.TRAJ_DTYPE)
+    return weights.apply_stats(np.asarray(stats_sum), n_total, best_result, best_traj, int(gidx[win] - first_episode))
+
+
 class BatchTrainer:
     def __init__(self, episodes_per_gpu, seed=1, device=None, cfg=None, weights=None, asset_dir=None, map_arrays=None,
                  distributed=None, want_sites=False):
@@ -56,7 +84,7 @@ class BatchTrainer:
         self.d_best_score = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.d_best_index = torch.zeros(1, dtype=torch.int64, device=self.device)
         # per-rank candidate record: [score f64 | global index i64 | eg_result | eg_traj]
-        self.rec_bytes = 16 + _abi.RESULT_DTYPE.itemsize + _abi.TRAJ_DTYPE.itemsize
+        self.rec_bytes = REC_BYTES
         self.d_rec = torch.zeros(self.rec_bytes, dtype=u8, device=self.device)
         self.d_all_rec = torch.zeros(self.world * self.rec_bytes, dtype=u8, device=self.device)
         self.h_stats = torch.zeros(_abi.STATS_WORDS, dtype=torch.int64).pin_memory()
@@ -113,18 +141,8 @@ class BatchTrainer:
             self.h_stats.copy_(self.d_stats, non_blocking=True)
             self.h_all_rec.copy_(self.d_all_rec, non_blocking=True)
         self.stream.synchronize()
-        rec = self.h_all_rec.numpy().reshape(self.world, self.rec_bytes)
-        scores = rec[:, 0:8].copy().view(np.float64).ravel()
-        gidx = rec[:, 8:16].copy().view(np.int64).ravel()
-        # batch winner: highest score, lowest episode id among ties (== first in episode order)
-        order = np.lexsort((gidx, -scores))
-        win = int(order[0])
-        rb = _abi.RESULT_DTYPE.itemsize
-        best_result = rec[win, 16:16 + rb].copy().view(_abi.RESULT_DTYPE)
-        best_traj = rec[win, 16 + rb:].copy().view(_abi.TRAJ_DTYPE)
         n_total = self.n * self.world
-        st = self.weights.apply_stats(self.h_stats.numpy(), n_total, best_result, best_traj,
-                                      int(gidx[win] - self.next_episode))
+        st = combine_and_apply(self.weights, self.h_stats.numpy(), self.h_all_rec.numpy(), n_total, self.next_episode)
         self.next_episode += n_total
         self.last_stats = st
         return st

@@ -1,0 +1,81 @@
+"""GPU tests of the batch-synchronous update: statistics kernel vs its numpy restatement, BatchTrainer steps."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import stats_ref
+from eirgrid_b200 import _abi, _lib
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ASSETS = os.path.join(ROOT, "tests", "golden", "ireland_map")
+
+
+def _best_lists(w):
+    has, nb, b, nd, d = w.best()
+    return [b[y, :nb[y]].tolist() for y in range(26)], [d[y, :nd[y]].tolist() for y in range(26)]
+
+
+@pytest.mark.parametrize("iwi", [0, 40, 900])
+def test_stats_kernel_matches_numpy(gpu_ctx, oracle_world, iwi):
+    import torch
+    n = 300
+    gw = _lib.Weights()
+    res0, traj0, _, _ = oracle_world.rollout(O.Weights(), 32, seed=41)
+    gw.update(res0, traj0)
+    t = gw.table()
+    t.iterations_without_improvement = iwi
+    gw.set_table(t)
+    res, traj, _, _ = gpu_ctx.rollout(gw, n, seed=42)
+    dev = torch.device("cuda", 0)
+    d_res = torch.from_numpy(res.view(np.uint8).copy()).to(dev)
+    d_traj = torch.from_numpy(traj.view(np.uint8).copy()).to(dev)
+    d_stats = torch.zeros(_abi.STATS_WORDS, dtype=torch.int64, device=dev)
+    d_bs = torch.zeros(1, dtype=torch.float64, device=dev)
+    d_bi = torch.zeros(1, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    gpu_ctx.weights_upload(gw)
+    gpu_ctx.update_stats_device(gw, n, d_res, d_traj, d_stats, d_bs, d_bi)
+    gpu_ctx.sync()
+    got = d_stats.cpu().numpy()
+    consts = stats_ref.contrast_consts(t, stats_ref.default_score(*list(t.best_metrics)[:3]))
+    best, best_def = _best_lists(gw)
+    exp, scores = stats_ref.batch_stats(res, traj, consts, best, best_def)
+    # occurrence counts and pass counts are integers: exact
+    assert got[0] == exp[0] == n and got[1] == exp[1]
+    g = got[stats_ref.HEADER:].reshape(26, stats_ref.YEAR_STRIDE)
+    e = exp[stats_ref.HEADER:].reshape(26, stats_ref.YEAR_STRIDE)
+    assert np.array_equal(g[:, 122:], e[:, 122:])
+    # summed fixed-point log factors: device log()/pow() may differ from libm in the last bit -> <= 1 unit per term
+    assert np.abs(g[:, :122] - e[:, :122]).max() <= n * 40
+    assert ((g[:, :122] != 0) == (e[:, :122] != 0)).all()
+    k = int(np.lexsort((np.arange(n), -scores))[0])
+    assert int(d_bi.item()) == k and abs(float(d_bs.item()) - scores[k]) <= 1e-12 * scores[k]
+
+
+def test_trainer_steps_learn_and_are_deterministic():
+    from eirgrid_b200 import trainer as T
+    tr = T.BatchTrainer(4096, seed=7, device=0, asset_dir=ASSETS)
+    s1 = tr.step()
+    assert s1.n_episodes == 4096 and s1.n_improvements == 1 and s1.best_score > 1.0
+    t1 = bytes(tr.weights.table())
+    res, traj = tr.fetch_results()
+    assert (res["flags"] == 0).all() and (res["power_reliability"] == 1.0).all()
+    # the stored best strategy is the batch winner's record
+    k = s1.batch_best_episode
+    has, nb, b, nd, d = tr.weights.best()
+    for y in range(26):
+        n = int(traj[k]["n_deficit"][y]) + int(traj[k]["n_additional"][y])
+        assert nb[y] == n and b[y, :n].tolist() == traj[k]["actions"][y, :n].tolist()
+    s2 = tr.step()
+    assert tr.weights.table().iteration_count == 8192
+    assert s2.best_score >= s1.best_score
+    w = tr.weights.table().arrays()[0]
+    assert w.min() >= 0.0001 and w.max() <= 0.999
+    tr.close()
+    tr2 = T.BatchTrainer(4096, seed=7, device=0, asset_dir=ASSETS)
+    tr2.step()
+    assert bytes(tr2.weights.table()) == t1
+    tr2.close()
