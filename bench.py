@@ -180,6 +180,7 @@ def main():
         tr.launch_rollout(first_episode=(k * world + rank) * args.episodes)
         tr.launch_stats()
         tr.reduce_stats()
+        tr.warm_exchange()  # first-use costs of the small torch ops / collectives of step(), weights untouched
     barrier()
 
     with ClockSampler(local) as clocks:

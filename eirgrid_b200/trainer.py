@@ -125,6 +125,19 @@ class BatchTrainer:
             with _torch().cuda.stream(self.stream):
                 self.dist.all_reduce(self.d_stats, op=self.dist.ReduceOp.SUM)
 
+    def warm_exchange(self):
+        """Run the gather / copy part of step() once without applying anything (warm-up)."""
+        torch = _torch()
+        self._pack_best()
+        with torch.cuda.stream(self.stream):
+            if self.dist and self.world > 1:
+                self.dist.all_gather_into_tensor(self.d_all_rec, self.d_rec)
+            else:
+                self.d_all_rec.copy_(self.d_rec)
+            self.h_stats.copy_(self.d_stats, non_blocking=True)
+            self.h_all_rec.copy_(self.d_all_rec, non_blocking=True)
+        self.stream.synchronize()
+
     def step(self):
         """One training batch through the public path: weights in from the host, update statistics back."""
         torch = _torch()
