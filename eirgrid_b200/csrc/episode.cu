@@ -9,31 +9,31 @@
 //   update_weights / update_deficit_weights (episode-local)     weights/learning.rs:21-88, weights/deficit.rs:82-135
 //   score_metrics                                               ai/metrics/scoring.rs:5-45
 //
-// Design (DESIGN.md §kernel).
+// Design (DESIGN.md §4.1).
 //  * Every float sum/product of the reference runs over Vec<Generator> in insertion order with the pre-existing
-//    plants first. The warp keeps the episode's scalar state replicated in every lane (uniform control flow, no
-//    broadcasts) and adds terms in that same order, so roundings are the reference's; the existing-plant prefix of
-//    each accumulator and everything needing pow/exp is tabulated per year on the host. Per-plant TERMS are computed
-//    32 at a time across the lanes and folded in sequentially by shuffle.
-//  * Episode state that is indexed dynamically lives in shared memory, one slice per warp: the list of plants and
-//    offsets built so far, this year's private copy of the weight rows, and a per-candidate-site map of the squared
-//    cell distance to the nearest plant built in this episode.
+//    plants first. The warp keeps the episode's scalar state replicated in every lane (uniform control flow) and adds
+//    terms in that same order, so roundings are the reference's; the existing-plant prefix of each accumulator and
+//    everything needing pow/exp is tabulated per year on the host. Per-plant TERMS are computed 32 at a time across
+//    the lanes, staged in shared memory and folded in sequentially from broadcast reads.
+//  * Episode state that is indexed dynamically lives in shared memory, one slice per warp, addressed through the
+//    shared window (LDS/STS, never generic loads): the list of plants and offsets built so far, this year's private
+//    copy of the weight rows, and a per-candidate-site map of the squared cell distance to the nearest plant built
+//    in this episode.
 //  * The 100x100 placement scan becomes a walk, 32 candidates per step, down a per-(class, year) list of sites sorted
 //    by static score. A site farther than the penalty radius from every new plant keeps its static score. A site in
 //    range can only lose score, and (static prefix) x (factor of its nearest new plant) is an exact upper bound of
-//    its score (rounding is monotone), so most in-range sites are rejected without touching the plant list; the few
-//    survivors multiply their factors in plant order. The walk stops once static scores fall below the best found.
+//    its score (rounding is monotone). In-range sites of a step are examined best-bound-first: the lanes compute the
+//    factors of 32 PLANTS of one site at a time and only the in-range factors are multiplied in, in plant order;
+//    every evaluation raises the running best and prunes the remaining candidates by their bounds. The walk stops
+//    once static scores fall below the best found.
+//  * Philox draws are produced 32 at a time (lane l computes draw base+l) and handed out by shuffle.
 //  * Compiled with --fmad=false: + - * / sqrt are the reference's IEEE operations, no contraction.
 #include "episode.cuh"
 #include <algorithm>
 
-namespace {
+extern __shared__ __align__(16) unsigned char smem[];  // dynamic shared memory of the episode kernels: one slice per warp
 
-#ifdef EG_NOINLINE_HELPERS
-#define EG_HELPER_INLINE __noinline__
-#else
-#define EG_HELPER_INLINE __forceinline__
-#endif
+namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kBattery100 = 3 * 12;   // AddGenerator(BatteryStorage, 100 %), simulation.rs:376
@@ -45,18 +45,20 @@ constexpr double kMaxAcceptableEmissions = 1000000.0;        // config/constants
 // ---- per-warp shared-memory slice --------------------------------------------------------------------------
 constexpr int kOffLw = 0;                                       // double[61]  this year's regular weights
 constexpr int kOffLdw = kOffLw + 8 * EG_N_ACTIONS;              // double[15]  this year's deficit weights
-constexpr int kOffScaled = kOffLdw + 8 * EG_N_DEFICIT_KEYS;     // double[61]  weights^power in sorted order
-constexpr int kOffGens = kOffScaled + 8 * EG_N_ACTIONS;         // uint32[EG_MAX_NEW_GENERATORS]
+constexpr int kOffScratch = kOffLdw + 8 * EG_N_DEFICIT_KEYS;    // double2[32] fold staging | double[61] + uint8[64] sorted row
+constexpr int kScratchBytes = 8 * EG_N_ACTIONS + 64;            // 552 >= 512
+constexpr int kOffSortIdx = kOffScratch + 8 * EG_N_ACTIONS;     // uint8[64] (inside the scratch area)
+constexpr int kOffGens = kOffScratch + kScratchBytes;           // uint32[EG_MAX_NEW_GENERATORS]
 constexpr int kOffOffs = kOffGens + 4 * EG_MAX_NEW_GENERATORS;  // uint16[EG_MAX_OFFSETS]
 constexpr int kOffYearSites = kOffOffs + 2 * EG_MAX_OFFSETS;    // uint16[40]
 constexpr int kOffYearActions = kOffYearSites + 2 * EG_MAX_ACTIONS_PER_YEAR;  // uint8[40]
-constexpr int kOffSortIdx = kOffYearActions + EG_MAX_ACTIONS_PER_YEAR;        // uint8[64]
-constexpr int kOffCounts = kOffSortIdx + 64;                    // uint8[26] deficit + uint8[26] additional
+constexpr int kOffCounts = kOffYearActions + EG_MAX_ACTIONS_PER_YEAR;         // uint8[26] deficit + uint8[26] additional
 constexpr int kOffNear = (kOffCounts + 2 * EG_NY + 15) & ~15;   // nearest-plant map, n_sites entries
-static_assert(kOffGens % 8 == 0 && kOffOffs % 4 == 0 && kOffYearSites % 4 == 0 && kOffYearActions % 4 == 0, "alignment");
+static_assert(kOffScratch % 16 == 0 && kOffGens % 8 == 0 && kOffOffs % 4 == 0 && kOffYearSites % 4 == 0 && kOffYearActions % 4 == 0, "alignment");
 
 // ---- Philox4x32-10, counter = (episode lo, episode hi, draw, stream 0), key = seed ------------------------
-__device__ EG_HELPER_INLINE unsigned long long philox_u64(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+__device__ __noinline__ unsigned long long philox_u64(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2) {
+  uint32_t c3 = 0u;
 #pragma unroll
   for (int r = 0; r < 10; r++) {
     uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -68,19 +70,12 @@ __device__ EG_HELPER_INLINE unsigned long long philox_u64(uint32_t k0, uint32_t 
   return (unsigned long long)c0 | ((unsigned long long)c1 << 32);
 }
 
-struct Rng {
-  uint32_t k0, k1, e0, e1, draw;
-  __device__ __forceinline__ unsigned long long u64() { return philox_u64(k0, k1, e0, e1, draw++, 0u); }
-  __device__ __forceinline__ double f64() { return (double)(u64() >> 11) * (1.0 / 9007199254740992.0); }
-  __device__ __forceinline__ uint32_t index(uint32_t n) { return (uint32_t)__umul64hi(u64(), (unsigned long long)n); }
-};
-
 struct State {  // ActionResult, ai/metrics/simulation_metrics.rs:14-19
   double net, opinion, balance, cost;
 };
 
 // evaluate_action_impact(.., None), scoring.rs:60-84
-__device__ EG_HELPER_INLINE double action_impact(const State& cur, const State& nw) {
+__device__ __forceinline__ double action_impact(const State& cur, const State& nw) {
   if (cur.net > 0.0) return (cur.net - nw.net) / fmax(fabs(cur.net), 1.0);
   double cost_change = nw.cost - cur.cost;
   double cost_improvement = -cost_change / fmax(fabs(cur.cost), 1.0);
@@ -97,22 +92,78 @@ __device__ __forceinline__ uint32_t pack_gen(int gi, int gj, int t, int m, int b
   return (uint32_t)gi | ((uint32_t)gj << 8) | ((uint32_t)t << 16) | ((uint32_t)m << 20) | ((uint32_t)b << 22);
 }
 
+// sampling.rs:445-490 / 492-528: the fixed fallback tables (replay mode without a stored action)
+__device__ __noinline__ int smart_fallback_pick(int y, uint32_t choice) {
+  const int year = EG_BASE_YEAR + y;
+  const uint32_t storage = year < 2035 ? 10 : 20;
+  const uint32_t offset = year < 2035 ? 5 : (year < 2045 ? 15 : 25);
+  const uint32_t gas = year < 2035 ? 15 : (year < 2045 ? 10 : 5);
+  if (choice < 15) return 3 * 0;
+  choice -= 15;
+  if (choice < 10) return 3 * 1;
+  choice -= 10;
+  if (choice < 15) return 3 * 4;
+  choice -= 15;
+  if (choice < storage) return 3 * 12;
+  choice -= storage;
+  if (choice < offset) return 45 + 3 * 0;
+  choice -= offset;
+  if (choice < offset) return 45 + 3 * 2;
+  choice -= offset;
+  if (choice < gas) return 3 * 7;
+  return kBattery100;
+}
+__device__ __forceinline__ uint32_t smart_fallback_total(int y) {
+  const int year = EG_BASE_YEAR + y;
+  return 40u + (year < 2035 ? 10u : 20u) + 2u * (year < 2035 ? 5u : (year < 2045 ? 15u : 25u)) + (year < 2035 ? 15u : (year < 2045 ? 10u : 5u));
+}
+__device__ __noinline__ int smart_deficit_fallback_pick(uint32_t choice) {  // ((0.07*0.5) as u32 == 0, (0.06*0.5*100) as u32 == 3)
+  if (choice < 30) return 3 * 8;
+  choice -= 30;
+  if (choice < 30) return 3 * 12;
+  choice -= 30;
+  if (choice < 20) return 3 * 7;
+  choice -= 20;
+  if (choice < 10) return 3 * 0;
+  choice -= 10;
+  if (choice < 3) return 3 * 4;
+  return kBattery100;
+}
+
+// stagnation branch of sample_action (sampling.rs:190-220) for rows edited in this episode: stable descending
+// sort by rank counting and the powers, both spread over the lanes
+__device__ __noinline__ void sort_local(uint32_t sb, int lane, double power) {
+  const double* lw = (const double*)(smem + sb + kOffLw);
+  double* scaled = (double*)(smem + sb + kOffScratch);
+  uint8_t* sort_idx = smem + sb + kOffSortIdx;
+  for (int k = lane; k < EG_N_ACTIONS; k += 32) {
+    const double wk = lw[k];
+    int rank = 0;
+    for (int j = 0; j < EG_N_ACTIONS; j++) {
+      const double wj = lw[j];
+      rank += (wj > wk) || (wj == wk && j < k);
+    }
+    sort_idx[rank] = (uint8_t)k;
+    scaled[rank] = pow(wk, power);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ int deficit_key_of_type(int t) {
+  // weights/core.rs:130-149 insertion order {8,7,12,11,9,0,1,4,10,5,2,3,13,14}; type -> key, 4 bits each (F = none: CoalPlant)
+  return (int)((0xDC238401F97BA65ull >> (4 * t)) & 0xF);
+}
+__device__ __forceinline__ int deficit_key_action(int k) {
+  // type of deficit key k, 4 bits each
+  return 3 * (int)((0xED325A4109BC78ull >> (4 * k)) & 0xF);
+}
+
 template <bool REPLAY, typename NearT>
 struct Warp {
   const EgEpisodeParams& p;
   const EgSmallTables* __restrict__ T;
   const int lane;
-  // shared-memory slice of this warp
-  double* lw;
-  double* ldw;
-  double* scaled;
-  uint32_t* gens;
-  uint16_t* offs;
-  uint16_t* year_sites;
-  uint8_t* year_actions;
-  uint8_t* sort_idx;
-  uint8_t* counts;
-  NearT* nearest;
+  const uint32_t sb;  // byte offset of this warp's slice in the block's dynamic shared memory
   // warp-uniform episode state (identical in every lane)
   double gen0, gen1, gen2;    // plain / intermittent / storage generation accumulators
   double co2, op_sum;
@@ -120,25 +171,39 @@ struct Warp {
   double ocost, ocost_prev;   // same for offsets (map_handler.rs:960-962)
   double off_amount;          // calc_total_carbon_offset(year)
   uint32_t n_gens, n_offs, flags;
-  bool lw_valid, sorted_valid, total_valid;
+  bool rows_dirty, dw_dirty, sorted_valid, total_valid;
   double lw_total;
-  Rng rng;
+  // Philox: lane l holds draw number rbase + l
+  uint32_t k0, k1, e0, e1, draw, rbase;
+  unsigned long long rbuf;
 
-  __device__ Warp(const EgEpisodeParams& p_, unsigned char* slice, int lane_)
-      : p(p_), T(p_.map.small), lane(lane_) {
-    lw = (double*)(slice + kOffLw);
-    ldw = (double*)(slice + kOffLdw);
-    scaled = (double*)(slice + kOffScaled);
-    gens = (uint32_t*)(slice + kOffGens);
-    offs = (uint16_t*)(slice + kOffOffs);
-    year_sites = (uint16_t*)(slice + kOffYearSites);
-    year_actions = (uint8_t*)(slice + kOffYearActions);
-    sort_idx = (uint8_t*)(slice + kOffSortIdx);
-    counts = (uint8_t*)(slice + kOffCounts);
-    nearest = (NearT*)(slice + kOffNear);
-  }
+  __device__ Warp(const EgEpisodeParams& p_, uint32_t sb_, int lane_) : p(p_), T(p_.map.small), lane(lane_), sb(sb_) {}
+
+  __device__ __forceinline__ double* LW() const { return (double*)(smem + sb + kOffLw); }
+  __device__ __forceinline__ double* LDW() const { return (double*)(smem + sb + kOffLdw); }
+  __device__ __forceinline__ double2* SCR() const { return (double2*)(smem + sb + kOffScratch); }
+  __device__ __forceinline__ uint32_t* GENS() const { return (uint32_t*)(smem + sb + kOffGens); }
+  __device__ __forceinline__ uint16_t* OFFS() const { return (uint16_t*)(smem + sb + kOffOffs); }
+  __device__ __forceinline__ uint16_t* YSITES() const { return (uint16_t*)(smem + sb + kOffYearSites); }
+  __device__ __forceinline__ uint8_t* YACT() const { return smem + sb + kOffYearActions; }
+  __device__ __forceinline__ uint8_t* COUNTS() const { return smem + sb + kOffCounts; }
+  __device__ __forceinline__ NearT* NEAR() const { return (NearT*)(smem + sb + kOffNear); }
 
   static constexpr NearT kFar = (NearT)~(NearT)0;
+
+  // ---- random draws ---------------------------------------------------------------------------------------
+  __device__ __forceinline__ unsigned long long u64() {
+    uint32_t off = draw - rbase;
+    if (off >= 32u) {
+      rbase = draw;
+      rbuf = philox_u64(k0, k1, e0, e1, draw + (uint32_t)lane);
+      off = 0;
+    }
+    draw++;
+    return __shfl_sync(kFull, rbuf, (int)off);
+  }
+  __device__ __forceinline__ double f64() { return (double)(u64() >> 11) * (1.0 / 9007199254740992.0); }
+  __device__ __forceinline__ uint32_t index(uint32_t n) { return (uint32_t)__umul64hi(u64(), (unsigned long long)n); }
 
   __device__ __forceinline__ double gen_cost(int t, int m, int b, int y) const {
     // get_current_cost: base_cost * inflation * technology_factor * location_modifier, then * multiplier
@@ -154,71 +219,72 @@ struct Warp {
   }
 
   // Start of a year: re-fold the per-plant terms that depend on the year, in plant order (the order of the
-  // reference's iterator sums). Terms are computed one plant per lane and folded in sequentially by shuffle.
+  // reference's iterator sums). Terms are computed one plant per lane, staged in shared memory and added
+  // sequentially from broadcast reads.
   //  * capital cost re-priced at year-1 over this year's fleet continues last year's sum (the plants built this year
   //    are appended to it), so it is carried, not recomputed;
   //  * generation and CO2 of a simulation-built plant do not depend on the year: those sums are re-folded only when
   //    the existing-plant prefix changed (the years the pre-existing fleet comes online, quirk Q1).
-  __device__ void year_start(int y) {
+  __device__ __forceinline__ void year_start(int y) {
     const EgYearRow& yr = T->year[y];
-    const bool refold = y == 0 || __ldg(&yr.prefix_changed) != 0;
-    if (refold) {
+    if (y == 0 || __ldg(&yr.prefix_changed) != 0) {
       gen0 = __ldg(&yr.ex_gen[0]); gen1 = __ldg(&yr.ex_gen[1]); gen2 = __ldg(&yr.ex_gen[2]);
       co2 = __ldg(&yr.ex_co2);
+      const uint32_t* gens = GENS();
+      for (uint32_t i = 0; i < n_gens; i++) {
+        const int t = (gens[i] >> 16) & 0xF;
+        const int c = __ldg(&T->acc_class[t]);
+        const double mw = __ldg(&T->net_mw[t]);
+        // adding +0.0 leaves the other two accumulators unchanged bit for bit
+        gen0 += c == EG_ACC_PLAIN ? mw : 0.0;
+        gen1 += c == EG_ACC_INTERMITTENT ? mw : 0.0;
+        gen2 += c == EG_ACC_STORAGE ? mw : 0.0;
+        co2 += __ldg(&T->co2[t]);
+      }
     }
     op_sum = __ldg(&yr.ex_opinion_sum);
     gcost_prev = gcost;
     gcost = 0.0;
     const int n = p.map.grid_n;
+    double2* scr = SCR();
     for (uint32_t base = 0; base < n_gens; base += 32) {
       const uint32_t i = base + lane;
-      double t_mw = 0.0, t_co2 = 0.0, t_op = 0.0, t_c = 0.0;
-      int cls = 0;
       if (i < n_gens) {
-        const uint32_t g = gens[i];
+        const uint32_t g = GENS()[i];
         const int gi = g & 0xFF, gj = (g >> 8) & 0xFF, t = (g >> 16) & 0xF, m = (g >> 20) & 0x3, b = (g >> 22) & 0x1F;
-        cls = __ldg(&T->acc_class[t]);
-        t_mw = __ldg(&T->net_mw[t]);
-        t_co2 = __ldg(&T->co2[t]);
-        t_op = gen_opinion(gi * n + gj, t, m, b, y);
-        t_c = gen_cost(t, m, b, y);
+        scr[lane] = make_double2(gen_opinion(gi * n + gj, t, m, b, y), gen_cost(t, m, b, y));
       }
+      __syncwarp();
       const int cnt = min(32u, n_gens - base);
       for (int j = 0; j < cnt; j++) {
-        op_sum += shfl_f64(t_op, j);
-        gcost += shfl_f64(t_c, j);
-        if (refold) {
-          const double mw = shfl_f64(t_mw, j);
-          const int c = __shfl_sync(kFull, cls, j);
-          // adding +0.0 leaves the other two accumulators unchanged bit for bit
-          gen0 += c == EG_ACC_PLAIN ? mw : 0.0;
-          gen1 += c == EG_ACC_INTERMITTENT ? mw : 0.0;
-          gen2 += c == EG_ACC_STORAGE ? mw : 0.0;
-          co2 += shfl_f64(t_co2, j);
-        }
+        const double2 v = scr[j];
+        op_sum += v.x;
+        gcost += v.y;
       }
+      __syncwarp();
     }
     ocost_prev = ocost;
     ocost = 0.0; off_amount = 0.0;
     for (uint32_t base = 0; base < n_offs; base += 32) {
       const uint32_t i = base + lane;
-      double t_a = 0.0, t_c = 0.0;
       if (i < n_offs) {
-        const uint32_t o = offs[i];
+        const uint32_t o = OFFS()[i];
         const int ot = o & 3, m = (o >> 2) & 3, b = (o >> 4) & 0x1F;
         const double maturity = __ldg(&T->natural_offset[ot]) ? __ldg(&T->maturity[y - b]) : 1.0;
-        t_a = __ldg(&T->off_amount[ot]) * maturity;
-        t_c = off_cost(ot, m, y);
+        scr[lane] = make_double2(__ldg(&T->off_amount[ot]) * maturity, off_cost(ot, m, y));
       }
+      __syncwarp();
       const int cnt = min(32u, n_offs - base);
       for (int j = 0; j < cnt; j++) {
-        off_amount += shfl_f64(t_a, j);
-        ocost += shfl_f64(t_c, j);
+        const double2 v = scr[j];
+        off_amount += v.x;
+        ocost += v.y;
       }
+      __syncwarp();
     }
   }
 
-  __device__ EG_HELPER_INLINE State state(int y) const {  // simulation.rs:122-135
+  __device__ __forceinline__ State state(int y) const {  // simulation.rs:122-135
     State s;
     s.net = co2 - off_amount;
     const uint32_t cnt = __ldg(&T->year[y].ex_active) + n_gens;
@@ -229,7 +295,7 @@ struct Warp {
   }
 
   // MetalLocationSearch::find_suitable_location (CPU branch) as a 32-wide walk down the pre-sorted site list.
-  __device__ int place(int t, int y) {
+  __device__ __forceinline__ int place(int t, int y) {
     const int pc = __ldg(&T->pclass[t]);
     const int rc = __ldg(&T->rclass_of_pclass[pc]);
     const bool water = __ldg(&T->water_of_pclass[pc]) != 0;
@@ -241,6 +307,8 @@ struct Warp {
     const double* __restrict__ pref = p.map.prefix_score + base;
     const double* __restrict__ nf = p.map.near_factor + (size_t)rc * p.map.r2_stride;  // distance/radius by squared cell distance
     const double size_factor = __ldg(&T->size_factor);
+    const NearT* nearest = NEAR();
+    const uint32_t* gens = GENS();
     double best_score = 0.0;
     int best_site = -1;
     for (int k0 = 0; k0 < ns; k0 += 32) {
@@ -249,70 +317,79 @@ struct Warp {
       const double s_first = shfl_f64(s_static, 0);
       // the list is sorted: nothing from here on can beat the best so far, and zero scores never win
       if (s_first < best_score || !(s_first > 0.0)) break;
-      bool live = k < ns && s_static > 0.0 && !(s_static < best_score);
-      double score = s_static;
-      int site = 0x7FFFFFFF;
-      int si = 0, sj = 0;
+      const bool live = s_static > 0.0 && !(s_static < best_score);
+      int site = 0, packed = 0;
+      bool inr = false;
+      int d2n = 0;
       if (live) {
-        const int packed = __ldg(&order[k]);  // (i << 8) | j of the candidate site
-        si = packed >> 8; sj = packed & 0xFF;
-        site = si * n + sj;
-        const int d2n = nearest[site];
-        if (d2n < r2lim) {
-          // in range of at least one new plant: all factors are < 1 and rounding is monotone, so the product with
-          // the nearest plant's factor alone bounds the true score from above
-          const double pre = __ldg(&pref[k]);
-          double bound = pre * __ldg(&nf[d2n]);
-          if (water) bound *= __ldg(&p.map.coast_factor[site]);
-          bound *= size_factor;
-          if (bound < best_score) {
-            live = false;
-          } else {
-            double sc = pre;
-            for (uint32_t g = 0; g < n_gens; g++) {  // plant order == multiplication order of the reference
-              const uint32_t pk = gens[g];
-              const int di = si - (int)(pk & 0xFF), dj = sj - (int)((pk >> 8) & 0xFF);
-              const int d2 = di * di + dj * dj;
-              if (d2 < r2lim) sc *= __ldg(&nf[d2]);  // score *= distance / penalty_radius
-            }
-            if (water) sc *= __ldg(&p.map.coast_factor[site]);
-            sc *= size_factor;
-            score = sc;
-          }
-        }
+        packed = __ldg(&order[k]);  // (i << 8) | j of the candidate site
+        site = (packed >> 8) * n + (packed & 0xFF);
+        d2n = nearest[site];
+        inr = d2n < r2lim;
       }
-      // strict '>' in scan order (metal_location_search.rs:168): the maximum wins, equal scores keep the lower site
-      const bool better = live && (score > best_score || (score == best_score && best_site >= 0 && site < best_site));
-      if (__any_sync(kFull, better)) {
-        double c_score = better ? score : -1.0;
-        int c_site = better ? site : 0x7FFFFFFF;
+      // sites out of range of every new plant keep their static score; in list order the first one is the best of them
+      // (descending scores, equal scores in scan order)
+      const unsigned m_out = __ballot_sync(kFull, live && !inr);
+      if (m_out) {
+        const int f = __ffs(m_out) - 1;
+        const double sc = shfl_f64(s_static, f);
+        const int st = __shfl_sync(kFull, site, f);
+        // strict '>' in scan order (metal_location_search.rs:168): the maximum wins, equal scores keep the lower site
+        if (sc > best_score || (sc == best_score && st < best_site)) { best_score = sc; best_site = st; }
+      }
+      // in range of at least one new plant: all factors are < 1 and rounding is monotone, so the product with the
+      // nearest plant's factor alone bounds the true score from above
+      bool cand = false;
+      double pre = 0.0;
+      if (inr) {
+        pre = __ldg(&pref[k]);
+        double bound = pre * __ldg(&nf[d2n]);
+        if (water) bound *= __ldg(&p.map.coast_factor[site]);
+        bound *= size_factor;
+        cand = bound > 0.0 && !(bound < best_score);
+      }
+      if (__any_sync(kFull, cand)) {
+        // survivors multiply their factors in plant order (== multiplication order of the reference), one site per lane
+        double sc = pre;
+        const int si = packed >> 8, sj = packed & 0xFF;
+        for (uint32_t g = 0; g < n_gens; g++) {
+          const uint32_t pk = gens[g];
+          const int di = si - (int)(pk & 0xFF), dj = sj - (int)((pk >> 8) & 0xFF);
+          const int d2 = di * di + dj * dj;
+          if (cand && d2 < r2lim) sc *= __ldg(&nf[d2]);  // score *= distance / penalty_radius
+        }
+        if (water) sc *= __ldg(&p.map.coast_factor[site]);
+        sc *= size_factor;
+        // strict '>' in scan order: the maximum wins, equal scores keep the lower site
+        double c_score = cand ? sc : -1.0;
+        int c_site = cand ? site : 0x7FFFFFFF;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           const double o_score = __shfl_xor_sync(kFull, c_score, o);
           const int o_site = __shfl_xor_sync(kFull, c_site, o);
           if (o_score > c_score || (o_score == c_score && o_site < c_site)) { c_score = o_score; c_site = o_site; }
         }
-        best_score = c_score;
-        best_site = c_site;
+        if (c_score > best_score || (c_score == best_score && best_site >= 0 && c_site < best_site)) { best_score = c_score; best_site = c_site; }
       }
     }
     return best_site;
   }
 
-  __device__ void add_generator(int site, int t, int m, int y) {
+  __device__ __forceinline__ void add_generator(int site, int t, int m, int y) {
     if (n_gens >= EG_MAX_NEW_GENERATORS) { flags |= EG_FLAG_GEN_OVERFLOW; return; }
     const int n = p.map.grid_n;
     const int gi = site / n, gj = site - gi * n;
-    if (lane == 0) gens[n_gens] = pack_gen(gi, gj, t, m, y);
+    if (lane == 0) GENS()[n_gens] = pack_gen(gi, gj, t, m, y);
     n_gens++;
     // nearest-plant map: squared cell distance to the closest plant built in this episode
     const int R = p.map.kmax - 1, r2max = p.map.r2_stride;
+    NearT* nearest = NEAR();
     for (int dj0 = -R; dj0 <= R; dj0 += 32) {  // one row of the (2R+1)^2 neighbourhood per step, one cell per lane
       const int dj = dj0 + lane, j = gj + dj;
       const bool col_ok = dj <= R && j >= 0 && j < n;
-      for (int di = -R; di <= R; di++) {
-        const int i = gi + di;
-        if (i < 0 || i >= n) continue;
+      const int ilo = max(gi - R, 0), ihi = min(gi + R, n - 1);
+      for (int i = ilo; i <= ihi; i++) {
+        const int di = i - gi;
         const int d2 = di * di + dj * dj;
         if (col_ok && d2 < r2max) {  // only cells inside the largest penalty radius can matter
           NearT* cell = &nearest[i * n + j];
@@ -331,9 +408,9 @@ struct Warp {
     gcost += gen_cost(t, m, y, y);
     if (y > 0) gcost_prev += gen_cost(t, m, y, y - 1);
   }
-  __device__ void add_offset(int ot, int m, int y) {
+  __device__ __forceinline__ void add_offset(int ot, int m, int y) {
     if (n_offs >= EG_MAX_OFFSETS) { flags |= EG_FLAG_OFFSET_OVERFLOW; return; }
-    if (lane == 0) offs[n_offs] = (uint16_t)(ot | (m << 2) | (y << 4));
+    if (lane == 0) OFFS()[n_offs] = (uint16_t)(ot | (m << 2) | (y << 4));
     n_offs++;
     __syncwarp();
     const double maturity = __ldg(&T->natural_offset[ot]) ? __ldg(&T->maturity[0]) : 1.0;
@@ -343,114 +420,76 @@ struct Warp {
   }
 
   // ---- episode-local learning (the deficit handler edits this year's rows of its private weights) ----------
-  __device__ void touch_local(int y) {
-    if (lw_valid) return;
+  __device__ __forceinline__ void load_rows(int y) {
+    double* lw = LW();
     for (int k = lane; k < EG_N_ACTIONS; k += 32) lw[k] = __ldg(&p.policy->w[y][k]);
-    if (lane < EG_N_DEFICIT_KEYS) ldw[lane] = __ldg(&p.policy->dw[y][lane]);
-    lw_valid = true;
+    if (lane < EG_N_DEFICIT_KEYS) LDW()[lane] = __ldg(&p.policy->dw[y][lane]);
+    rows_dirty = false; dw_dirty = false; sorted_valid = false; total_valid = false;
     __syncwarp();
   }
-  __device__ __forceinline__ double weight(int y, int k) const { return lw_valid ? lw[k] : __ldg(&p.policy->w[y][k]); }
-  __device__ __forceinline__ double dweight(int y, int k) const { return lw_valid ? ldw[k] : __ldg(&p.policy->dw[y][k]); }
 
-  __device__ static int deficit_key_of_type(int t) {  // weights/core.rs:130-149 insertion order
-    switch (t) {
-      case 8: return 0; case 7: return 1; case 12: return 2; case 11: return 3; case 9: return 4; case 0: return 5;
-      case 1: return 6; case 4: return 7; case 10: return 8; case 5: return 9; case 2: return 10; case 3: return 11;
-      case 13: return 12; case 14: return 13;
-    }
-    return -1;  // CoalPlant has no deficit key
-  }
-  __device__ static int deficit_key_action(int k) {
-    // type of deficit key k (weights/core.rs:130-149), 4 bits each: {8,7,12,11,9,0,1,4,10,5,2,3,13,14}
-    return 3 * (int)((0xED325A4109BC78ull >> (4 * k)) & 0xF);
-  }
-
-  __device__ void update_deficit_weights(int y, int action, double improvement) {  // deficit.rs:82-135
-    const int key = deficit_key_of_type(action / 3);
-    if (key < 0 || action % 3 != 0) return;
-    touch_local(y);
+  __device__ __forceinline__ void update_deficit_weights(int y, int action, double improvement) {  // deficit.rs:82-135
+    const int t = action / 3;
+    const int key = deficit_key_of_type(t);
+    if (action >= 45 || key == 0xF || action - 3 * t != 0) return;
     const double lr = p.policy->learning_rate;
     const double adj = improvement > 0.0 ? 1.0 + (lr * improvement * 1.5) : 1.0 / (1.0 + (lr * fabs(improvement) * 1.5));
     const double boost = 1.0 + (lr * 0.1);
+    double* ldw = LDW();
     if (lane < 14) {
       if (lane == key) ldw[lane] = fmin(fmax(ldw[lane] * adj, kMinWeight), kMaxWeight);
       else if (improvement < 0.0) ldw[lane] = fmin(ldw[lane] * boost, kMaxWeight);
     }
+    dw_dirty = true;
     __syncwarp();
   }
-  __device__ void update_weights(int y, int action, double improvement) {  // learning.rs:21-88
-    touch_local(y);
+  __device__ __forceinline__ void update_weights(int y, int action, double improvement) {  // learning.rs:21-88
     const double lr = p.policy->learning_rate;
     const double rel = p.policy->relative_improvement;
     const double immediate = rel > 0.0 ? 0.7 : 0.3;
     const double combined = immediate * improvement + (1.0 - immediate) * rel;
     const double adj = combined > 0.0 ? 1.0 + (lr * combined) : 1.0 / (1.0 + (lr * fabs(combined)));
     const double boost = 1.0 + (lr * 0.1);
+    double* lw = LW();
     for (int k = lane; k < EG_N_ACTIONS; k += 32) {
       if (k == action) lw[k] = fmin(fmax(lw[k] * adj, kMinWeight), kMaxWeight);
       else if (combined < 0.0 && k < 45) lw[k] = fmin(lw[k] * boost, kMaxWeight);
       else if (combined < 0.0 && k == EG_ACT_DO_NOTHING && p.policy->noop_boost) lw[k] = fmin(lw[k] * (1.0 + lr * 0.2), kMaxWeight);
     }
+    rows_dirty = true;
     sorted_valid = false;
     total_valid = false;
     __syncwarp();
   }
 
   // ---- sampling (canonical key order replaces HashMap iteration order) ---------------------------------------
-  __device__ __noinline__ int smart_fallback_action(int y) {  // sampling.rs:445-490
-    const int year = EG_BASE_YEAR + y;
-    const uint32_t storage = year < 2035 ? 10 : 20;
-    const uint32_t offset = year < 2035 ? 5 : (year < 2045 ? 15 : 25);
-    const uint32_t gas = year < 2035 ? 15 : (year < 2045 ? 10 : 5);
-    const int act[7] = {3 * 0, 3 * 1, 3 * 4, 3 * 12, 45 + 3 * 0, 45 + 3 * 2, 3 * 7};
-    const uint32_t wt[7] = {15, 10, 15, storage, offset, offset, gas};
-    uint32_t total = 0;
-    for (int i = 0; i < 7; i++) total += wt[i];
-    uint32_t choice = rng.index(total);
-    for (int i = 0; i < 7; i++) {
-      if (choice < wt[i]) return act[i];
-      choice -= wt[i];
-    }
-    return kBattery100;
-  }
-  __device__ __noinline__ int smart_deficit_fallback_action() {  // sampling.rs:492-528 ((0.07*0.5) as u32 == 0, (0.06*0.5*100) as u32 == 3)
-    const int act[6] = {3 * 8, 3 * 12, 3 * 7, 3 * 0, 3 * 1, 3 * 4};
-    const uint32_t wt[6] = {30, 30, 20, 10, 0, 3};
-    uint32_t choice = rng.index(93);
-    for (int i = 0; i < 6; i++) {
-      if (choice < wt[i]) return act[i];
-      choice -= wt[i];
-    }
-    return kBattery100;
-  }
-
-  __device__ int sample_deficit_action(int y, uint32_t* replay_pos) {  // sampling.rs:240-378
+  __device__ __forceinline__ int sample_deficit_action(int y, uint32_t* replay_pos) {  // sampling.rs:240-378
     if (p.replay_best) {
       if (p.policy->has_best && *replay_pos < p.policy->n_best_deficit[y]) return p.policy->best_deficit[y][(*replay_pos)++];
-      return smart_deficit_fallback_action();
+      return smart_deficit_fallback_pick(index(93));
     }
-    const bool explore = rng.f64() < p.policy->exploration_rate;
-    if (explore) return deficit_key_action((int)rng.index(14));
+    const bool explore = f64() < p.policy->exploration_rate;
+    if (explore) return deficit_key_action((int)index(14));
+    const double* ldw = LDW();
     double total;
-    if (lw_valid) {
+    if (dw_dirty) {
       total = 0.0;
       for (int k = 0; k < 14; k++) total += ldw[k];
     } else {
       total = __ldg(&p.policy->dw_total[y]);  // same left-to-right sum, done once per snapshot on the host
     }
     if (total <= 0.0) return kGasPeaker100;
-    double rv = rng.f64() * total;
+    double rv = f64() * total;
     for (int k = 0; k < 14; k++) {
-      rv -= dweight(y, k);
+      rv -= ldw[k];
       if (rv <= 0.0) return deficit_key_action(k);
     }
     return kGasPeaker100;
   }
-  __device__ uint32_t sample_additional_actions(int y, uint32_t deficit_count) {  // sampling.rs:380-443
+  __device__ __forceinline__ uint32_t sample_additional_actions(int y, uint32_t deficit_count) {  // sampling.rs:380-443
     const uint32_t max_possible = deficit_count >= 20 ? 0 : 20 - deficit_count;
     if (max_possible == 0) return 0;
-    const double random_val = rng.f64();
+    const double random_val = f64();
     if (p.policy->has_count_weights) {
       const double total = __ldg(&p.policy->cw_total[y]);
       if (total <= 0.0) return 0;
@@ -465,38 +504,22 @@ struct Warp {
     const uint32_t min_actions = (uint32_t)round(2.0 / scaled_eps), max_actions = (uint32_t)round(12.0 / scaled_eps);
     const uint32_t cmax = min(max_actions, max_possible), cmin = min(min_actions, cmax);
     if (cmin == cmax) return cmin;
-    return cmin + rng.index(cmax - cmin + 1);
+    return cmin + index(cmax - cmin + 1);
   }
 
-  // stagnation branch of sample_action (sampling.rs:190-220) for rows edited in this episode: stable descending
-  // sort by rank counting and the powers, both spread over the lanes
-  __device__ __noinline__ void sort_local(double power) {
-    for (int k = lane; k < EG_N_ACTIONS; k += 32) {
-      const double wk = lw[k];
-      int rank = 0;
-      for (int j = 0; j < EG_N_ACTIONS; j++) {
-        const double wj = lw[j];
-        rank += (wj > wk) || (wj == wk && j < k);
-      }
-      sort_idx[rank] = (uint8_t)k;
-      scaled[rank] = pow(wk, power);
-    }
-    sorted_valid = true;
-    __syncwarp();
-  }
-
-  __device__ int sample_action(int y, uint32_t* replay_pos) {  // sampling.rs:76-238
+  __device__ __forceinline__ int sample_action(int y, uint32_t* replay_pos) {  // sampling.rs:76-238
     if (p.replay_best) {
       if (p.policy->has_best && *replay_pos < p.policy->n_best[y]) return p.policy->best[y][(*replay_pos)++];
-      return smart_fallback_action(y);
+      return smart_fallback_pick(y, index(smart_fallback_total(y)));
     }
     const uint32_t iwi = p.policy->iwi;
     const double eps = p.policy->exploration_rate;
     const double cur_eps = iwi > 100 ? eps * (1.0 / (1.0 + 0.01 * (double)iwi)) : eps;
-    const bool explore = rng.f64() < cur_eps;
-    if (explore) return (int)rng.index(EG_N_ACTIONS);
+    const bool explore = f64() < cur_eps;
+    if (explore) return (int)index(EG_N_ACTIONS);
+    const double* lw = LW();
     double total;
-    if (lw_valid) {
+    if (rows_dirty) {
       if (!total_valid) {
         lw_total = 0.0;
         for (int k = 0; k < EG_N_ACTIONS; k++) lw_total += lw[k];
@@ -510,24 +533,31 @@ struct Warp {
     if (iwi > 500) {
       const double* sc;
       const uint8_t* idx;
-      if (lw_valid) {
-        if (!sorted_valid) sort_local(p.policy->stagnation_power);
-        sc = scaled; idx = sort_idx;
-      } else {
-        sc = p.policy->scaled_sorted[y]; idx = p.policy->sorted_idx[y];  // host libm, per snapshot
+      if (rows_dirty) {
+        if (!sorted_valid) { sort_local(sb, lane, p.policy->stagnation_power); sorted_valid = true; }
+        double total_scaled = 0.0;
+        const double* scl = (const double*)(smem + sb + kOffScratch);
+        for (int k = 0; k < EG_N_ACTIONS; k++) total_scaled += scl[k];
+        double rv = f64() * total_scaled;
+        for (int k = 0; k < EG_N_ACTIONS; k++) {
+          rv -= scl[k];
+          if (rv <= 0.0) return (smem + sb + kOffSortIdx)[k];
+        }
+        return (smem + sb + kOffSortIdx)[0];
       }
+      sc = p.policy->scaled_sorted[y]; idx = p.policy->sorted_idx[y];  // host libm, per snapshot
       double total_scaled = 0.0;
-      for (int k = 0; k < EG_N_ACTIONS; k++) total_scaled += sc[k];
-      double rv = rng.f64() * total_scaled;
+      for (int k = 0; k < EG_N_ACTIONS; k++) total_scaled += __ldg(&sc[k]);
+      double rv = f64() * total_scaled;
       for (int k = 0; k < EG_N_ACTIONS; k++) {
-        rv -= sc[k];
+        rv -= __ldg(&sc[k]);
         if (rv <= 0.0) return idx[k];
       }
       return idx[0];
     }
-    double rv = rng.f64() * total;
+    double rv = f64() * total;
     for (int k = 0; k < EG_N_ACTIONS; k++) {
-      rv -= weight(y, k);
+      rv -= lw[k];
       if (rv <= 0.0) return k;
     }
     return kGasPeaker100;
@@ -536,30 +566,34 @@ struct Warp {
   __device__ __forceinline__ void record(int slot, int action, int site) {
     if (slot >= EG_MAX_ACTIONS_PER_YEAR) { flags |= EG_FLAG_YEAR_OVERFLOW; return; }
     if (lane == 0) {
-      year_actions[slot] = (uint8_t)action;
-      year_sites[slot] = site >= 0 ? (uint16_t)site : (uint16_t)EG_SITE_NONE;
+      YACT()[slot] = (uint8_t)action;
+      YSITES()[slot] = site >= 0 ? (uint16_t)site : (uint16_t)EG_SITE_NONE;
     }
   }
 
-  __device__ void run(uint32_t ep) {
+  __device__ __forceinline__ void run(uint32_t ep) {
     const unsigned long long id = p.same_stream ? 0ull : p.first_episode + ep;
-    rng.k0 = (uint32_t)p.seed; rng.k1 = (uint32_t)(p.seed >> 32);
-    rng.e0 = (uint32_t)id; rng.e1 = (uint32_t)(id >> 32); rng.draw = 0;
+    k0 = (uint32_t)p.seed; k1 = (uint32_t)(p.seed >> 32);
+    e0 = (uint32_t)id; e1 = (uint32_t)(id >> 32); draw = 0; rbase = 0x80000000u; rbuf = 0ull;
     n_gens = 0; n_offs = 0; flags = 0;
     gcost = 0.0; ocost = 0.0; gen0 = gen1 = gen2 = 0.0; co2 = 0.0;
-    for (int i = lane; i < p.map.n_sites; i += 32) nearest[i] = kFar;
+    {
+      // clear the nearest-plant map, 4 bytes per lane and step (n_sites entries, padded to 16 bytes by the launcher)
+      uint32_t* nw = (uint32_t*)(smem + sb + kOffNear);
+      const int words = (p.map.n_sites * (int)sizeof(NearT) + 3) / 4;
+      for (int i = lane; i < words; i += 32) nw[i] = 0xFFFFFFFFu;
+    }
     __syncwarp();
     const eg_traj* in = REPLAY ? p.replay_in + ep : nullptr;
     double total_cost = 0.0, total_credit = 0.0, total_sales = 0.0;
     uint32_t n_def_total = 0, n_add_total = 0;
-    eg_result res;
+    double r_net = 0.0, r_opinion = 0.0, r_cost = 0.0, r_rel = 0.0;
+    const bool learn = !REPLAY && !p.replay_best;
 
     for (int y = 0; y < EG_NY; y++) {
       year_start(y);
-      lw_valid = false;
-      sorted_valid = false;
-      total_valid = false;
-      State cur = state(y);
+      if (!REPLAY) load_rows(y);
+      State cur = state(y);                                  // state of the map after the latest change
       bool deficit_mode = cur.balance < 0.0;                 // simulation.rs:137
       const State initial = cur;                             // simulation.rs:341-356
       double remaining = deficit_mode ? -cur.balance : 0.0;  // Map::handle_power_deficit returns it unchanged (Q2)
@@ -577,12 +611,11 @@ struct Warp {
             else action = attempts < 5 ? sample_deficit_action(y, &replay_def) : kBattery100;
             is_def = true;
           } else {                                           // simulation.rs:490-519
-            if (!REPLAY && !p.replay_best) {
-              const State fin = state(y);
-              const double overall_success = action_impact(initial, fin);
-              if (fin.balance >= 0.0 && overall_success > 0.0 && n_def > 0) {
+            if (learn) {
+              const double overall_success = action_impact(initial, cur);
+              if (cur.balance >= 0.0 && overall_success > 0.0 && n_def > 0) {
                 const double success_factor = 0.1 * overall_success;
-                for (uint32_t i = 0; i < n_def && i < EG_MAX_ACTIONS_PER_YEAR; i++) update_deficit_weights(y, year_actions[i], success_factor);
+                for (uint32_t i = 0; i < n_def && i < EG_MAX_ACTIONS_PER_YEAR; i++) update_deficit_weights(y, YACT()[i], success_factor);
               }
             }
             deficit_mode = false;
@@ -606,8 +639,6 @@ struct Warp {
           break;
         }
 
-        State before;
-        if (is_def) before = state(y);                       // simulation.rs:380-395
         int site = -1;
         if (action < 45) {                                   // apply_action, actions.rs:42-76
           const int t = action / 3, m = action - 3 * t;
@@ -616,28 +647,31 @@ struct Warp {
           else flags |= EG_FLAG_NO_SITE;
         } else if (action < 57) {                            // actions.rs:129-179
           const int a = action - 45;
-          add_offset(a / 3, a % 3, y);
+          const int ot = a / 3;
+          add_offset(ot, a - 3 * ot, y);
         }                                                    // 57..60: no generator id matches / DoNothing (Q4)
-        if (is_def && site < 0) { remaining = 0.0; continue; }  // no site with score > 0: flagged, loop left
+        if (is_def && site < 0 && action < 45) { remaining = 0.0; continue; }  // no site with score > 0: flagged, loop left
         record(n_def + n_add, action, site);
         if (is_def) {
           n_def++;
+          // state_before of this iteration (simulation.rs:380-395) is the state after the previous change: `cur`
           const State after = state(y);                      // simulation.rs:412-427
-          if (!REPLAY && !p.replay_best) {
-            const double overall = action_impact(before, after);
-            const double emis = after.net < before.net ? (before.net - after.net) / fmax(fabs(before.net), 1.0) : 0.0;
+          if (learn) {
+            const double overall = action_impact(cur, after);
+            const double emis = after.net < cur.net ? (cur.net - after.net) / fmax(fabs(cur.net), 1.0) : 0.0;
             double cost_imp = 0.0;
             if (after.net < 1000.0) {
-              const double cost_change = after.cost - before.cost;
-              cost_imp = -cost_change / fmax(fabs(before.cost), 1.0);
+              const double cost_change = after.cost - cur.cost;
+              cost_imp = -cost_change / fmax(fabs(cur.cost), 1.0);
             }
-            const double op_imp = after.cost < kMaxAcceptableCost * 8.0 ? (after.opinion - before.opinion) / fmax(1.0 - before.opinion, 0.1) : 0.0;
+            const double op_imp = after.cost < kMaxAcceptableCost * 8.0 ? (after.opinion - cur.opinion) / fmax(1.0 - cur.opinion, 0.1) : 0.0;
             const double combined = overall * 0.7 + emis * 0.15 + cost_imp * 0.1 + op_imp * 0.05;
             __syncwarp();
             update_deficit_weights(y, action, combined);     // simulation.rs:479
             update_weights(y, action, overall * 0.5);        // simulation.rs:482
           }
           remaining = -fmin(after.balance, 0.0);             // simulation.rs:486
+          cur = after;
         } else {
           n_add++;
         }
@@ -646,26 +680,22 @@ struct Warp {
 
       const uint32_t nd_rec = min(n_def, (uint32_t)EG_MAX_ACTIONS_PER_YEAR);
       const uint32_t na_rec = min(n_add, (uint32_t)EG_MAX_ACTIONS_PER_YEAR - nd_rec);
-      if (lane == 0) { counts[y] = (uint8_t)nd_rec; counts[EG_NY + y] = (uint8_t)na_rec; }
+      if (lane == 0) { COUNTS()[y] = (uint8_t)nd_rec; COUNTS()[EG_NY + y] = (uint8_t)na_rec; }
       n_def_total += n_def; n_add_total += n_add;
       const uint32_t used = nd_rec + na_rec;
       if (p.traj) {  // 40 B row, one 32-bit word per lane
         if (lane < EG_MAX_ACTIONS_PER_YEAR / 4) {
-          uint32_t word = 0;
-          for (int b = 0; b < 4; b++) {
-            const uint32_t i = lane * 4 + b;
-            if (i < used) word |= (uint32_t)year_actions[i] << (8 * b);
-          }
-          ((uint32_t*)p.traj[ep].actions[y])[lane] = word;
+          const uint32_t raw = ((const uint32_t*)YACT())[lane];
+          const uint32_t first = lane * 4;
+          const uint32_t keep = used <= first ? 0u : (used - first >= 4u ? 0xFFFFFFFFu : (1u << (8 * (used - first))) - 1u);
+          ((uint32_t*)p.traj[ep].actions[y])[lane] = raw & keep;
         }
       }
       if (p.sites) {
         if (lane < EG_MAX_ACTIONS_PER_YEAR / 2) {
-          uint32_t word = 0;
-          for (int b = 0; b < 2; b++) {
-            const uint32_t i = lane * 2 + b;
-            word |= (uint32_t)(i < used ? year_sites[i] : (uint16_t)EG_SITE_NONE) << (16 * b);
-          }
+          const uint32_t raw = ((const uint32_t*)YSITES())[lane];
+          const uint32_t first = lane * 2;
+          const uint32_t word = used <= first ? 0xFFFFFFFFu : (used - first >= 2u ? raw : (raw | 0xFFFF0000u));
           ((uint32_t*)p.sites[ep].site[y])[lane] = word;
         }
       }
@@ -679,67 +709,77 @@ struct Warp {
       const double net = co2 - off_amount;
       const double credit = net >= 0.0 ? 0.0 : (-net) * __ldg(&yr.carbon_price);
       const uint32_t active = __ldg(&yr.ex_active) + n_gens;
-      const double opinion = active > 0 ? op_sum / (double)active : 1.0;
       const double total_capital = gcost + ocost;
       const double yearly_capital = y == 0 ? total_capital : total_capital - (gcost_prev + ocost_prev);
       const double sales = (p.energy_sales && balance > 0.0) ? (balance * 8.76) * 50000.0 : 0.0;
       const double yearly_total = yearly_capital + 0.0 + 0.0 - credit - (p.energy_sales ? sales : 0.0);
       if (y == 0) { total_cost = yearly_total; total_credit = credit; total_sales = sales; }
       else { total_cost = total_cost + yearly_total; total_credit = total_credit + credit; total_sales = total_sales + sales; }
-      if (p.yearly && lane == 0) {
-        eg_year_metrics& m = p.yearly[ep].y[y];
-        m.total_population = __ldg(&yr.pop_total);
-        m.active_generators = active;
-        m.total_power_usage = usage;
-        m.total_power_generation = generation;
-        m.power_balance = balance;
-        m.average_public_opinion = opinion;
-        m.yearly_capital_cost = yearly_capital;
-        m.total_capital_cost = total_capital;
-        m.inflation_factor = __ldg(&yr.inflation);
-        m.total_co2_emissions = co2;
-        m.total_carbon_offset = off_amount;
-        m.net_co2_emissions = net;
-        m.yearly_carbon_credit_revenue = credit;
-        m.total_carbon_credit_revenue = total_credit;
-        m.yearly_energy_sales_revenue = sales;
-        m.total_energy_sales_revenue = total_sales;
-        m.yearly_total_cost = yearly_total;
-        m.total_cost = total_cost;
-        m.reserved = 0.0;
-      }
-      if (y == EG_NY - 1) {  // iteration.rs:57-84
-        res.net_emissions = net;
-        res.public_opinion = opinion;
-        res.total_cost = total_capital;
-        res.power_reliability = balance >= 0.0 ? 1.0 : 0.0;
+      if (p.yearly || y == EG_NY - 1) {
+        const double opinion = active > 0 ? op_sum / (double)active : 1.0;
+        if (p.yearly && lane == 0) {
+          eg_year_metrics& m = p.yearly[ep].y[y];
+          m.total_population = __ldg(&yr.pop_total);
+          m.active_generators = active;
+          m.total_power_usage = usage;
+          m.total_power_generation = generation;
+          m.power_balance = balance;
+          m.average_public_opinion = opinion;
+          m.yearly_capital_cost = yearly_capital;
+          m.total_capital_cost = total_capital;
+          m.inflation_factor = __ldg(&yr.inflation);
+          m.total_co2_emissions = co2;
+          m.total_carbon_offset = off_amount;
+          m.net_co2_emissions = net;
+          m.yearly_carbon_credit_revenue = credit;
+          m.total_carbon_credit_revenue = total_credit;
+          m.yearly_energy_sales_revenue = sales;
+          m.total_energy_sales_revenue = total_sales;
+          m.yearly_total_cost = yearly_total;
+          m.total_cost = total_cost;
+          m.reserved = 0.0;
+        }
+        if (y == EG_NY - 1) {  // iteration.rs:57-84
+          r_net = net;
+          r_opinion = opinion;
+          r_cost = total_capital;
+          r_rel = balance >= 0.0 ? 1.0 : 0.0;
+        }
       }
     }
 
     // score_metrics, scoring.rs:5-45 (ln evaluated on the device: <= 1 ulp from the host libm)
+    double score;
     {
-      const double normalized_cost = fmax(res.total_cost / kMaxAcceptableCost, 1.0);
+      const double normalized_cost = fmax(r_cost / kMaxAcceptableCost, 1.0);
       const double cost_term = fmin(log(normalized_cost) / p.ln100, 1.0);
-      if (p.cost_only) res.score = 2.0 - cost_term;
-      else if (res.net_emissions > 0.0) res.score = 1.0 - fmin(res.net_emissions / kMaxAcceptableEmissions, 1.0);
+      if (p.cost_only) score = 2.0 - cost_term;
+      else if (r_net > 0.0) score = 1.0 - fmin(r_net / kMaxAcceptableEmissions, 1.0);
       else {
         const double cost_score = 1.0 - cost_term;
         const double cost_weight = normalized_cost > 8.0 ? 0.8 : 0.5;
         const double opinion_weight = 1.0 - cost_weight;
-        res.score = 1.0 + (cost_score * cost_weight + res.public_opinion * opinion_weight);
+        score = 1.0 + (cost_score * cost_weight + r_opinion * opinion_weight);
       }
     }
-    res.n_generators = n_gens;
-    res.n_offsets = n_offs;
-    res.n_deficit_actions = (uint16_t)n_def_total;
-    res.n_additional_actions = (uint16_t)n_add_total;
-    res.flags = flags;
-    res.reserved = 0;
-    if (lane == 0) p.out[ep] = res;
+    if (lane < 8) {  // eg_result, 64 B: one 8-byte word per lane
+      unsigned long long word;
+      switch (lane) {
+        case 0: word = (unsigned long long)__double_as_longlong(score); break;
+        case 1: word = (unsigned long long)__double_as_longlong(r_net); break;
+        case 2: word = (unsigned long long)__double_as_longlong(r_opinion); break;
+        case 3: word = (unsigned long long)__double_as_longlong(r_cost); break;
+        case 4: word = (unsigned long long)__double_as_longlong(r_rel); break;
+        case 5: word = (unsigned long long)n_gens | ((unsigned long long)n_offs << 32); break;
+        case 6: word = (unsigned long long)(n_def_total & 0xFFFFu) | ((unsigned long long)(n_add_total & 0xFFFFu) << 16) | ((unsigned long long)flags << 32); break;
+        default: word = 0ull; break;
+      }
+      ((unsigned long long*)(p.out + ep))[lane] = word;
+    }
     if (p.traj) {
       __syncwarp();
       uint8_t* dst = p.traj[ep].n_deficit;  // n_deficit[26] then n_additional[26] are contiguous
-      for (int i = lane; i < 2 * EG_NY; i += 32) dst[i] = counts[i];
+      for (int i = lane; i < 2 * EG_NY; i += 32) dst[i] = COUNTS()[i];
     }
     __syncwarp();
   }
@@ -747,11 +787,10 @@ struct Warp {
 
 template <bool REPLAY, typename NearT>
 __global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) eg_episode_kernel(const __grid_constant__ EgEpisodeParams p, int slice_bytes) {
-  extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ep = blockIdx.x * (blockDim.x >> 5) + warp;
   if (ep >= p.n) return;  // whole warps leave together
-  Warp<REPLAY, NearT> w(p, smem + (size_t)warp * slice_bytes, lane);
+  Warp<REPLAY, NearT> w(p, (uint32_t)(warp * slice_bytes), lane);
   w.run(ep);
 }
 
@@ -764,23 +803,23 @@ cudaError_t launch(const EgEpisodeParams& p, cudaStream_t stream) {
   // as many warps per block as keep several blocks resident in the 227 KB of an SM
   int warps = EG_EPISODE_WARPS;
   while (warps > 1 && warps * slice > 100 * 1024) warps >>= 1;
-  const size_t smem = (size_t)warps * slice;
-  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  const size_t smem_bytes = (size_t)warps * slice;
+  if (smem_bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
   const uint32_t blocks = (p.n + warps - 1) / warps;
   // shared-memory carveout: room for as many blocks as the register budget allows, the rest stays L1
-  const int resident = (int)std::min<size_t>(EG_EPISODE_MIN_BLOCKS * (EG_EPISODE_WARPS / warps), (227 * 1024) / (smem + 1024));
-  const int carveout = std::min(100, (int)((resident * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
+  const int resident = (int)std::min<size_t>(EG_EPISODE_MIN_BLOCKS * (EG_EPISODE_WARPS / warps), (227 * 1024) / (smem_bytes + 1024));
+  const int carveout = std::min(100, (int)((resident * (smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
   cudaError_t err;
   if (wide) {
-    err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
     cudaFuncSetAttribute(eg_episode_kernel<REPLAY, uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
-    eg_episode_kernel<REPLAY, uint16_t><<<blocks, 32 * warps, smem, stream>>>(p, slice);
+    eg_episode_kernel<REPLAY, uint16_t><<<blocks, 32 * warps, smem_bytes, stream>>>(p, slice);
   } else {
-    err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
     cudaFuncSetAttribute(eg_episode_kernel<REPLAY, uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
-    eg_episode_kernel<REPLAY, uint8_t><<<blocks, 32 * warps, smem, stream>>>(p, slice);
+    eg_episode_kernel<REPLAY, uint8_t><<<blocks, 32 * warps, smem_bytes, stream>>>(p, slice);
   }
   return cudaGetLastError();
 }
