@@ -39,7 +39,8 @@ struct eg_ctx {
   EgHostTables htab;
   // device memory
   EgSmallTables* d_small = nullptr;
-  double* d_op_cost = nullptr;
+  double* d_plant_terms = nullptr;
+  uint32_t* d_stamp = nullptr;
   double* d_site_opinion = nullptr;
   double* d_coast = nullptr;
   double* d_prefix = nullptr;          // [6][26][ns]
@@ -66,11 +67,11 @@ struct eg_ctx {
 namespace {
 
 void free_map(eg_ctx* c) {
-  void* ptrs[] = {c->d_small, c->d_op_cost, c->d_site_opinion, c->d_coast, c->d_prefix, c->d_static_unsorted, c->d_order,
+  void* ptrs[] = {c->d_small, c->d_plant_terms, c->d_stamp, c->d_site_opinion, c->d_coast, c->d_prefix, c->d_static_unsorted, c->d_order,
                   c->d_static_sorted, c->d_prefix_sorted, c->d_near, c->d_r2_limit, c->d_sx, c->d_sy, c->d_ex, c->d_ey, c->d_cx, c->d_cy, c->d_pop};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  c->d_small = nullptr; c->d_op_cost = nullptr; c->d_site_opinion = nullptr; c->d_coast = nullptr; c->d_prefix = nullptr;
+  c->d_small = nullptr; c->d_plant_terms = nullptr; c->d_stamp = nullptr; c->d_site_opinion = nullptr; c->d_coast = nullptr; c->d_prefix = nullptr;
   c->d_static_unsorted = nullptr; c->d_order = nullptr; c->d_static_sorted = nullptr; c->d_prefix_sorted = nullptr;
   c->d_near = nullptr; c->d_r2_limit = nullptr; c->d_sx = c->d_sy = c->d_ex = c->d_ey = c->d_cx = c->d_cy = nullptr; c->d_pop = nullptr;
   c->map_ready = false;
@@ -93,7 +94,8 @@ int build_device_map(eg_ctx* c) {
   const int ns = m.grid_n * m.grid_n;
   cudaStream_t s = c->stream;
   if ((rc = upload(&c->d_small, &c->htab.small, 1, s))) return rc;
-  if ((rc = upload(&c->d_op_cost, c->htab.op_cost.data(), c->htab.op_cost.size(), s))) return rc;
+  if ((rc = upload(&c->d_plant_terms, c->htab.plant_terms.data(), c->htab.plant_terms.size(), s))) return rc;
+  if ((rc = upload(&c->d_stamp, c->htab.stamp.data(), c->htab.stamp.size(), s))) return rc;
   if ((rc = upload(&c->d_near, c->htab.near_factor.data(), c->htab.near_factor.size(), s))) return rc;
   if ((rc = upload(&c->d_r2_limit, c->htab.r2_limit, (size_t)EG_N_RCLASS, s))) return rc;
   if ((rc = upload(&c->d_sx, m.sx.data(), m.sx.size(), s))) return rc;
@@ -124,7 +126,11 @@ int build_device_map(eg_ctx* c) {
   c->launches += (uint64_t)launches;
   EG_CUDA(cudaStreamSynchronize(s));
   c->dmap.small = c->d_small;
-  c->dmap.op_cost = c->d_op_cost;
+  c->dmap.plant_terms = c->d_plant_terms;
+  c->dmap.stamp = c->d_stamp;
+  c->dmap.stamp_w = c->htab.stamp_w;
+  c->dmap.near_stride = c->htab.near_stride;
+  c->dmap.near_wide = c->htab.near_wide;
   c->dmap.site_opinion = c->d_site_opinion;
   c->dmap.coast_factor = c->d_coast;
   c->dmap.order = c->d_order;

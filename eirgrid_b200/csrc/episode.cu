@@ -87,9 +87,9 @@ __device__ __forceinline__ double action_impact(const State& cur, const State& n
 
 __device__ __forceinline__ double shfl_f64(double v, int src) { return __shfl_sync(kFull, v, src); }
 
-// packed plant: gi(8) gj(8) type(4) mult(2) build(5)
+// packed plant: gj(8) gi(8) type(4) mult(2) build(5) — the low half has the byte order of the `order` table, (i << 8) | j
 __device__ __forceinline__ uint32_t pack_gen(int gi, int gj, int t, int m, int b) {
-  return (uint32_t)gi | ((uint32_t)gj << 8) | ((uint32_t)t << 16) | ((uint32_t)m << 20) | ((uint32_t)b << 22);
+  return (uint32_t)gj | ((uint32_t)gi << 8) | ((uint32_t)t << 16) | ((uint32_t)m << 20) | ((uint32_t)b << 22);
 }
 
 // sampling.rs:445-490 / 492-528: the fixed fallback tables (replay mode without a stored action)
@@ -164,6 +164,7 @@ struct Warp {
   const EgSmallTables* __restrict__ T;
   const int lane;
   const uint32_t sb;  // byte offset of this warp's slice in the block's dynamic shared memory
+  const uint32_t nf_off;  // byte offset of the block-shared near_factor copy (narrow maps)
   // warp-uniform episode state (identical in every lane)
   double gen0, gen1, gen2;    // plain / intermittent / storage generation accumulators
   double co2, op_sum;
@@ -177,7 +178,7 @@ struct Warp {
   uint32_t k0, k1, e0, e1, draw, rbase;
   unsigned long long rbuf;
 
-  __device__ Warp(const EgEpisodeParams& p_, uint32_t sb_, int lane_) : p(p_), T(p_.map.small), lane(lane_), sb(sb_) {}
+  __device__ Warp(const EgEpisodeParams& p_, uint32_t sb_, uint32_t nf_off_, int lane_) : p(p_), T(p_.map.small), lane(lane_), sb(sb_), nf_off(nf_off_) {}
 
   __device__ __forceinline__ double* LW() const { return (double*)(smem + sb + kOffLw); }
   __device__ __forceinline__ double* LDW() const { return (double*)(smem + sb + kOffLdw); }
@@ -205,17 +206,18 @@ struct Warp {
   __device__ __forceinline__ double f64() { return (double)(u64() >> 11) * (1.0 / 9007199254740992.0); }
   __device__ __forceinline__ uint32_t index(uint32_t n) { return (uint32_t)__umul64hi(u64(), (unsigned long long)n); }
 
-  __device__ __forceinline__ double gen_cost(int t, int m, int b, int y) const {
-    // get_current_cost: base_cost * inflation * technology_factor * location_modifier, then * multiplier
-    // (const_funcs.rs:56, generator.rs:593)
-    return __ldg(&T->base_cost[t][b]) * __ldg(&T->year[y].inflation) * __ldg(&T->tech[t][y]) * __ldg(&T->loc_mod[t]) * __ldg(&T->mult[m]);
+  // (cost-opinion term, get_current_cost) of a simulation-built plant in year y: one 16-byte read of the host table
+  // (base_cost * inflation * technology_factor * location_modifier * multiplier, const_funcs.rs:56, generator.rs:593)
+  __device__ __forceinline__ double2 plant_terms(int t, int m, int b, int y) const {
+    return __ldg((const double2*)p.map.plant_terms + EG_OPC_INDEX(y, t, m, b));
   }
+  __device__ __forceinline__ double gen_cost(int t, int m, int b, int y) const { return plant_terms(t, m, b, y).y; }
   __device__ __forceinline__ double off_cost(int o, int m, int y) const {
     return __ldg(&T->off_base_cost[o]) * __ldg(&T->year[y].inflation) * __ldg(&T->mult[m]);  // carbon_offset.rs:188-195
   }
-  __device__ __forceinline__ double gen_opinion(int site, int t, int m, int b, int y) const {
+  __device__ __forceinline__ double gen_opinion(int site, int t, int y, double cost_term) const {
     // calc_new_generator_opinion, map_handler.rs:946-948
-    return 0.03 * __ldg(&p.map.site_opinion[site]) + __ldg(&T->op_type[y][t]) + __ldg(&p.map.op_cost[EG_OPC_INDEX(y, t, m, b)]);
+    return 0.03 * __ldg(&p.map.site_opinion[site]) + __ldg(&T->op_type[y][t]) + cost_term;
   }
 
   // Start of a year: re-fold the per-plant terms that depend on the year, in plant order (the order of the
@@ -251,8 +253,9 @@ struct Warp {
       const uint32_t i = base + lane;
       if (i < n_gens) {
         const uint32_t g = GENS()[i];
-        const int gi = g & 0xFF, gj = (g >> 8) & 0xFF, t = (g >> 16) & 0xF, m = (g >> 20) & 0x3, b = (g >> 22) & 0x1F;
-        scr[lane] = make_double2(gen_opinion(gi * n + gj, t, m, b, y), gen_cost(t, m, b, y));
+        const int gj = g & 0xFF, gi = (g >> 8) & 0xFF, t = (g >> 16) & 0xF, m = (g >> 20) & 0x3, b = (g >> 22) & 0x1F;
+        const double2 pt = plant_terms(t, m, b, y);
+        scr[lane] = make_double2(gen_opinion(gi * n + gj, t, y, pt.x), pt.y);
       }
       __syncwarp();
       const int cnt = min(32u, n_gens - base);
@@ -305,7 +308,9 @@ struct Warp {
     const uint16_t* __restrict__ order = p.map.order + base;
     const double* __restrict__ stat = p.map.static_score + base;
     const double* __restrict__ pref = p.map.prefix_score + base;
-    const double* __restrict__ nf = p.map.near_factor + (size_t)rc * p.map.r2_stride;  // distance/radius by squared cell distance
+    // distance/radius by squared cell distance: block-shared copy in shared memory (narrow maps), else global
+    const double* __restrict__ nf = (sizeof(NearT) == 1 ? (const double*)(smem + nf_off) : p.map.near_factor) + (size_t)rc * p.map.r2_stride;
+    const int nstride = p.map.near_stride;
     const double size_factor = __ldg(&T->size_factor);
     const NearT* nearest = NEAR();
     const uint32_t* gens = GENS();
@@ -324,7 +329,7 @@ struct Warp {
       if (live) {
         packed = __ldg(&order[k]);  // (i << 8) | j of the candidate site
         site = (packed >> 8) * n + (packed & 0xFF);
-        d2n = nearest[site];
+        d2n = nearest[(packed >> 8) * nstride + (packed & 0xFF)];
         inr = d2n < r2lim;
       }
       // sites out of range of every new plant keep their static score; in list order the first one is the best of them
@@ -343,7 +348,7 @@ struct Warp {
       double pre = 0.0;
       if (inr) {
         pre = __ldg(&pref[k]);
-        double bound = pre * __ldg(&nf[d2n]);
+        double bound = pre * nf[d2n];
         if (water) bound *= __ldg(&p.map.coast_factor[site]);
         bound *= size_factor;
         cand = bound > 0.0 && !(bound < best_score);
@@ -351,12 +356,22 @@ struct Warp {
       if (__any_sync(kFull, cand)) {
         // survivors multiply their factors in plant order (== multiplication order of the reference), one site per lane
         double sc = pre;
-        const int si = packed >> 8, sj = packed & 0xFF;
-        for (uint32_t g = 0; g < n_gens; g++) {
-          const uint32_t pk = gens[g];
-          const int di = si - (int)(pk & 0xFF), dj = sj - (int)((pk >> 8) & 0xFF);
-          const int d2 = di * di + dj * dj;
-          if (cand && d2 < r2lim) sc *= __ldg(&nf[d2]);  // score *= distance / penalty_radius
+        if (sizeof(NearT) == 1) {
+          // coordinates < 128: both byte differences at once, no borrow between the bytes, then di*di + dj*dj by IDP.4A
+          const uint32_t spo = (uint32_t)packed | 0x8080u;
+          for (uint32_t g = 0; g < n_gens; g++) {
+            const uint32_t v = ((spo - gens[g]) ^ 0x8080u) & 0xFFFFu;
+            const int d2 = __dp4a((int)v, (int)v, 0);
+            if (cand && d2 < r2lim) sc *= nf[d2];  // score *= distance / penalty_radius
+          }
+        } else {
+          const int si = packed >> 8, sj = packed & 0xFF;
+          for (uint32_t g = 0; g < n_gens; g++) {
+            const uint32_t pk = gens[g];
+            const int dj = sj - (int)(pk & 0xFF), di = si - (int)((pk >> 8) & 0xFF);
+            const int d2 = di * di + dj * dj;
+            if (cand && d2 < r2lim) sc *= __ldg(&nf[d2]);
+          }
         }
         if (water) sc *= __ldg(&p.map.coast_factor[site]);
         sc *= size_factor;
@@ -381,19 +396,23 @@ struct Warp {
     const int gi = site / n, gj = site - gi * n;
     if (lane == 0) GENS()[n_gens] = pack_gen(gi, gj, t, m, y);
     n_gens++;
-    // nearest-plant map: squared cell distance to the closest plant built in this episode
-    const int R = p.map.kmax - 1, r2max = p.map.r2_stride;
-    NearT* nearest = NEAR();
-    for (int dj0 = -R; dj0 <= R; dj0 += 32) {  // one row of the (2R+1)^2 neighbourhood per step, one cell per lane
-      const int dj = dj0 + lane, j = gj + dj;
-      const bool col_ok = dj <= R && j >= 0 && j < n;
-      const int ilo = max(gi - R, 0), ihi = min(gi + R, n - 1);
-      for (int i = ilo; i <= ihi; i++) {
-        const int di = i - gi;
-        const int d2 = di * di + dj * dj;
-        if (col_ok && d2 < r2max) {  // only cells inside the largest penalty radius can matter
-          NearT* cell = &nearest[i * n + j];
-          if (d2 < (int)*cell) *cell = (NearT)d2;
+    // nearest-plant map: squared cell distance to the closest plant built in this episode. One 32-bit word (4 or 2
+    // cells) per lane: packed minimum of the map word and the host-built pattern word for this column alignment.
+    {
+      constexpr int cpw = 4 / (int)sizeof(NearT);
+      const int R = p.map.kmax - 1, rows = 2 * R + 1, W = p.map.stamp_w, nstride = p.map.near_stride;
+      const int a = gj % cpw;
+      const int j0 = gj - a - (R + cpw - 1) / cpw * cpw;  // first column of the pattern, word aligned
+      const uint32_t* __restrict__ pat = p.map.stamp + (size_t)a * rows * W;
+      uint32_t* near_w = (uint32_t*)(smem + sb + kOffNear);
+      const int items = rows * W;
+      for (int it = lane; it < items; it += 32) {
+        const int r = it / W, w = it - r * W;
+        const int i = gi - R + r, jw = j0 + w * cpw;
+        if (i >= 0 && i < n && jw >= 0 && jw < nstride) {
+          uint32_t* cell = near_w + (i * nstride + jw) / cpw;
+          const uint32_t pw = __ldg(&pat[it]);
+          *cell = sizeof(NearT) == 1 ? __vminu4(*cell, pw) : __vminu2(*cell, pw);
         }
       }
     }
@@ -404,8 +423,9 @@ struct Warp {
     gen1 += cls == EG_ACC_INTERMITTENT ? mw : 0.0;
     gen2 += cls == EG_ACC_STORAGE ? mw : 0.0;
     co2 += __ldg(&T->co2[t]);
-    op_sum += gen_opinion(site, t, m, y, y);
-    gcost += gen_cost(t, m, y, y);
+    const double2 pt = plant_terms(t, m, y, y);
+    op_sum += gen_opinion(site, t, y, pt.x);
+    gcost += pt.y;
     if (y > 0) gcost_prev += gen_cost(t, m, y, y - 1);
   }
   __device__ __forceinline__ void add_offset(int ot, int m, int y) {
@@ -580,7 +600,7 @@ struct Warp {
     {
       // clear the nearest-plant map, 4 bytes per lane and step (n_sites entries, padded to 16 bytes by the launcher)
       uint32_t* nw = (uint32_t*)(smem + sb + kOffNear);
-      const int words = (p.map.n_sites * (int)sizeof(NearT) + 3) / 4;
+      const int words = (p.map.grid_n * p.map.near_stride * (int)sizeof(NearT) + 3) / 4;
       for (int i = lane; i < words; i += 32) nw[i] = 0xFFFFFFFFu;
     }
     __syncwarp();
@@ -788,40 +808,45 @@ struct Warp {
 template <bool REPLAY, typename NearT>
 __global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) eg_episode_kernel(const __grid_constant__ EgEpisodeParams p, int slice_bytes) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t nf_off = (uint32_t)((blockDim.x >> 5) * slice_bytes);
+  if (sizeof(NearT) == 1) {  // block-shared copy of the distance/radius factors
+    double* nf_s = (double*)(smem + nf_off);
+    const int cnt = EG_N_RCLASS * p.map.r2_stride;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) nf_s[i] = __ldg(&p.map.near_factor[i]);
+    __syncthreads();
+  }
   const uint32_t ep = blockIdx.x * (blockDim.x >> 5) + warp;
   if (ep >= p.n) return;  // whole warps leave together
-  Warp<REPLAY, NearT> w(p, (uint32_t)(warp * slice_bytes), lane);
+  Warp<REPLAY, NearT> w(p, (uint32_t)(warp * slice_bytes), nf_off, lane);
   w.run(ep);
 }
 
-template <bool REPLAY>
-cudaError_t launch(const EgEpisodeParams& p, cudaStream_t stream) {
-  if (p.n == 0) return cudaSuccess;
-  const bool wide = p.map.kmax > 12 + 1 || p.map.r2_stride > 255;  // squared cell distances do not fit a byte
-  const int near_bytes = p.map.n_sites * (wide ? 2 : 1);
+template <bool REPLAY, typename NearT>
+cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
+  const bool wide = sizeof(NearT) == 2;
+  const int near_bytes = p.map.grid_n * p.map.near_stride * (int)sizeof(NearT);
   const int slice = (kOffNear + near_bytes + 15) & ~15;
+  const int shared_tab = wide ? 0 : EG_N_RCLASS * p.map.r2_stride * (int)sizeof(double);
   // as many warps per block as keep several blocks resident in the 227 KB of an SM
   int warps = EG_EPISODE_WARPS;
-  while (warps > 1 && warps * slice > 100 * 1024) warps >>= 1;
-  const size_t smem_bytes = (size_t)warps * slice;
+  while (warps > 1 && warps * slice + shared_tab > 100 * 1024) warps >>= 1;
+  const size_t smem_bytes = (size_t)warps * slice + shared_tab;
   if (smem_bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
   const uint32_t blocks = (p.n + warps - 1) / warps;
   // shared-memory carveout: room for as many blocks as the register budget allows, the rest stays L1
   const int resident = (int)std::min<size_t>(EG_EPISODE_MIN_BLOCKS * (EG_EPISODE_WARPS / warps), (227 * 1024) / (smem_bytes + 1024));
   const int carveout = std::min(100, (int)((resident * (smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
-  cudaError_t err;
-  if (wide) {
-    err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (err != cudaSuccess) return err;
-    cudaFuncSetAttribute(eg_episode_kernel<REPLAY, uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
-    eg_episode_kernel<REPLAY, uint16_t><<<blocks, 32 * warps, smem_bytes, stream>>>(p, slice);
-  } else {
-    err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (err != cudaSuccess) return err;
-    cudaFuncSetAttribute(eg_episode_kernel<REPLAY, uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
-    eg_episode_kernel<REPLAY, uint8_t><<<blocks, 32 * warps, smem_bytes, stream>>>(p, slice);
-  }
+  cudaError_t err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, NearT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (err != cudaSuccess) return err;
+  cudaFuncSetAttribute(eg_episode_kernel<REPLAY, NearT>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+  eg_episode_kernel<REPLAY, NearT><<<blocks, 32 * warps, smem_bytes, stream>>>(p, slice);
   return cudaGetLastError();
+}
+
+template <bool REPLAY>
+cudaError_t launch(const EgEpisodeParams& p, cudaStream_t stream) {
+  if (p.n == 0) return cudaSuccess;
+  return p.map.near_wide ? launch_as<REPLAY, uint16_t>(p, stream) : launch_as<REPLAY, uint8_t>(p, stream);
 }
 
 }  // namespace

@@ -25,7 +25,7 @@ struct EgEpisodeParams {
 #define EG_EPISODE_WARPS 4   // episodes (warps) per block for the Irish map; fewer when the per-warp slice is large
 #endif
 #ifndef EG_EPISODE_MIN_BLOCKS
-#define EG_EPISODE_MIN_BLOCKS 7  // register cap 65536 / (128 threads * 7) = 72; measured best of 4..8 on B200
+#define EG_EPISODE_MIN_BLOCKS 6  // register cap 65536 / (128 threads * 6) = 80; 6 blocks of (4 slices + factor table) fill the shared memory
 #endif
 
 cudaError_t eg_launch_rollout(const EgEpisodeParams& p, cudaStream_t stream);

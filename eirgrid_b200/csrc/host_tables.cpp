@@ -282,13 +282,15 @@ void eg_host_build_tables(const EgHostMap& m, EgHostTables* out) {
   for (int d = 0; d < EG_NY; d++) T.maturity[d] = std::min(std::max(1.0 - std::exp(-0.1 * (double)d), 0.0), 1.0);  // carbon_offset.rs:226-227
 
   // ---- CONSTRUCTION_COST_WEIGHT * cost opinion of a simulation-built plant
-  out->op_cost.assign(EG_OPC_SIZE, 0.0);
+  // (the cost re-priced at the year before the build year is read too: yearly capital cost, map_handler.rs:968-985)
+  out->plant_terms.assign((size_t)EG_OPC_SIZE * 2, 0.0);
   for (int y = 0; y < EG_NY; y++)
     for (int t = 0; t < EG_NT; t++)
       for (int mi = 0; mi < EG_N_MULTS; mi++)
-        for (int b = 0; b <= y; b++) {
+        for (int b = 0; b < EG_NY; b++) {
           const double cost = T.base_cost[t][b] * inflation(y) * T.tech[t][y] * T.loc_mod[t] * T.mult[mi];
-          out->op_cost[EG_OPC_INDEX(y, t, mi, b)] = 0.82 * cost_opinion(cost, y);
+          out->plant_terms[(size_t)EG_OPC_INDEX(y, t, mi, b) * 2] = 0.82 * cost_opinion(cost, y);
+          out->plant_terms[(size_t)EG_OPC_INDEX(y, t, mi, b) * 2 + 1] = cost;
         }
 
   // ---- settlements: population growth and demand (simulation.rs:107-120, map_handler.rs:813-827)
@@ -381,5 +383,27 @@ void eg_host_build_tables(const EgHostMap& m, EgHostTables* out) {
       const double distance = std::sqrt((double)d2 * m.step * m.step);
       out->near_factor[(size_t)rc * stride + d2] = distance / kRadii[rc];
     }
+  // ---- stamp pattern of the nearest-plant map (episode.cu add_generator)
+  // squared cell distances do not fit a byte, or site coordinates do not fit 7 bits (packed byte arithmetic in place())
+  out->near_wide = (stride > 255 || m.grid_n > 128) ? 1 : 0;
+  const int cpw = out->near_wide ? 2 : 4;                     // cells per 32-bit word
+  const int R = kmax - 1, rows = 2 * R + 1;
+  const int Rp = (R + cpw - 1) / cpw * cpw;                   // pattern starts at column gj - (gj mod cpw) - Rp: word aligned
+  out->near_stride = (m.grid_n + cpw - 1) / cpw * cpw;
+  out->stamp_w = (Rp + cpw - 1 + R + 1 + cpw - 1) / cpw;      // words covering columns up to gj + R
+  out->stamp.assign((size_t)cpw * rows * out->stamp_w, 0xFFFFFFFFu);
+  for (int a = 0; a < cpw; a++)
+    for (int r = 0; r < rows; r++)
+      for (int w = 0; w < out->stamp_w; w++) {
+        uint32_t word = 0;
+        for (int b = 0; b < cpw; b++) {
+          const int di = r - R, dj = w * cpw + b - Rp - a;
+          const long d2 = (long)di * di + (long)dj * dj;
+          const uint32_t far = out->near_wide ? 0xFFFFu : 0xFFu;
+          const uint32_t v = (std::abs(dj) <= R && d2 < stride) ? (uint32_t)d2 : far;  // only cells inside the largest radius matter
+          word |= v << (b * (32 / cpw));
+        }
+        out->stamp[((size_t)a * rows + r) * out->stamp_w + w] = word;
+      }
   (void)kRadius;
 }

@@ -16,12 +16,16 @@ struct EgHostMap {
 
 struct EgHostTables {
   EgSmallTables small;
-  std::vector<double> op_cost;       // [EG_OPC_SIZE]
+  std::vector<double> plant_terms;   // [EG_OPC_SIZE][2]
   std::vector<uint32_t> pop;         // [26][S]
   std::vector<double> near_factor;   // [6][r2_stride], by squared cell distance
   int r2_limit[EG_N_RCLASS] = {0};
   int r2_stride = 0;
   int kmax = 0;
+  std::vector<uint32_t> stamp;       // [cells per word][2*(kmax-1)+1][stamp_w]
+  int stamp_w = 0;
+  int near_stride = 0;
+  int near_wide = 0;
 };
 
 int eg_host_map_load(EgHostMap* m, const char* settlements_json, const char* generators_csv, const char* coastline_json);

@@ -51,14 +51,17 @@ struct EgSmallTables {   // ~35 KB, read-mostly, L1/L2 resident
   uint8_t pad[3];
 };
 
-// CONSTRUCTION_COST_WEIGHT * calc_cost_opinion(get_current_cost(year), year), map_handler.rs:944-948
+// per simulation-built plant and year, two doubles:
+//   [0] CONSTRUCTION_COST_WEIGHT * calc_cost_opinion(get_current_cost(year), year)   map_handler.rs:944-948
+//   [1] get_current_cost(year) = base_cost * inflation * technology factor * location modifier * multiplier
+//                                                                                     const_funcs.rs:28-57, generator.rs:582-594
 // index [year][type][mult][build year]
 #define EG_OPC_INDEX(y, t, m, b) ((((y) * EG_NT + (t)) * EG_N_MULTS + (m)) * EG_NY + (b))
 #define EG_OPC_SIZE (EG_NY * EG_NT * EG_N_MULTS * EG_NY)
 
 struct EgDeviceMap {      // device pointers + sizes, passed by value to the kernels
   const EgSmallTables* small;
-  const double* op_cost;          // [EG_OPC_SIZE]
+  const double* plant_terms;      // [EG_OPC_SIZE][2] (cost opinion term, current cost)
   const double* site_opinion;     // [n_sites] avg_settlement_opinion of a plant on the site  map_handler.rs:931-941
   const double* coast_factor;     // [n_sites] 1/(1+min_coast_distance/5000)                  metal_location_search.rs:157-162
   // placement lists, sorted by static score (descending, ties by scan order), per (pclass, year)
@@ -71,6 +74,14 @@ struct EgDeviceMap {      // device pointers + sizes, passed by value to the ker
   int n_sites;
   int grid_n;
   int kmax;                       // plants farther than kmax-1 cells (in x or y) are outside every radius
+  // nearest-plant map of an episode (shared memory): rows padded to near_stride cells so that rows start on 32-bit
+  // words; cells are uint8 squared cell distances (uint16 when near_wide). A new plant is stamped into it with
+  // packed minima against this pattern: [cells per word][2*(kmax-1)+1 rows][stamp_w words], the squared distances
+  // around a plant whose column is congruent to the first index modulo the cells per word.
+  const uint32_t* stamp;
+  int stamp_w;
+  int near_stride;
+  int near_wide;
 };
 
 struct EgPolicyDevice {   // weights snapshot + the per-batch constants of update_weights (learning.rs:36-55)
