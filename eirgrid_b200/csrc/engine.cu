@@ -53,6 +53,7 @@ struct eg_ctx {
   double *d_sx = nullptr, *d_sy = nullptr, *d_ex = nullptr, *d_ey = nullptr, *d_cx = nullptr, *d_cy = nullptr;
   uint32_t* d_pop = nullptr;
   EgPolicyDevice* d_policy = nullptr;
+  uint32_t* d_next_episode = nullptr;  // work counter of the persistent episode kernels
   EgDeviceMap dmap{};
   // scratch for the host-buffer entry points
   size_t cap = 0;
@@ -128,7 +129,7 @@ int build_device_map(eg_ctx* c) {
   c->dmap.small = c->d_small;
   c->dmap.plant_terms = c->d_plant_terms;
   c->dmap.stamp = c->d_stamp;
-  c->dmap.stamp_w = c->htab.stamp_w;
+  c->dmap.stamp_w_log2 = c->htab.stamp_w_log2;
   c->dmap.near_stride = c->htab.near_stride;
   c->dmap.near_wide = c->htab.near_wide;
   c->dmap.site_opinion = c->d_site_opinion;
@@ -197,6 +198,7 @@ EgEpisodeParams make_params(const eg_ctx* c, const eg_run_cfg* cfg, uint64_t see
   p.same_stream = cfg->same_stream_all_episodes;
   p.replay_best = cfg->replay_best;
   p.ln100 = std::log(50000000000.0 * 100.0 / 50000000000.0);
+  p.next_episode = c->d_next_episode;
   return p;
 }
 
@@ -223,6 +225,8 @@ int eg_init(int device, void* cuda_stream, eg_ctx** out) {
     if (e2 != cudaSuccess) { delete c; return eg_fail(EG_ERR_CUDA, cudaGetErrorString(e2)); }
     c->own_stream = true;
   }
+  cudaError_t e3 = cudaMalloc((void**)&c->d_next_episode, sizeof(uint32_t));
+  if (e3 != cudaSuccess) { if (c->own_stream) cudaStreamDestroy(c->stream); delete c; return eg_fail(EG_ERR_CUDA, cudaGetErrorString(e3)); }
   *out = c;
   return EG_OK;
 }
@@ -232,7 +236,7 @@ void eg_destroy(eg_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   free_map(c);
-  void* ptrs[] = {c->d_policy, c->s_out, c->s_traj, c->s_traj_in, c->s_sites, c->s_yearly};
+  void* ptrs[] = {c->d_policy, c->d_next_episode, c->s_out, c->s_traj, c->s_traj_in, c->s_sites, c->s_yearly};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->own_stream) cudaStreamDestroy(c->stream);

@@ -48,13 +48,18 @@ constexpr int kOffLdw = kOffLw + 8 * EG_N_ACTIONS;              // double[15]  t
 constexpr int kOffScratch = kOffLdw + 8 * EG_N_DEFICIT_KEYS;    // double2[32] fold staging | double[61] + uint8[64] sorted row
 constexpr int kScratchBytes = 8 * EG_N_ACTIONS + 64;            // 552 >= 512
 constexpr int kOffSortIdx = kOffScratch + 8 * EG_N_ACTIONS;     // uint8[64] (inside the scratch area)
-constexpr int kOffGens = kOffScratch + kScratchBytes;           // uint32[EG_MAX_NEW_GENERATORS]
-constexpr int kOffOffs = kOffGens + 4 * EG_MAX_NEW_GENERATORS;  // uint16[EG_MAX_OFFSETS]
+constexpr int kOffVars = kOffScratch + kScratchBytes;           // double[16]  rarely used episode scalars (kV*)
+constexpr int kOffGxy = kOffVars + 8 * 16;                      // uint16[EG_MAX_NEW_GENERATORS] plant cells (gi << 8) | gj
+constexpr int kOffGat = kOffGxy + 2 * EG_MAX_NEW_GENERATORS;    // uint16[EG_MAX_NEW_GENERATORS] type(4) mult(2) build(5)
+constexpr int kOffOffs = kOffGat + 2 * EG_MAX_NEW_GENERATORS;   // uint16[EG_MAX_OFFSETS]
 constexpr int kOffYearSites = kOffOffs + 2 * EG_MAX_OFFSETS;    // uint16[40]
 constexpr int kOffYearActions = kOffYearSites + 2 * EG_MAX_ACTIONS_PER_YEAR;  // uint8[40]
 constexpr int kOffCounts = kOffYearActions + EG_MAX_ACTIONS_PER_YEAR;         // uint8[26] deficit + uint8[26] additional
 constexpr int kOffNear = (kOffCounts + 2 * EG_NY + 15) & ~15;   // nearest-plant map, n_sites entries
-static_assert(kOffScratch % 16 == 0 && kOffGens % 8 == 0 && kOffOffs % 4 == 0 && kOffYearSites % 4 == 0 && kOffYearActions % 4 == 0, "alignment");
+static_assert(kOffScratch % 16 == 0 && kOffVars % 8 == 0 && kOffGxy % 8 == 0 && kOffOffs % 4 == 0 && kOffYearSites % 4 == 0 && kOffYearActions % 4 == 0, "alignment");
+
+// slots of the per-warp scalar area: values every lane agrees on that are touched a few times per year
+enum { kVTotalCost = 0, kVTotalCredit, kVTotalSales, kVGcostPrev, kVOcostPrev, kVLwTotal, kVInitNet, kVInitOpinion, kVInitBalance, kVInitCost };
 
 // ---- Philox4x32-10, counter = (episode lo, episode hi, draw, stream 0), key = seed ------------------------
 __device__ __noinline__ unsigned long long philox_u64(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2) {
@@ -87,9 +92,13 @@ __device__ __forceinline__ double action_impact(const State& cur, const State& n
 
 __device__ __forceinline__ double shfl_f64(double v, int src) { return __shfl_sync(kFull, v, src); }
 
-// packed plant: gj(8) gi(8) type(4) mult(2) build(5) — the low half has the byte order of the `order` table, (i << 8) | j
-__device__ __forceinline__ uint32_t pack_gen(int gi, int gj, int t, int m, int b) {
-  return (uint32_t)gj | ((uint32_t)gi << 8) | ((uint32_t)t << 16) | ((uint32_t)m << 20) | ((uint32_t)b << 22);
+// plant attributes: type(4) mult(2) build(5); plant cells use the byte order of the `order` table, (i << 8) | j
+__device__ __forceinline__ uint32_t pack_attr(int t, int m, int b) { return (uint32_t)t | ((uint32_t)m << 4) | ((uint32_t)b << 6); }
+
+// keeps a value in a register: the compiler may not re-derive it from its definition inside the hot loops
+__device__ __forceinline__ uint32_t opaque(uint32_t v) {
+  asm volatile("" : "+r"(v));
+  return v;
 }
 
 // sampling.rs:445-490 / 492-528: the fixed fallback tables (replay mode without a stored action)
@@ -164,26 +173,28 @@ struct Warp {
   const EgSmallTables* __restrict__ T;
   const int lane;
   const uint32_t sb;  // byte offset of this warp's slice in the block's dynamic shared memory
-  const uint32_t nf_off;  // byte offset of the block-shared near_factor copy (narrow maps)
   // warp-uniform episode state (identical in every lane)
   double gen0, gen1, gen2;    // plain / intermittent / storage generation accumulators
   double co2, op_sum;
-  double gcost, gcost_prev;   // capital cost of new plants re-priced at year / year-1 (map_handler.rs:955-958)
-  double ocost, ocost_prev;   // same for offsets (map_handler.rs:960-962)
+  double gcost, ocost;        // capital cost of new plants / offsets re-priced at the current year (map_handler.rs:955-962);
+                              // the same sums re-priced at year-1 live in the scalar area (kVGcostPrev, kVOcostPrev)
   double off_amount;          // calc_total_carbon_offset(year)
   uint32_t n_gens, n_offs, flags;
   bool rows_dirty, dw_dirty, sorted_valid, total_valid;
-  double lw_total;
-  // Philox: lane l holds draw number rbase + l
-  uint32_t k0, k1, e0, e1, draw, rbase;
+  // Philox: lane l holds draw number rbase + l of episode `rng_id`
+  unsigned long long rng_id;
+  uint32_t draw, rbase;
   unsigned long long rbuf;
 
-  __device__ Warp(const EgEpisodeParams& p_, uint32_t sb_, uint32_t nf_off_, int lane_) : p(p_), T(p_.map.small), lane(lane_), sb(sb_), nf_off(nf_off_) {}
+  __device__ Warp(const EgEpisodeParams& p_, uint32_t sb_, int lane_) : p(p_), T(p_.map.small), lane(lane_), sb(sb_) {}
+
+  __device__ __forceinline__ double* VARS() const { return (double*)(smem + sb + kOffVars); }
+  __device__ __forceinline__ uint16_t* GXY() const { return (uint16_t*)(smem + sb + kOffGxy); }
+  __device__ __forceinline__ uint16_t* GAT() const { return (uint16_t*)(smem + sb + kOffGat); }
 
   __device__ __forceinline__ double* LW() const { return (double*)(smem + sb + kOffLw); }
   __device__ __forceinline__ double* LDW() const { return (double*)(smem + sb + kOffLdw); }
   __device__ __forceinline__ double2* SCR() const { return (double2*)(smem + sb + kOffScratch); }
-  __device__ __forceinline__ uint32_t* GENS() const { return (uint32_t*)(smem + sb + kOffGens); }
   __device__ __forceinline__ uint16_t* OFFS() const { return (uint16_t*)(smem + sb + kOffOffs); }
   __device__ __forceinline__ uint16_t* YSITES() const { return (uint16_t*)(smem + sb + kOffYearSites); }
   __device__ __forceinline__ uint8_t* YACT() const { return smem + sb + kOffYearActions; }
@@ -197,7 +208,7 @@ struct Warp {
     uint32_t off = draw - rbase;
     if (off >= 32u) {
       rbase = draw;
-      rbuf = philox_u64(k0, k1, e0, e1, draw + (uint32_t)lane);
+      rbuf = philox_u64((uint32_t)p.seed, (uint32_t)(p.seed >> 32), (uint32_t)rng_id, (uint32_t)(rng_id >> 32), draw + (uint32_t)lane);
       off = 0;
     }
     draw++;
@@ -232,9 +243,9 @@ struct Warp {
     if (y == 0 || __ldg(&yr.prefix_changed) != 0) {
       gen0 = __ldg(&yr.ex_gen[0]); gen1 = __ldg(&yr.ex_gen[1]); gen2 = __ldg(&yr.ex_gen[2]);
       co2 = __ldg(&yr.ex_co2);
-      const uint32_t* gens = GENS();
+      const uint16_t* gat = GAT();
       for (uint32_t i = 0; i < n_gens; i++) {
-        const int t = (gens[i] >> 16) & 0xF;
+        const int t = gat[i] & 0xF;
         const int c = __ldg(&T->acc_class[t]);
         const double mw = __ldg(&T->net_mw[t]);
         // adding +0.0 leaves the other two accumulators unchanged bit for bit
@@ -245,15 +256,15 @@ struct Warp {
       }
     }
     op_sum = __ldg(&yr.ex_opinion_sum);
-    gcost_prev = gcost;
+    if (lane == 0) { VARS()[kVGcostPrev] = gcost; VARS()[kVOcostPrev] = ocost; }
     gcost = 0.0;
     const int n = p.map.grid_n;
     double2* scr = SCR();
     for (uint32_t base = 0; base < n_gens; base += 32) {
       const uint32_t i = base + lane;
       if (i < n_gens) {
-        const uint32_t g = GENS()[i];
-        const int gj = g & 0xFF, gi = (g >> 8) & 0xFF, t = (g >> 16) & 0xF, m = (g >> 20) & 0x3, b = (g >> 22) & 0x1F;
+        const uint32_t xy = GXY()[i], at = GAT()[i];
+        const int gj = xy & 0xFF, gi = xy >> 8, t = at & 0xF, m = (at >> 4) & 0x3, b = at >> 6;
         const double2 pt = plant_terms(t, m, b, y);
         scr[lane] = make_double2(gen_opinion(gi * n + gj, t, y, pt.x), pt.y);
       }
@@ -266,7 +277,6 @@ struct Warp {
       }
       __syncwarp();
     }
-    ocost_prev = ocost;
     ocost = 0.0; off_amount = 0.0;
     for (uint32_t base = 0; base < n_offs; base += 32) {
       const uint32_t i = base + lane;
@@ -309,11 +319,13 @@ struct Warp {
     const double* __restrict__ stat = p.map.static_score + base;
     const double* __restrict__ pref = p.map.prefix_score + base;
     // distance/radius by squared cell distance: block-shared copy in shared memory (narrow maps), else global
-    const double* __restrict__ nf = (sizeof(NearT) == 1 ? (const double*)(smem + nf_off) : p.map.near_factor) + (size_t)rc * p.map.r2_stride;
+    // (the block-shared copy sits at the start of the dynamic shared memory)
+    const uint32_t nf_row = opaque((uint32_t)(rc * p.map.r2_stride));
+    const double* __restrict__ nf = (sizeof(NearT) == 1 ? (const double*)smem : p.map.near_factor) + nf_row;
     const int nstride = p.map.near_stride;
     const double size_factor = __ldg(&T->size_factor);
     const NearT* nearest = NEAR();
-    const uint32_t* gens = GENS();
+    const uint16_t* gxy = GXY();
     double best_score = 0.0;
     int best_site = -1;
     for (int k0 = 0; k0 < ns; k0 += 32) {
@@ -360,15 +372,15 @@ struct Warp {
           // coordinates < 128: both byte differences at once, no borrow between the bytes, then di*di + dj*dj by IDP.4A
           const uint32_t spo = (uint32_t)packed | 0x8080u;
           for (uint32_t g = 0; g < n_gens; g++) {
-            const uint32_t v = ((spo - gens[g]) ^ 0x8080u) & 0xFFFFu;
+            const uint32_t v = (spo - gxy[g]) ^ 0x8080u;
             const int d2 = __dp4a((int)v, (int)v, 0);
             if (cand && d2 < r2lim) sc *= nf[d2];  // score *= distance / penalty_radius
           }
         } else {
           const int si = packed >> 8, sj = packed & 0xFF;
           for (uint32_t g = 0; g < n_gens; g++) {
-            const uint32_t pk = gens[g];
-            const int dj = sj - (int)(pk & 0xFF), di = si - (int)((pk >> 8) & 0xFF);
+            const uint32_t pk = gxy[g];
+            const int dj = sj - (int)(pk & 0xFF), di = si - (int)(pk >> 8);
             const int d2 = di * di + dj * dj;
             if (cand && d2 < r2lim) sc *= __ldg(&nf[d2]);
           }
@@ -394,23 +406,22 @@ struct Warp {
     if (n_gens >= EG_MAX_NEW_GENERATORS) { flags |= EG_FLAG_GEN_OVERFLOW; return; }
     const int n = p.map.grid_n;
     const int gi = site / n, gj = site - gi * n;
-    if (lane == 0) GENS()[n_gens] = pack_gen(gi, gj, t, m, y);
+    if (lane == 0) { GXY()[n_gens] = (uint16_t)((gi << 8) | gj); GAT()[n_gens] = (uint16_t)pack_attr(t, m, y); }
     n_gens++;
     // nearest-plant map: squared cell distance to the closest plant built in this episode. One 32-bit word (4 or 2
     // cells) per lane: packed minimum of the map word and the host-built pattern word for this column alignment.
     {
       constexpr int cpw = 4 / (int)sizeof(NearT);
-      const int R = p.map.kmax - 1, rows = 2 * R + 1, W = p.map.stamp_w, nstride = p.map.near_stride;
+      const int R = p.map.kmax - 1, rows = 2 * R + 1, wl = p.map.stamp_w_log2, nstride_w = p.map.near_stride / cpw;
       const int a = gj % cpw;
-      const int j0 = gj - a - (R + cpw - 1) / cpw * cpw;  // first column of the pattern, word aligned
-      const uint32_t* __restrict__ pat = p.map.stamp + (size_t)a * rows * W;
+      const int w0 = (gj - a - (R + cpw - 1) / cpw * cpw) / cpw;  // first word column of the pattern (may be negative)
+      const uint32_t* __restrict__ pat = p.map.stamp + (uint32_t)((a * rows) << wl);
       uint32_t* near_w = (uint32_t*)(smem + sb + kOffNear);
-      const int items = rows * W;
+      const int items = rows << wl;
       for (int it = lane; it < items; it += 32) {
-        const int r = it / W, w = it - r * W;
-        const int i = gi - R + r, jw = j0 + w * cpw;
-        if (i >= 0 && i < n && jw >= 0 && jw < nstride) {
-          uint32_t* cell = near_w + (i * nstride + jw) / cpw;
+        const int i = gi - R + (it >> wl), jw = w0 + (it & ((1 << wl) - 1));
+        if (i >= 0 && i < n && jw >= 0 && jw < nstride_w) {
+          uint32_t* cell = near_w + i * nstride_w + jw;
           const uint32_t pw = __ldg(&pat[it]);
           *cell = sizeof(NearT) == 1 ? __vminu4(*cell, pw) : __vminu2(*cell, pw);
         }
@@ -426,7 +437,7 @@ struct Warp {
     const double2 pt = plant_terms(t, m, y, y);
     op_sum += gen_opinion(site, t, y, pt.x);
     gcost += pt.y;
-    if (y > 0) gcost_prev += gen_cost(t, m, y, y - 1);
+    if (y > 0 && lane == 0) VARS()[kVGcostPrev] += gen_cost(t, m, y, y - 1);
   }
   __device__ __forceinline__ void add_offset(int ot, int m, int y) {
     if (n_offs >= EG_MAX_OFFSETS) { flags |= EG_FLAG_OFFSET_OVERFLOW; return; }
@@ -436,7 +447,7 @@ struct Warp {
     const double maturity = __ldg(&T->natural_offset[ot]) ? __ldg(&T->maturity[0]) : 1.0;
     off_amount += __ldg(&T->off_amount[ot]) * maturity;
     ocost += off_cost(ot, m, y);
-    if (y > 0) ocost_prev += off_cost(ot, m, y - 1);
+    if (y > 0 && lane == 0) VARS()[kVOcostPrev] += off_cost(ot, m, y - 1);
   }
 
   // ---- episode-local learning (the deficit handler edits this year's rows of its private weights) ----------
@@ -541,11 +552,13 @@ struct Warp {
     double total;
     if (rows_dirty) {
       if (!total_valid) {
-        lw_total = 0.0;
-        for (int k = 0; k < EG_N_ACTIONS; k++) lw_total += lw[k];
+        double t = 0.0;
+        for (int k = 0; k < EG_N_ACTIONS; k++) t += lw[k];
+        if (lane == 0) VARS()[kVLwTotal] = t;
         total_valid = true;
+        __syncwarp();
       }
-      total = lw_total;
+      total = VARS()[kVLwTotal];
     } else {
       total = __ldg(&p.policy->w_total[y]);
     }
@@ -592,9 +605,8 @@ struct Warp {
   }
 
   __device__ __forceinline__ void run(uint32_t ep) {
-    const unsigned long long id = p.same_stream ? 0ull : p.first_episode + ep;
-    k0 = (uint32_t)p.seed; k1 = (uint32_t)(p.seed >> 32);
-    e0 = (uint32_t)id; e1 = (uint32_t)(id >> 32); draw = 0; rbase = 0x80000000u; rbuf = 0ull;
+    rng_id = p.same_stream ? 0ull : p.first_episode + ep;
+    draw = 0; rbase = 0x80000000u; rbuf = 0ull;
     n_gens = 0; n_offs = 0; flags = 0;
     gcost = 0.0; ocost = 0.0; gen0 = gen1 = gen2 = 0.0; co2 = 0.0;
     {
@@ -605,9 +617,8 @@ struct Warp {
     }
     __syncwarp();
     const eg_traj* in = REPLAY ? p.replay_in + ep : nullptr;
-    double total_cost = 0.0, total_credit = 0.0, total_sales = 0.0;
     uint32_t n_def_total = 0, n_add_total = 0;
-    double r_net = 0.0, r_opinion = 0.0, r_cost = 0.0, r_rel = 0.0;
+    double* vars = VARS();
     const bool learn = !REPLAY && !p.replay_best;
 
     for (int y = 0; y < EG_NY; y++) {
@@ -615,7 +626,9 @@ struct Warp {
       if (!REPLAY) load_rows(y);
       State cur = state(y);                                  // state of the map after the latest change
       bool deficit_mode = cur.balance < 0.0;                 // simulation.rs:137
-      const State initial = cur;                             // simulation.rs:341-356
+      if (deficit_mode && lane == 0) {                       // initial state of handle_power_deficit, simulation.rs:341-356
+        vars[kVInitNet] = cur.net; vars[kVInitOpinion] = cur.opinion; vars[kVInitBalance] = cur.balance; vars[kVInitCost] = cur.cost;
+      }
       double remaining = deficit_mode ? -cur.balance : 0.0;  // Map::handle_power_deficit returns it unchanged (Q2)
       uint32_t attempts = 0, n_def = 0, n_add = 0, n_to_add = 0, replay_def = 0, replay_act = 0;
       bool counted = false;
@@ -632,6 +645,9 @@ struct Warp {
             is_def = true;
           } else {                                           // simulation.rs:490-519
             if (learn) {
+              __syncwarp();
+              State initial;
+              initial.net = vars[kVInitNet]; initial.opinion = vars[kVInitOpinion]; initial.balance = vars[kVInitBalance]; initial.cost = vars[kVInitCost];
               const double overall_success = action_impact(initial, cur);
               if (cur.balance >= 0.0 && overall_success > 0.0 && n_def > 0) {
                 const double success_factor = 0.1 * overall_success;
@@ -721,23 +737,27 @@ struct Warp {
       }
       __syncwarp();
 
-      // calculate_yearly_metrics, analysis/metrics_calculation.rs:32-175
-      const EgYearRow& yr = T->year[y];
-      const double usage = __ldg(&yr.usage_total);
-      const double generation = gen0 + gen1 + gen2;
-      const double balance = generation - usage;
-      const double net = co2 - off_amount;
-      const double credit = net >= 0.0 ? 0.0 : (-net) * __ldg(&yr.carbon_price);
-      const uint32_t active = __ldg(&yr.ex_active) + n_gens;
-      const double total_capital = gcost + ocost;
-      const double yearly_capital = y == 0 ? total_capital : total_capital - (gcost_prev + ocost_prev);
-      const double sales = (p.energy_sales && balance > 0.0) ? (balance * 8.76) * 50000.0 : 0.0;
-      const double yearly_total = yearly_capital + 0.0 + 0.0 - credit - (p.energy_sales ? sales : 0.0);
-      if (y == 0) { total_cost = yearly_total; total_credit = credit; total_sales = sales; }
-      else { total_cost = total_cost + yearly_total; total_credit = total_credit + credit; total_sales = total_sales + sales; }
-      if (p.yearly || y == EG_NY - 1) {
+      // calculate_yearly_metrics, analysis/metrics_calculation.rs:32-175 (only the rows somebody asked for; the
+      // episode result needs the 2050 row alone, iteration.rs:57-84)
+      if (p.yearly) {
+        const EgYearRow& yr = T->year[y];
+        const double usage = __ldg(&yr.usage_total);
+        const double generation = gen0 + gen1 + gen2;
+        const double balance = generation - usage;
+        const double net = co2 - off_amount;
+        const double credit = net >= 0.0 ? 0.0 : (-net) * __ldg(&yr.carbon_price);
+        const uint32_t active = __ldg(&yr.ex_active) + n_gens;
+        const double total_capital = gcost + ocost;
+        const double yearly_capital = y == 0 ? total_capital : total_capital - (vars[kVGcostPrev] + vars[kVOcostPrev]);
+        const double sales = (p.energy_sales && balance > 0.0) ? (balance * 8.76) * 50000.0 : 0.0;
+        const double yearly_total = yearly_capital + 0.0 + 0.0 - credit - (p.energy_sales ? sales : 0.0);
+        double total_cost, total_credit, total_sales;
+        if (y == 0) { total_cost = yearly_total; total_credit = credit; total_sales = sales; }
+        else { total_cost = vars[kVTotalCost] + yearly_total; total_credit = vars[kVTotalCredit] + credit; total_sales = vars[kVTotalSales] + sales; }
         const double opinion = active > 0 ? op_sum / (double)active : 1.0;
-        if (p.yearly && lane == 0) {
+        __syncwarp();
+        if (lane == 0) {
+          vars[kVTotalCost] = total_cost; vars[kVTotalCredit] = total_credit; vars[kVTotalSales] = total_sales;
           eg_year_metrics& m = p.yearly[ep].y[y];
           m.total_population = __ldg(&yr.pop_total);
           m.active_generators = active;
@@ -759,14 +779,17 @@ struct Warp {
           m.total_cost = total_cost;
           m.reserved = 0.0;
         }
-        if (y == EG_NY - 1) {  // iteration.rs:57-84
-          r_net = net;
-          r_opinion = opinion;
-          r_cost = total_capital;
-          r_rel = balance >= 0.0 ? 1.0 : 0.0;
-        }
+        __syncwarp();
       }
     }
+
+    // SimulationMetrics from the 2050 state (iteration.rs:57-84); nothing changed since the last year's actions
+    const EgYearRow& last = T->year[EG_NY - 1];
+    const double r_net = co2 - off_amount;
+    const uint32_t r_active = __ldg(&last.ex_active) + n_gens;
+    const double r_opinion = r_active > 0 ? op_sum / (double)r_active : 1.0;
+    const double r_cost = gcost + ocost;
+    const double r_rel = ((gen0 + gen1 + gen2) - __ldg(&last.usage_total)) >= 0.0 ? 1.0 : 0.0;
 
     // score_metrics, scoring.rs:5-45 (ln evaluated on the device: <= 1 ulp from the host libm)
     double score;
@@ -806,19 +829,24 @@ struct Warp {
 };
 
 template <bool REPLAY, typename NearT>
-__global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) eg_episode_kernel(const __grid_constant__ EgEpisodeParams p, int slice_bytes) {
+__global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) eg_episode_kernel(const __grid_constant__ EgEpisodeParams p, int slice_bytes, int table_bytes) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t nf_off = (uint32_t)((blockDim.x >> 5) * slice_bytes);
-  if (sizeof(NearT) == 1) {  // block-shared copy of the distance/radius factors
-    double* nf_s = (double*)(smem + nf_off);
+  if (sizeof(NearT) == 1) {  // block-shared copy of the distance/radius factors at the start of the shared memory
+    double* nf_s = (double*)smem;
     const int cnt = EG_N_RCLASS * p.map.r2_stride;
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) nf_s[i] = __ldg(&p.map.near_factor[i]);
     __syncthreads();
   }
-  const uint32_t ep = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (ep >= p.n) return;  // whole warps leave together
-  Warp<REPLAY, NearT> w(p, (uint32_t)(warp * slice_bytes), nf_off, lane);
-  w.run(ep);
+  Warp<REPLAY, NearT> w(p, opaque((uint32_t)(table_bytes + warp * slice_bytes)), lane);
+  // persistent warps: every warp fetches the next unclaimed episode of the batch until none is left, so a short
+  // episode never leaves its warp idle while the block's longest one finishes
+  for (;;) {
+    uint32_t ep = 0;
+    if (lane == 0) ep = atomicAdd(p.next_episode, 1u);
+    ep = __shfl_sync(kFull, ep, 0);
+    if (ep >= p.n) break;
+    w.run(ep);
+  }
 }
 
 template <bool REPLAY, typename NearT>
@@ -826,20 +854,29 @@ cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
   const bool wide = sizeof(NearT) == 2;
   const int near_bytes = p.map.grid_n * p.map.near_stride * (int)sizeof(NearT);
   const int slice = (kOffNear + near_bytes + 15) & ~15;
-  const int shared_tab = wide ? 0 : EG_N_RCLASS * p.map.r2_stride * (int)sizeof(double);
+  const int shared_tab = wide ? 0 : (EG_N_RCLASS * p.map.r2_stride * (int)sizeof(double) + 15) & ~15;
   // as many warps per block as keep several blocks resident in the 227 KB of an SM
   int warps = EG_EPISODE_WARPS;
   while (warps > 1 && warps * slice + shared_tab > 100 * 1024) warps >>= 1;
   const size_t smem_bytes = (size_t)warps * slice + shared_tab;
   if (smem_bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
-  const uint32_t blocks = (p.n + warps - 1) / warps;
-  // shared-memory carveout: room for as many blocks as the register budget allows, the rest stays L1
-  const int resident = (int)std::min<size_t>(EG_EPISODE_MIN_BLOCKS * (EG_EPISODE_WARPS / warps), (227 * 1024) / (smem_bytes + 1024));
-  const int carveout = std::min(100, (int)((resident * (smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
   cudaError_t err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, NearT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (err != cudaSuccess) return err;
+  // shared-memory carveout: room for as many blocks as the register budget allows, the rest stays L1
+  const int resident_want = (int)std::min<size_t>(EG_EPISODE_MIN_BLOCKS * (EG_EPISODE_WARPS / warps), (227 * 1024) / (smem_bytes + 1024));
+  const int carveout = std::min(100, (int)((resident_want * (smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
   cudaFuncSetAttribute(eg_episode_kernel<REPLAY, NearT>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
-  eg_episode_kernel<REPLAY, NearT><<<blocks, 32 * warps, smem_bytes, stream>>>(p, slice);
+  // grid = every block the device can hold at once (a multiple of the SM count), never more warps than episodes
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eg_episode_kernel<REPLAY, NearT>, 32 * warps, smem_bytes);
+  if (err != cudaSuccess) return err;
+  if (per_sm < 1) return cudaErrorInvalidConfiguration;
+  const uint32_t blocks = std::min<uint32_t>((uint32_t)(sms * per_sm), (p.n + warps - 1) / warps);
+  err = cudaMemsetAsync(p.next_episode, 0, sizeof(uint32_t), stream);
+  if (err != cudaSuccess) return err;
+  eg_episode_kernel<REPLAY, NearT><<<blocks, 32 * warps, smem_bytes, stream>>>(p, slice, shared_tab);
   return cudaGetLastError();
 }
 

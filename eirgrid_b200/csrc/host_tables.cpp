@@ -390,11 +390,14 @@ void eg_host_build_tables(const EgHostMap& m, EgHostTables* out) {
   const int R = kmax - 1, rows = 2 * R + 1;
   const int Rp = (R + cpw - 1) / cpw * cpw;                   // pattern starts at column gj - (gj mod cpw) - Rp: word aligned
   out->near_stride = (m.grid_n + cpw - 1) / cpw * cpw;
-  out->stamp_w = (Rp + cpw - 1 + R + 1 + cpw - 1) / cpw;      // words covering columns up to gj + R
-  out->stamp.assign((size_t)cpw * rows * out->stamp_w, 0xFFFFFFFFu);
+  const int words = (Rp + cpw - 1 + R + 1 + cpw - 1) / cpw;   // words covering columns up to gj + R
+  out->stamp_w_log2 = 0;
+  while ((1 << out->stamp_w_log2) < words) out->stamp_w_log2++;
+  const int Wp = 1 << out->stamp_w_log2;                      // padded row (padding = far: a no-op minimum)
+  out->stamp.assign((size_t)cpw * rows * Wp, 0xFFFFFFFFu);
   for (int a = 0; a < cpw; a++)
     for (int r = 0; r < rows; r++)
-      for (int w = 0; w < out->stamp_w; w++) {
+      for (int w = 0; w < words; w++) {
         uint32_t word = 0;
         for (int b = 0; b < cpw; b++) {
           const int di = r - R, dj = w * cpw + b - Rp - a;
@@ -403,7 +406,7 @@ void eg_host_build_tables(const EgHostMap& m, EgHostTables* out) {
           const uint32_t v = (std::abs(dj) <= R && d2 < stride) ? (uint32_t)d2 : far;  // only cells inside the largest radius matter
           word |= v << (b * (32 / cpw));
         }
-        out->stamp[((size_t)a * rows + r) * out->stamp_w + w] = word;
+        out->stamp[((size_t)a * rows + r) * Wp + w] = word;
       }
   (void)kRadius;
 }

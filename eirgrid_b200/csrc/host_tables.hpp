@@ -23,7 +23,7 @@ struct EgHostTables {
   int r2_stride = 0;
   int kmax = 0;
   std::vector<uint32_t> stamp;       // [cells per word][2*(kmax-1)+1][stamp_w]
-  int stamp_w = 0;
+  int stamp_w_log2 = 0;
   int near_stride = 0;
   int near_wide = 0;
 };

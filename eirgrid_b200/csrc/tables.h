@@ -79,7 +79,7 @@ struct EgDeviceMap {      // device pointers + sizes, passed by value to the ker
   // packed minima against this pattern: [cells per word][2*(kmax-1)+1 rows][stamp_w words], the squared distances
   // around a plant whose column is congruent to the first index modulo the cells per word.
   const uint32_t* stamp;
-  int stamp_w;
+  int stamp_w_log2;               // pattern rows are padded to 1 << stamp_w_log2 words
   int near_stride;
   int near_wide;
 };
