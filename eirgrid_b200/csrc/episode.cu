@@ -95,6 +95,13 @@ __device__ __forceinline__ double shfl_f64(double v, int src) { return __shfl_sy
 // plant attributes: type(4) mult(2) build(5); plant cells use the byte order of the `order` table, (i << 8) | j
 __device__ __forceinline__ uint32_t pack_attr(int t, int m, int b) { return (uint32_t)t | ((uint32_t)m << 4) | ((uint32_t)b << 6); }
 
+// read-only table in shared memory addressed by a 32-bit shared-window address (kept in a register by the caller)
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
 // keeps a value in a register: the compiler may not re-derive it from its definition inside the hot loops
 __device__ __forceinline__ uint32_t opaque(uint32_t v) {
   asm volatile("" : "+r"(v));
@@ -320,8 +327,8 @@ struct Warp {
     const double* __restrict__ pref = p.map.prefix_score + base;
     // distance/radius by squared cell distance: block-shared copy in shared memory (narrow maps), else global
     // (the block-shared copy sits at the start of the dynamic shared memory)
-    const uint32_t nf_row = opaque((uint32_t)(rc * p.map.r2_stride));
-    const double* __restrict__ nf = (sizeof(NearT) == 1 ? (const double*)smem : p.map.near_factor) + nf_row;
+    const double* __restrict__ nf = p.map.near_factor + rc * p.map.r2_stride;
+    const uint32_t nf_s = opaque((uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)(rc * p.map.r2_stride) * 8u);
     const int nstride = p.map.near_stride;
     const double size_factor = __ldg(&T->size_factor);
     const NearT* nearest = NEAR();
@@ -360,7 +367,7 @@ struct Warp {
       double pre = 0.0;
       if (inr) {
         pre = __ldg(&pref[k]);
-        double bound = pre * nf[d2n];
+        double bound = pre * (sizeof(NearT) == 1 ? lds_f64(nf_s + 8u * (uint32_t)d2n) : __ldg(&nf[d2n]));
         if (water) bound *= __ldg(&p.map.coast_factor[site]);
         bound *= size_factor;
         cand = bound > 0.0 && !(bound < best_score);
@@ -374,7 +381,7 @@ struct Warp {
           for (uint32_t g = 0; g < n_gens; g++) {
             const uint32_t v = (spo - gxy[g]) ^ 0x8080u;
             const int d2 = __dp4a((int)v, (int)v, 0);
-            if (cand && d2 < r2lim) sc *= nf[d2];  // score *= distance / penalty_radius
+            if (cand && d2 < r2lim) sc *= lds_f64(nf_s + 8u * (uint32_t)d2);  // score *= distance / penalty_radius
           }
         } else {
           const int si = packed >> 8, sj = packed & 0xFF;

@@ -26,7 +26,7 @@ struct EgEpisodeParams {
 #define EG_EPISODE_WARPS 4   // episodes (warps) per block for the Irish map; fewer when the per-warp slice is large
 #endif
 #ifndef EG_EPISODE_MIN_BLOCKS
-#define EG_EPISODE_MIN_BLOCKS 6  // register cap 65536 / (128 threads * 6) = 80; 6 blocks of (4 slices + factor table) fill the shared memory
+#define EG_EPISODE_MIN_BLOCKS 5  // register cap 65536 / (128 threads * 5) = 96; measured best of {4w x 4,5,6; 2w x 8,10; 6w x 3; 8w x 2,3} on B200
 #endif
 
 cudaError_t eg_launch_rollout(const EgEpisodeParams& p, cudaStream_t stream);
