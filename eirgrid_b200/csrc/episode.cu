@@ -512,12 +512,14 @@ struct Warp {
     double total;
     if (dw_dirty) {
       total = 0.0;
+      #pragma unroll 4
       for (int k = 0; k < 14; k++) total += ldw[k];
     } else {
       total = __ldg(&p.policy->dw_total[y]);  // same left-to-right sum, done once per snapshot on the host
     }
     if (total <= 0.0) return kGasPeaker100;
     double rv = f64() * total;
+    #pragma unroll 4
     for (int k = 0; k < 14; k++) {
       rv -= ldw[k];
       if (rv <= 0.0) return deficit_key_action(k);
@@ -532,6 +534,7 @@ struct Warp {
       const double total = __ldg(&p.policy->cw_total[y]);
       if (total <= 0.0) return 0;
       double rc = random_val * total;
+      #pragma unroll 4
       for (int c = 0; c < EG_N_COUNT_KEYS; c++) {
         rc -= __ldg(&p.policy->cw[y][c]);
         if (rc <= 0.0) return min((uint32_t)c, max_possible);
@@ -560,6 +563,7 @@ struct Warp {
     if (rows_dirty) {
       if (!total_valid) {
         double t = 0.0;
+        #pragma unroll 4
         for (int k = 0; k < EG_N_ACTIONS; k++) t += lw[k];
         if (lane == 0) VARS()[kVLwTotal] = t;
         total_valid = true;
@@ -577,8 +581,10 @@ struct Warp {
         if (!sorted_valid) { sort_local(sb, lane, p.policy->stagnation_power); sorted_valid = true; }
         double total_scaled = 0.0;
         const double* scl = (const double*)(smem + sb + kOffScratch);
+        #pragma unroll 1
         for (int k = 0; k < EG_N_ACTIONS; k++) total_scaled += scl[k];
         double rv = f64() * total_scaled;
+        #pragma unroll 1
         for (int k = 0; k < EG_N_ACTIONS; k++) {
           rv -= scl[k];
           if (rv <= 0.0) return (smem + sb + kOffSortIdx)[k];
@@ -587,8 +593,10 @@ struct Warp {
       }
       sc = p.policy->scaled_sorted[y]; idx = p.policy->sorted_idx[y];  // host libm, per snapshot
       double total_scaled = 0.0;
+      #pragma unroll 1
       for (int k = 0; k < EG_N_ACTIONS; k++) total_scaled += __ldg(&sc[k]);
       double rv = f64() * total_scaled;
+      #pragma unroll 1
       for (int k = 0; k < EG_N_ACTIONS; k++) {
         rv -= __ldg(&sc[k]);
         if (rv <= 0.0) return idx[k];
@@ -596,6 +604,7 @@ struct Warp {
       return idx[0];
     }
     double rv = f64() * total;
+    #pragma unroll 4
     for (int k = 0; k < EG_N_ACTIONS; k++) {
       rv -= lw[k];
       if (rv <= 0.0) return k;
