@@ -75,16 +75,20 @@ __device__ __noinline__ unsigned long long philox_u64(uint32_t k0, uint32_t k1, 
   return (unsigned long long)c0 | ((unsigned long long)c1 << 32);
 }
 
+// IEEE-754 double division (correctly rounded, like the reference's `/`). One out-of-line copy: the kernel is bound
+// by instruction fetch, and ~20 inlined division sequences were a fifth of its hot code.
+__device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+
 struct State {  // ActionResult, ai/metrics/simulation_metrics.rs:14-19
   double net, opinion, balance, cost;
 };
 
 // evaluate_action_impact(.., None), scoring.rs:60-84
 __device__ __forceinline__ double action_impact(const State& cur, const State& nw) {
-  if (cur.net > 0.0) return (cur.net - nw.net) / fmax(fabs(cur.net), 1.0);
+  if (cur.net > 0.0) return ddiv(cur.net - nw.net, fmax(fabs(cur.net), 1.0));
   double cost_change = nw.cost - cur.cost;
-  double cost_improvement = -cost_change / fmax(fabs(cur.cost), 1.0);
-  double opinion_improvement = (nw.opinion - cur.opinion) / fmax(fabs(cur.opinion), 1.0);
+  double cost_improvement = ddiv(-cost_change, fmax(fabs(cur.cost), 1.0));
+  double opinion_improvement = ddiv(nw.opinion - cur.opinion, fmax(fabs(cur.opinion), 1.0));
   double cost_weight = cur.cost > kMaxAcceptableCost * 8.0 ? 0.8 : 0.5;
   double opinion_weight = 1.0 - cost_weight;
   return cost_improvement * cost_weight + opinion_improvement * opinion_weight;
@@ -251,6 +255,7 @@ struct Warp {
       gen0 = __ldg(&yr.ex_gen[0]); gen1 = __ldg(&yr.ex_gen[1]); gen2 = __ldg(&yr.ex_gen[2]);
       co2 = __ldg(&yr.ex_co2);
       const uint16_t* gat = GAT();
+#pragma unroll 1
       for (uint32_t i = 0; i < n_gens; i++) {
         const int t = gat[i] & 0xF;
         const int c = __ldg(&T->acc_class[t]);
@@ -277,6 +282,7 @@ struct Warp {
       }
       __syncwarp();
       const int cnt = min(32u, n_gens - base);
+#pragma unroll 2
       for (int j = 0; j < cnt; j++) {
         const double2 v = scr[j];
         op_sum += v.x;
@@ -295,6 +301,7 @@ struct Warp {
       }
       __syncwarp();
       const int cnt = min(32u, n_offs - base);
+#pragma unroll 2
       for (int j = 0; j < cnt; j++) {
         const double2 v = scr[j];
         off_amount += v.x;
@@ -308,7 +315,7 @@ struct Warp {
     State s;
     s.net = co2 - off_amount;
     const uint32_t cnt = __ldg(&T->year[y].ex_active) + n_gens;
-    s.opinion = cnt > 0 ? op_sum / (double)cnt : 1.0;
+    s.opinion = cnt > 0 ? ddiv(op_sum, (double)cnt) : 1.0;
     s.balance = (gen0 + gen1 + gen2) - __ldg(&T->year[y].usage_total);
     s.cost = gcost + ocost;
     return s;
@@ -394,15 +401,14 @@ struct Warp {
         }
         if (water) sc *= __ldg(&p.map.coast_factor[site]);
         sc *= size_factor;
-        // strict '>' in scan order: the maximum wins, equal scores keep the lower site
-        double c_score = cand ? sc : -1.0;
-        int c_site = cand ? site : 0x7FFFFFFF;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double o_score = __shfl_xor_sync(kFull, c_score, o);
-          const int o_site = __shfl_xor_sync(kFull, c_site, o);
-          if (o_score > c_score || (o_score == c_score && o_site < c_site)) { c_score = o_score; c_site = o_site; }
-        }
+        // strict '>' in scan order: the maximum wins, equal scores keep the lower site. Scores are >= 0, so their
+        // high and low words order like the doubles: two 32-bit maximum reductions give the exact maximum.
+        const uint32_t hi = cand ? (uint32_t)__double2hiint(sc) : 0u;
+        const uint32_t mh = __reduce_max_sync(kFull, hi);
+        const uint32_t lo = (cand && hi == mh) ? (uint32_t)__double2loint(sc) : 0u;
+        const uint32_t ml = __reduce_max_sync(kFull, lo);
+        const int c_site = (int)__reduce_min_sync(kFull, (cand && hi == mh && lo == ml) ? (uint32_t)site : 0x7FFFFFFFu);
+        const double c_score = __hiloint2double((int)mh, (int)ml);
         if (c_score > best_score || (c_score == best_score && best_site >= 0 && c_site < best_site)) { best_score = c_score; best_site = c_site; }
       }
     }
@@ -471,7 +477,7 @@ struct Warp {
     const int key = deficit_key_of_type(t);
     if (action >= 45 || key == 0xF || action - 3 * t != 0) return;
     const double lr = p.policy->learning_rate;
-    const double adj = improvement > 0.0 ? 1.0 + (lr * improvement * 1.5) : 1.0 / (1.0 + (lr * fabs(improvement) * 1.5));
+    const double adj = improvement > 0.0 ? 1.0 + (lr * improvement * 1.5) : ddiv(1.0, 1.0 + (lr * fabs(improvement) * 1.5));
     const double boost = 1.0 + (lr * 0.1);
     double* ldw = LDW();
     if (lane < 14) {
@@ -486,7 +492,7 @@ struct Warp {
     const double rel = p.policy->relative_improvement;
     const double immediate = rel > 0.0 ? 0.7 : 0.3;
     const double combined = immediate * improvement + (1.0 - immediate) * rel;
-    const double adj = combined > 0.0 ? 1.0 + (lr * combined) : 1.0 / (1.0 + (lr * fabs(combined)));
+    const double adj = combined > 0.0 ? 1.0 + (lr * combined) : ddiv(1.0, 1.0 + (lr * fabs(combined)));
     const double boost = 1.0 + (lr * 0.1);
     double* lw = LW();
     for (int k = lane; k < EG_N_ACTIONS; k += 32) {
@@ -542,7 +548,7 @@ struct Warp {
       return min(5u, max_possible);
     }
     const double scaled_eps = sqrt(p.policy->exploration_rate);  // powf(0.5) of a non-negative value
-    const uint32_t min_actions = (uint32_t)round(2.0 / scaled_eps), max_actions = (uint32_t)round(12.0 / scaled_eps);
+    const uint32_t min_actions = (uint32_t)round(ddiv(2.0, scaled_eps)), max_actions = (uint32_t)round(ddiv(12.0, scaled_eps));
     const uint32_t cmax = min(max_actions, max_possible), cmin = min(min_actions, cmax);
     if (cmin == cmax) return cmin;
     return cmin + index(cmax - cmin + 1);
@@ -555,7 +561,7 @@ struct Warp {
     }
     const uint32_t iwi = p.policy->iwi;
     const double eps = p.policy->exploration_rate;
-    const double cur_eps = iwi > 100 ? eps * (1.0 / (1.0 + 0.01 * (double)iwi)) : eps;
+    const double cur_eps = iwi > 100 ? eps * ddiv(1.0, 1.0 + 0.01 * (double)iwi) : eps;
     const bool explore = f64() < cur_eps;
     if (explore) return (int)index(EG_N_ACTIONS);
     const double* lw = LW();
@@ -629,6 +635,7 @@ struct Warp {
       // clear the nearest-plant map, 4 bytes per lane and step (n_sites entries, padded to 16 bytes by the launcher)
       uint32_t* nw = (uint32_t*)(smem + sb + kOffNear);
       const int words = (p.map.grid_n * p.map.near_stride * (int)sizeof(NearT) + 3) / 4;
+#pragma unroll 2
       for (int i = lane; i < words; i += 32) nw[i] = 0xFFFFFFFFu;
     }
     __syncwarp();
@@ -710,13 +717,13 @@ struct Warp {
           const State after = state(y);                      // simulation.rs:412-427
           if (learn) {
             const double overall = action_impact(cur, after);
-            const double emis = after.net < cur.net ? (cur.net - after.net) / fmax(fabs(cur.net), 1.0) : 0.0;
+            const double emis = after.net < cur.net ? ddiv(cur.net - after.net, fmax(fabs(cur.net), 1.0)) : 0.0;
             double cost_imp = 0.0;
             if (after.net < 1000.0) {
               const double cost_change = after.cost - cur.cost;
-              cost_imp = -cost_change / fmax(fabs(cur.cost), 1.0);
+              cost_imp = ddiv(-cost_change, fmax(fabs(cur.cost), 1.0));
             }
-            const double op_imp = after.cost < kMaxAcceptableCost * 8.0 ? (after.opinion - cur.opinion) / fmax(1.0 - cur.opinion, 0.1) : 0.0;
+            const double op_imp = after.cost < kMaxAcceptableCost * 8.0 ? ddiv(after.opinion - cur.opinion, fmax(1.0 - cur.opinion, 0.1)) : 0.0;
             const double combined = overall * 0.7 + emis * 0.15 + cost_imp * 0.1 + op_imp * 0.05;
             __syncwarp();
             update_deficit_weights(y, action, combined);     // simulation.rs:479
@@ -770,7 +777,7 @@ struct Warp {
         double total_cost, total_credit, total_sales;
         if (y == 0) { total_cost = yearly_total; total_credit = credit; total_sales = sales; }
         else { total_cost = vars[kVTotalCost] + yearly_total; total_credit = vars[kVTotalCredit] + credit; total_sales = vars[kVTotalSales] + sales; }
-        const double opinion = active > 0 ? op_sum / (double)active : 1.0;
+        const double opinion = active > 0 ? ddiv(op_sum, (double)active) : 1.0;
         __syncwarp();
         if (lane == 0) {
           vars[kVTotalCost] = total_cost; vars[kVTotalCredit] = total_credit; vars[kVTotalSales] = total_sales;
@@ -803,17 +810,17 @@ struct Warp {
     const EgYearRow& last = T->year[EG_NY - 1];
     const double r_net = co2 - off_amount;
     const uint32_t r_active = __ldg(&last.ex_active) + n_gens;
-    const double r_opinion = r_active > 0 ? op_sum / (double)r_active : 1.0;
+    const double r_opinion = r_active > 0 ? ddiv(op_sum, (double)r_active) : 1.0;
     const double r_cost = gcost + ocost;
     const double r_rel = ((gen0 + gen1 + gen2) - __ldg(&last.usage_total)) >= 0.0 ? 1.0 : 0.0;
 
     // score_metrics, scoring.rs:5-45 (ln evaluated on the device: <= 1 ulp from the host libm)
     double score;
     {
-      const double normalized_cost = fmax(r_cost / kMaxAcceptableCost, 1.0);
-      const double cost_term = fmin(log(normalized_cost) / p.ln100, 1.0);
+      const double normalized_cost = fmax(ddiv(r_cost, kMaxAcceptableCost), 1.0);
+      const double cost_term = fmin(ddiv(log(normalized_cost), p.ln100), 1.0);
       if (p.cost_only) score = 2.0 - cost_term;
-      else if (r_net > 0.0) score = 1.0 - fmin(r_net / kMaxAcceptableEmissions, 1.0);
+      else if (r_net > 0.0) score = 1.0 - fmin(ddiv(r_net, kMaxAcceptableEmissions), 1.0);
       else {
         const double cost_score = 1.0 - cost_term;
         const double cost_weight = normalized_cost > 8.0 ? 0.8 : 0.5;
