@@ -48,6 +48,7 @@ struct eg_ctx {
   uint16_t* d_order = nullptr;
   double* d_static_sorted = nullptr;
   double* d_prefix_sorted = nullptr;
+  double* d_walk = nullptr;            // [7][26][ns][2]
   double* d_near = nullptr;
   int* d_r2_limit = nullptr;
   double *d_sx = nullptr, *d_sy = nullptr, *d_ex = nullptr, *d_ey = nullptr, *d_cx = nullptr, *d_cy = nullptr;
@@ -69,11 +70,11 @@ namespace {
 
 void free_map(eg_ctx* c) {
   void* ptrs[] = {c->d_small, c->d_plant_terms, c->d_stamp, c->d_site_opinion, c->d_coast, c->d_prefix, c->d_static_unsorted, c->d_order,
-                  c->d_static_sorted, c->d_prefix_sorted, c->d_near, c->d_r2_limit, c->d_sx, c->d_sy, c->d_ex, c->d_ey, c->d_cx, c->d_cy, c->d_pop};
+                  c->d_static_sorted, c->d_prefix_sorted, c->d_walk, c->d_near, c->d_r2_limit, c->d_sx, c->d_sy, c->d_ex, c->d_ey, c->d_cx, c->d_cy, c->d_pop};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   c->d_small = nullptr; c->d_plant_terms = nullptr; c->d_stamp = nullptr; c->d_site_opinion = nullptr; c->d_coast = nullptr; c->d_prefix = nullptr;
-  c->d_static_unsorted = nullptr; c->d_order = nullptr; c->d_static_sorted = nullptr; c->d_prefix_sorted = nullptr;
+  c->d_static_unsorted = nullptr; c->d_order = nullptr; c->d_static_sorted = nullptr; c->d_prefix_sorted = nullptr; c->d_walk = nullptr;
   c->d_near = nullptr; c->d_r2_limit = nullptr; c->d_sx = c->d_sy = c->d_ex = c->d_ey = c->d_cx = c->d_cy = nullptr; c->d_pop = nullptr;
   c->map_ready = false;
 }
@@ -98,7 +99,7 @@ int build_device_map(eg_ctx* c) {
   if ((rc = upload(&c->d_plant_terms, c->htab.plant_terms.data(), c->htab.plant_terms.size(), s))) return rc;
   if ((rc = upload(&c->d_stamp, c->htab.stamp.data(), c->htab.stamp.size(), s))) return rc;
   if ((rc = upload(&c->d_near, c->htab.near_factor.data(), c->htab.near_factor.size(), s))) return rc;
-  if ((rc = upload(&c->d_r2_limit, c->htab.r2_limit, (size_t)EG_N_RCLASS, s))) return rc;
+  if ((rc = upload(&c->d_r2_limit, c->htab.r2_limit, (size_t)(2 * EG_N_RCLASS + 1), s))) return rc;
   if ((rc = upload(&c->d_sx, m.sx.data(), m.sx.size(), s))) return rc;
   if ((rc = upload(&c->d_sy, m.sy.data(), m.sy.size(), s))) return rc;
   if ((rc = upload(&c->d_ex, m.ex.data(), m.ex.size(), s))) return rc;
@@ -113,6 +114,7 @@ int build_device_map(eg_ctx* c) {
   EG_CUDA(cudaMalloc((void**)&c->d_order, (size_t)EG_N_PCLASS * EG_NY * ns * sizeof(uint16_t)));
   EG_CUDA(cudaMalloc((void**)&c->d_static_sorted, (size_t)EG_N_PCLASS * EG_NY * ns * sizeof(double)));
   EG_CUDA(cudaMalloc((void**)&c->d_prefix_sorted, (size_t)EG_N_PCLASS * EG_NY * ns * sizeof(double)));
+  EG_CUDA(cudaMalloc((void**)&c->d_walk, (size_t)EG_N_PCLASS * EG_NY * ns * 2 * sizeof(double)));
   EgSiteBuildParams bp{};
   bp.grid_n = m.grid_n; bp.n_sites = ns; bp.step = m.step;
   bp.n_settlements = (int)m.sx.size(); bp.sx = c->d_sx; bp.sy = c->d_sy; bp.pop = c->d_pop;
@@ -122,6 +124,7 @@ int build_device_map(eg_ctx* c) {
   bp.prefix = c->d_prefix; bp.coast_factor = c->d_coast; bp.site_opinion = c->d_site_opinion;
   bp.static_unsorted = c->d_static_unsorted; bp.order = c->d_order; bp.static_sorted = c->d_static_sorted;
   bp.prefix_sorted = c->d_prefix_sorted;
+  bp.walk = (double2*)c->d_walk;
   int launches = 0;
   EG_CUDA(eg_build_site_tables(bp, s, &launches));
   c->launches += (uint64_t)launches;
@@ -137,6 +140,7 @@ int build_device_map(eg_ctx* c) {
   c->dmap.order = c->d_order;
   c->dmap.static_score = c->d_static_sorted;
   c->dmap.prefix_score = c->d_prefix_sorted;
+  c->dmap.walk = c->d_walk;
   c->dmap.near_factor = c->d_near;
   c->dmap.r2_limit = c->d_r2_limit;
   c->dmap.r2_stride = c->htab.r2_stride;
@@ -199,6 +203,7 @@ EgEpisodeParams make_params(const eg_ctx* c, const eg_run_cfg* cfg, uint64_t see
   p.replay_best = cfg->replay_best;
   p.ln100 = std::log(50000000000.0 * 100.0 / 50000000000.0);
   p.next_episode = c->d_next_episode;
+  p.nf_entries = c->htab.r2_limit[2 * EG_N_RCLASS];
   return p;
 }
 

@@ -43,9 +43,12 @@ constexpr double kMaxAcceptableCost = 50000000000.0;         // config/constants
 constexpr double kMaxAcceptableEmissions = 1000000.0;        // config/constants.rs:112
 
 // ---- per-warp shared-memory slice --------------------------------------------------------------------------
-constexpr int kOffLw = 0;                                       // double[61]  this year's regular weights
-constexpr int kOffLdw = kOffLw + 8 * EG_N_ACTIONS;              // double[15]  this year's deficit weights
-constexpr int kOffScratch = kOffLdw + 8 * EG_N_DEFICIT_KEYS;    // double2[32] fold staging | double[61] + uint8[64] sorted row
+// two buffers of policy rows (year parity): [61 regular | 15 deficit | 21 count weights | pad]; the rows of year y+1 are
+// copied in asynchronously (cp.async) while year y runs, the rows of year y are this episode's private, editable copy
+constexpr int kRowDoubles = EG_N_ACTIONS + EG_N_DEFICIT_KEYS + EG_N_COUNT_KEYS + 1;  // 98
+constexpr int kRowBytes = 8 * kRowDoubles;
+constexpr int kOffRows = 0;
+constexpr int kOffScratch = kOffRows + 2 * kRowBytes;           // double2[32] fold staging | double[61] + uint8[64] sorted row
 constexpr int kScratchBytes = 8 * EG_N_ACTIONS + 64;            // 552 >= 512
 constexpr int kOffSortIdx = kOffScratch + 8 * EG_N_ACTIONS;     // uint8[64] (inside the scratch area)
 constexpr int kOffVars = kOffScratch + kScratchBytes;           // double[16]  rarely used episode scalars (kV*)
@@ -152,8 +155,8 @@ __device__ __noinline__ int smart_deficit_fallback_pick(uint32_t choice) {  // (
 
 // stagnation branch of sample_action (sampling.rs:190-220) for rows edited in this episode: stable descending
 // sort by rank counting and the powers, both spread over the lanes
-__device__ __noinline__ void sort_local(uint32_t sb, int lane, double power) {
-  const double* lw = (const double*)(smem + sb + kOffLw);
+__device__ __noinline__ void sort_local(uint32_t sb, uint32_t sb_rows, int lane, double power) {
+  const double* lw = (const double*)(smem + sb_rows);
   double* scaled = (double*)(smem + sb + kOffScratch);
   uint8_t* sort_idx = smem + sb + kOffSortIdx;
   for (int k = lane; k < EG_N_ACTIONS; k += 32) {
@@ -203,8 +206,9 @@ struct Warp {
   __device__ __forceinline__ uint16_t* GXY() const { return (uint16_t*)(smem + sb + kOffGxy); }
   __device__ __forceinline__ uint16_t* GAT() const { return (uint16_t*)(smem + sb + kOffGat); }
 
-  __device__ __forceinline__ double* LW() const { return (double*)(smem + sb + kOffLw); }
-  __device__ __forceinline__ double* LDW() const { return (double*)(smem + sb + kOffLdw); }
+  __device__ __forceinline__ double* LW(int y) const { return (double*)(smem + sb + kOffRows + (y & 1) * kRowBytes); }
+  __device__ __forceinline__ double* LDW(int y) const { return LW(y) + EG_N_ACTIONS; }
+  __device__ __forceinline__ double* LCW(int y) const { return LW(y) + EG_N_ACTIONS + EG_N_DEFICIT_KEYS; }
   __device__ __forceinline__ double2* SCR() const { return (double2*)(smem + sb + kOffScratch); }
   __device__ __forceinline__ uint16_t* OFFS() const { return (uint16_t*)(smem + sb + kOffOffs); }
   __device__ __forceinline__ uint16_t* YSITES() const { return (uint16_t*)(smem + sb + kOffYearSites); }
@@ -330,31 +334,42 @@ struct Warp {
     const int r2lim = __ldg(&p.map.r2_limit[rc]);  // cell offsets with d2 < r2lim are inside the penalty radius
     const size_t base = ((size_t)pc * EG_NY + y) * ns;
     const uint16_t* __restrict__ order = p.map.order + base;
-    const double* __restrict__ stat = p.map.static_score + base;
-    const double* __restrict__ pref = p.map.prefix_score + base;
+    const double2* __restrict__ walk = (const double2*)p.map.walk + base;
     // distance/radius by squared cell distance: block-shared copy in shared memory (narrow maps), else global
     // (the block-shared copy sits at the start of the dynamic shared memory)
     const double* __restrict__ nf = p.map.near_factor + rc * p.map.r2_stride;
-    const uint32_t nf_s = opaque((uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)(rc * p.map.r2_stride) * 8u);
+    const uint32_t nf_s = opaque((uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)__ldg(&p.map.r2_limit[EG_N_RCLASS + rc]) * 8u);
     const int nstride = p.map.near_stride;
     const double size_factor = __ldg(&T->size_factor);
     const NearT* nearest = NEAR();
     const uint16_t* gxy = GXY();
     double best_score = 0.0;
     int best_site = -1;
+    double2 sp_next = lane < ns ? __ldg(&walk[lane]) : make_double2(0.0, 0.0);   // (static score, prefix score)
+    int packed_next = lane < ns ? (int)__ldg(&order[lane]) : 0;                  // (i << 8) | j of the candidate site
     for (int k0 = 0; k0 < ns; k0 += 32) {
-      const int k = k0 + lane;
-      const double s_static = k < ns ? __ldg(&stat[k]) : 0.0;
+#ifdef EG_WALK_NOPIPE
+      if (k0 + lane < ns && k0 > 0) { sp_next = __ldg(&walk[k0 + lane]); packed_next = (int)__ldg(&order[k0 + lane]); }
+      else if (k0 > 0) sp_next = make_double2(0.0, 0.0);
+      const double s_static = sp_next.x, pre = sp_next.y;
+      const int packed = packed_next;
+#else
+      const double s_static = sp_next.x, pre = sp_next.y;
+      const int packed = packed_next;
+      {  // entries of the next step: in flight while this step is examined
+        const int kn = k0 + 32 + lane;
+        sp_next = make_double2(0.0, 0.0);
+        if (kn < ns) { sp_next = __ldg(&walk[kn]); packed_next = (int)__ldg(&order[kn]); }
+      }
+#endif
       const double s_first = shfl_f64(s_static, 0);
       // the list is sorted: nothing from here on can beat the best so far, and zero scores never win
       if (s_first < best_score || !(s_first > 0.0)) break;
       const bool live = s_static > 0.0 && !(s_static < best_score);
-      int site = 0, packed = 0;
+      const int site = (packed >> 8) * n + (packed & 0xFF);
       bool inr = false;
       int d2n = 0;
       if (live) {
-        packed = __ldg(&order[k]);  // (i << 8) | j of the candidate site
-        site = (packed >> 8) * n + (packed & 0xFF);
         d2n = nearest[(packed >> 8) * nstride + (packed & 0xFF)];
         inr = d2n < r2lim;
       }
@@ -371,9 +386,7 @@ struct Warp {
       // in range of at least one new plant: all factors are < 1 and rounding is monotone, so the product with the
       // nearest plant's factor alone bounds the true score from above
       bool cand = false;
-      double pre = 0.0;
       if (inr) {
-        pre = __ldg(&pref[k]);
         double bound = pre * (sizeof(NearT) == 1 ? lds_f64(nf_s + 8u * (uint32_t)d2n) : __ldg(&nf[d2n]));
         if (water) bound *= __ldg(&p.map.coast_factor[site]);
         bound *= size_factor;
@@ -464,12 +477,30 @@ struct Warp {
   }
 
   // ---- episode-local learning (the deficit handler edits this year's rows of its private weights) ----------
+  // asynchronous copy of the policy rows of year y (w[y] | dw[y] | cw[y]) into the buffer of that year's parity
+  __device__ __forceinline__ void prefetch_rows(int y) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem) + sb + kOffRows + (uint32_t)(y & 1) * kRowBytes;
+    for (int k = lane; k < EG_N_ACTIONS + EG_N_DEFICIT_KEYS + EG_N_COUNT_KEYS; k += 32) {
+      const double* src = k < EG_N_ACTIONS ? &p.policy->w[y][k]
+                          : (k < EG_N_ACTIONS + EG_N_DEFICIT_KEYS ? &p.policy->dw[y][k - EG_N_ACTIONS] : &p.policy->cw[y][k - EG_N_ACTIONS - EG_N_DEFICIT_KEYS]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * (uint32_t)k), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // the rows of year y are complete (requested a year earlier); request those of year y+1
   __device__ __forceinline__ void load_rows(int y) {
-    double* lw = LW();
+#ifdef EG_ROWS_SYNC
+    double* lw = LW(y);
     for (int k = lane; k < EG_N_ACTIONS; k += 32) lw[k] = __ldg(&p.policy->w[y][k]);
-    if (lane < EG_N_DEFICIT_KEYS) LDW()[lane] = __ldg(&p.policy->dw[y][lane]);
-    rows_dirty = false; dw_dirty = false; sorted_valid = false; total_valid = false;
+    if (lane < EG_N_DEFICIT_KEYS) LDW(y)[lane] = __ldg(&p.policy->dw[y][lane]);
+    if (lane < EG_N_COUNT_KEYS) LCW(y)[lane] = __ldg(&p.policy->cw[y][lane]);
     __syncwarp();
+#else
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    if (y + 1 < EG_NY) prefetch_rows(y + 1);
+#endif
+    rows_dirty = false; dw_dirty = false; sorted_valid = false; total_valid = false;
   }
 
   __device__ __forceinline__ void update_deficit_weights(int y, int action, double improvement) {  // deficit.rs:82-135
@@ -479,7 +510,7 @@ struct Warp {
     const double lr = p.policy->learning_rate;
     const double adj = improvement > 0.0 ? 1.0 + (lr * improvement * 1.5) : ddiv(1.0, 1.0 + (lr * fabs(improvement) * 1.5));
     const double boost = 1.0 + (lr * 0.1);
-    double* ldw = LDW();
+    double* ldw = LDW(y);
     if (lane < 14) {
       if (lane == key) ldw[lane] = fmin(fmax(ldw[lane] * adj, kMinWeight), kMaxWeight);
       else if (improvement < 0.0) ldw[lane] = fmin(ldw[lane] * boost, kMaxWeight);
@@ -494,7 +525,7 @@ struct Warp {
     const double combined = immediate * improvement + (1.0 - immediate) * rel;
     const double adj = combined > 0.0 ? 1.0 + (lr * combined) : ddiv(1.0, 1.0 + (lr * fabs(combined)));
     const double boost = 1.0 + (lr * 0.1);
-    double* lw = LW();
+    double* lw = LW(y);
     for (int k = lane; k < EG_N_ACTIONS; k += 32) {
       if (k == action) lw[k] = fmin(fmax(lw[k] * adj, kMinWeight), kMaxWeight);
       else if (combined < 0.0 && k < 45) lw[k] = fmin(lw[k] * boost, kMaxWeight);
@@ -514,7 +545,7 @@ struct Warp {
     }
     const bool explore = f64() < p.policy->exploration_rate;
     if (explore) return deficit_key_action((int)index(14));
-    const double* ldw = LDW();
+    const double* ldw = LDW(y);
     double total;
     if (dw_dirty) {
       total = 0.0;
@@ -538,11 +569,12 @@ struct Warp {
     const double random_val = f64();
     if (p.policy->has_count_weights) {
       const double total = __ldg(&p.policy->cw_total[y]);
+      const double* lcw = LCW(y);
       if (total <= 0.0) return 0;
       double rc = random_val * total;
       #pragma unroll 4
       for (int c = 0; c < EG_N_COUNT_KEYS; c++) {
-        rc -= __ldg(&p.policy->cw[y][c]);
+        rc -= lcw[c];
         if (rc <= 0.0) return min((uint32_t)c, max_possible);
       }
       return min(5u, max_possible);
@@ -564,7 +596,7 @@ struct Warp {
     const double cur_eps = iwi > 100 ? eps * ddiv(1.0, 1.0 + 0.01 * (double)iwi) : eps;
     const bool explore = f64() < cur_eps;
     if (explore) return (int)index(EG_N_ACTIONS);
-    const double* lw = LW();
+    const double* lw = LW(y);
     double total;
     if (rows_dirty) {
       if (!total_valid) {
@@ -584,7 +616,7 @@ struct Warp {
       const double* sc;
       const uint8_t* idx;
       if (rows_dirty) {
-        if (!sorted_valid) { sort_local(sb, lane, p.policy->stagnation_power); sorted_valid = true; }
+        if (!sorted_valid) { sort_local(sb, sb + kOffRows + (uint32_t)(y & 1) * kRowBytes, lane, p.policy->stagnation_power); sorted_valid = true; }
         double total_scaled = 0.0;
         const double* scl = (const double*)(smem + sb + kOffScratch);
         #pragma unroll 1
@@ -643,6 +675,9 @@ struct Warp {
     uint32_t n_def_total = 0, n_add_total = 0;
     double* vars = VARS();
     const bool learn = !REPLAY && !p.replay_best;
+#ifndef EG_ROWS_SYNC
+    if (!REPLAY) prefetch_rows(0);
+#endif
 
     for (int y = 0; y < EG_NY; y++) {
       year_start(y);
@@ -855,9 +890,11 @@ template <bool REPLAY, typename NearT>
 __global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) eg_episode_kernel(const __grid_constant__ EgEpisodeParams p, int slice_bytes, int table_bytes) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (sizeof(NearT) == 1) {  // block-shared copy of the distance/radius factors at the start of the shared memory
-    double* nf_s = (double*)smem;
-    const int cnt = EG_N_RCLASS * p.map.r2_stride;
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) nf_s[i] = __ldg(&p.map.near_factor[i]);
+    double* nf_s = (double*)smem;  // compact: class rc holds its r2_limit[rc] entries from offset r2_limit[6 + rc]
+    for (int rc = 0; rc < EG_N_RCLASS; rc++) {
+      const int cnt = __ldg(&p.map.r2_limit[rc]), off = __ldg(&p.map.r2_limit[EG_N_RCLASS + rc]);
+      for (int i = threadIdx.x; i < cnt; i += blockDim.x) nf_s[off + i] = __ldg(&p.map.near_factor[rc * p.map.r2_stride + i]);
+    }
     __syncthreads();
   }
   Warp<REPLAY, NearT> w(p, opaque((uint32_t)(table_bytes + warp * slice_bytes)), lane);
@@ -877,7 +914,7 @@ cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
   const bool wide = sizeof(NearT) == 2;
   const int near_bytes = p.map.grid_n * p.map.near_stride * (int)sizeof(NearT);
   const int slice = (kOffNear + near_bytes + 15) & ~15;
-  const int shared_tab = wide ? 0 : (EG_N_RCLASS * p.map.r2_stride * (int)sizeof(double) + 15) & ~15;
+  const int shared_tab = wide ? 0 : (p.nf_entries * (int)sizeof(double) + 15) & ~15;
   // as many warps per block as keep several blocks resident in the 227 KB of an SM
   int warps = EG_EPISODE_WARPS;
   while (warps > 1 && warps * slice + shared_tab > 100 * 1024) warps >>= 1;

@@ -11,6 +11,7 @@ struct EgEpisodeParams {
   eg_traj* traj;                 // nullable
   eg_sites* sites;               // nullable
   eg_yearly* yearly;             // nullable
+  int nf_entries;                // size of the compact distance/radius table copied to shared memory (narrow maps)
   uint32_t* next_episode;        // device counter the persistent warps claim episodes from (zeroed by the launcher)
   unsigned long long seed;
   unsigned long long first_episode;

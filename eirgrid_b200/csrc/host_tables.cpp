@@ -377,6 +377,10 @@ void eg_host_build_tables(const EgHostMap& m, EgHostTables* out) {
     stride = std::max(stride, d2);
   }
   out->r2_stride = stride;
+  for (int rc = 0, off = 0; rc <= EG_N_RCLASS; rc++) {
+    out->r2_limit[EG_N_RCLASS + rc] = off;
+    if (rc < EG_N_RCLASS) off += out->r2_limit[rc];
+  }
   out->near_factor.assign((size_t)EG_N_RCLASS * stride, 1.0);
   for (int rc = 0; rc < EG_N_RCLASS; rc++)
     for (int d2 = 0; d2 < out->r2_limit[rc]; d2++) {

@@ -19,7 +19,7 @@ struct EgHostTables {
   std::vector<double> plant_terms;   // [EG_OPC_SIZE][2]
   std::vector<uint32_t> pop;         // [26][S]
   std::vector<double> near_factor;   // [6][r2_stride], by squared cell distance
-  int r2_limit[EG_N_RCLASS] = {0};
+  int r2_limit[2 * EG_N_RCLASS + 1] = {0};  // limits, compact-table offsets, compact-table size
   int r2_stride = 0;
   int kmax = 0;
   std::vector<uint32_t> stamp;       // [cells per word][2*(kmax-1)+1][stamp_w]

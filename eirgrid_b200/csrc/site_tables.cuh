@@ -26,6 +26,7 @@ struct EgSiteBuildParams {
   uint16_t* order;         // [7][26][n_sites]
   double* static_sorted;   // [7][26][n_sites]
   double* prefix_sorted;   // [7][26][n_sites]
+  double2* walk;           // [7][26][n_sites] (static_sorted, prefix_sorted) interleaved: one 16-byte read per walk entry
 };
 
 // launches 3 kernels on `stream`; returns the number of launches in *launches

@@ -68,8 +68,10 @@ struct EgDeviceMap {      // device pointers + sizes, passed by value to the ker
   const uint16_t* order;          // [7][26][n_sites] candidate site as (i << 8) | j
   const double* static_score;     // [7][26][n_sites] score of the site when no simulation-built plant is in range
   const double* prefix_score;     // [7][26][n_sites] score after settlements + existing plants (before new plants)
+  const double* walk;             // [7][26][n_sites][2] (static_score, prefix_score) interleaved, what the placement walk reads
   const double* near_factor;      // [6][r2_stride] distance/radius by squared cell distance d2 (valid for d2 < r2_limit[rc])
-  const int* r2_limit;            // [6] first squared cell distance that is NOT inside the penalty radius
+  const int* r2_limit;            // [6] first squared cell distance that is NOT inside the penalty radius, followed by
+                                  // [6] start of the class in the compact table (prefix sums of the limits) and [1] its size
   int r2_stride;
   int n_sites;
   int grid_n;
