@@ -244,16 +244,29 @@ def main():
     peak, peak_src = load_peaks()
     info = tr.ctx.map_info()
     ns = info["grid_n"] ** 2
-    static_bytes = 7 * 26 * ns * (2 + 8 + 8) + ns * 16 + 26 * 15 * 3 * 26 * 8 + 40000 + POLICY_BYTES
+    # algorithmic HBM bytes of one rollout launch: every episode writes its result and action record
+    # once; the static tables (walk lists 16 B + order 2 B per (class, year, site), per-site factors, plant terms, small
+    # tables, stamp pattern, policy snapshot) are read once and then live in L2
+    static_bytes = 7 * 26 * ns * (16 + 2) + ns * 16 + 26 * 15 * 3 * 26 * 16 + 40000 + 3200 + POLICY_BYTES
     algo_bytes = args.episodes * (RESULT_BYTES + TRAJ_BYTES) + static_bytes
     achieved = algo_bytes / (rollout_ms / 1e3) / 1e9
-    traffic = None
+    traffic, issue = None, None
     tp = os.path.join(ROOT, "profiles", "rollout_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            prof = json.load(open(tp))
+            if prof.get("episodes_per_launch") == args.episodes:
+                traffic = prof.get("dram_bytes_per_launch")
+            # what binds instead of HBM: warp-instruction issue. Instructions per episode are a property of the code and
+            # the workload (counted by ncu, profiles/), the rate is measured live here.
+            sms, sched = torch.cuda.get_device_properties(local).multi_processor_count, 4
+            ipe = prof["warp_instructions_per_episode"]
+            peak_issue = sms * sched * (clock_summary.get("sm_mhz") or 1965.0) * 1e6
+            issue = {"warp_instructions_per_episode": ipe, "achieved_ginst_s": ipe * args.episodes / (rollout_ms / 1e3) / 1e9,
+                     "peak_ginst_s": peak_issue / 1e9, "frac": ipe * args.episodes / (rollout_ms / 1e3) / peak_issue,
+                     "source": "profiles/rollout_traffic.json (ncu smsp__inst_executed.sum) x live kernel time"}
         except Exception:
-            traffic = None
+            traffic, issue = None, None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -264,15 +277,17 @@ def main():
                    "timing": "CUDA events on the launching stream per step, max over ranks",
                    "rollout_kernel_ms": rollout_ms},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": POLICY_BYTES, "d2h_bytes_per_step": tr.d2h_bytes_per_step,
-                "what": "BatchTrainer.step(): weights H2D, rollout+stats kernels, stats + batch winner D2H (pinned), host update",
+                "what": "BatchTrainer.step(): weights H2D from the host, rollout + statistics + winner-record kernels, statistics and "
+                        "winner record D2H (pinned), host-side weight update applied",
                 "with_all_results_to_host": {"value": args.episodes * world * K / full_s, "unit": UNIT,
                                              "d2h_bytes_per_step": args.episodes * (RESULT_BYTES + TRAJ_BYTES)}},
         "gpu_launches": int(launches),
         "clocks": clock_summary,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "eg_episode_kernel<false> (rollout)",
-                     "algorithmic_bytes_per_launch": algo_bytes,
-                     "note": "the path is instruction/latency-bound, not HBM-bound: see DESIGN.md §roofline and profiles/"},
+                     "algorithmic_bytes_per_launch": algo_bytes, "issue": issue,
+                     "note": "the path moves ~1.2 KB per episode and is bound by warp-instruction issue/latency, not HBM: "
+                             "see roofline.issue, DESIGN.md §4.1 and profiles/"},
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

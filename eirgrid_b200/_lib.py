@@ -19,7 +19,7 @@ EXPORTS = [
     "eg_weights_clone", "eg_weights_load_json", "eg_weights_save_json", "eg_weights_merge", "eg_weights_get_table",
     "eg_weights_set_table", "eg_weights_get_best", "eg_deficit_key_action", "eg_rollout_batch", "eg_weights_upload",
     "eg_rollout_batch_device", "eg_replay_batch", "eg_replay_batch_device", "eg_update", "eg_update_stats_device",
-    "eg_update_apply_stats", "eg_location_analysis",
+    "eg_update_apply_stats", "eg_location_analysis", "eg_update_stats_clear_device", "eg_update_pack_best_device",
 ]
 
 
@@ -73,6 +73,8 @@ def lib():
     L.eg_replay_batch_device.argtypes = [vp, C.POINTER(_abi.RunCfg), vp, u32, vp, vp, vp]
     L.eg_update.argtypes = [vp, vp, vp, u32, u32, u64, C.POINTER(_abi.UpdateStats)]
     L.eg_update_stats_device.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp]
+    L.eg_update_stats_clear_device.argtypes = [vp, vp]
+    L.eg_update_pack_best_device.argtypes = [vp, vp, vp, u32, vp, vp, u64, vp]
     L.eg_update_apply_stats.argtypes = [vp, vp, u64, vp, vp, i64, C.POINTER(_abi.UpdateStats)]
     L.eg_location_analysis.argtypes = [vp, C.c_int, C.c_int32, C.c_double, vp, u32, u32]
     _lib = L
@@ -273,6 +275,13 @@ class Context:
     def update_stats_device(self, weights, n, d_results, d_traj, d_stats, d_best_score, d_best_index):
         check(self.L.eg_update_stats_device(self.h, weights.h, _dev_ptr(d_results), _dev_ptr(d_traj), n,
                                             _dev_ptr(d_stats), _dev_ptr(d_best_score), _dev_ptr(d_best_index)))
+
+    def update_stats_clear_device(self, d_stats):
+        check(self.L.eg_update_stats_clear_device(self.h, _dev_ptr(d_stats)))
+
+    def update_pack_best_device(self, n, d_results, d_traj, d_best_score, d_best_index, first_global_episode, d_record):
+        check(self.L.eg_update_pack_best_device(self.h, _dev_ptr(d_results), _dev_ptr(d_traj), n, _dev_ptr(d_best_score),
+                                                _dev_ptr(d_best_index), first_global_episode, _dev_ptr(d_record)))
 
     def location_analysis(self, use_loaded_map, half_steps=25, step=2000.0, first_point=0, n_points=None):
         side = 2 * half_steps + 1

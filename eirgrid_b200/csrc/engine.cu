@@ -406,6 +406,23 @@ int eg_update_stats_device(eg_ctx* c, const eg_weights* w, const eg_result* d_re
   return EG_OK;
 }
 
+int eg_update_stats_clear_device(eg_ctx* c, int64_t* d_stats) {
+  if (!c || !d_stats) return eg_fail(EG_ERR_INVALID, "eg_update_stats_clear_device: NULL argument");
+  EG_CUDA(cudaSetDevice(c->device));
+  EG_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)EG_STATS_WORDS * sizeof(int64_t), c->stream));
+  return EG_OK;
+}
+
+int eg_update_pack_best_device(eg_ctx* c, const eg_result* d_results, const eg_traj* d_trajs, uint32_t n, const double* d_best_score,
+                               const unsigned long long* d_best_index, uint64_t first_global_episode, void* d_record) {
+  if (!c || !d_results || !d_trajs || !d_best_score || !d_best_index || !d_record)
+    return eg_fail(EG_ERR_INVALID, "eg_update_pack_best_device: NULL argument");
+  EG_CUDA(cudaSetDevice(c->device));
+  EG_CUDA(eg_launch_pack_best(d_results, d_trajs, n, d_best_score, d_best_index, first_global_episode, d_record, c->stream));
+  c->launches++;
+  return EG_OK;
+}
+
 int eg_location_analysis(eg_ctx* c, int use_loaded_map, int32_t half_steps, double step, double* scores_out,
                          uint32_t first_point, uint32_t n_points) {
   if (!c || !scores_out) return eg_fail(EG_ERR_INVALID, "eg_location_analysis: NULL argument");

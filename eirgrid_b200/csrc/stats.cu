@@ -108,7 +108,27 @@ __global__ void __launch_bounds__(256) eg_stats_argbest_kernel(const EgStatsPara
   if (score == *p.best_score) atomicMin(p.best_index, (unsigned long long)ep);
 }
 
+__global__ void __launch_bounds__(320) eg_stats_pack_best_kernel(const eg_result* results, const eg_traj* trajs, uint32_t n, const double* best_score,
+                                                                 const unsigned long long* best_index, unsigned long long first_global, uint32_t* record) {
+  // 16 + 64 + 1092 bytes = 293 words, one per thread
+  const unsigned long long raw = *best_index;
+  const uint32_t idx = raw < n ? (uint32_t)raw : (n ? n - 1 : 0);
+  const int w = threadIdx.x;
+  constexpr int kRes = (int)sizeof(eg_result) / 4, kTraj = (int)sizeof(eg_traj) / 4;
+  if (w < 2) record[w] = ((const uint32_t*)best_score)[w];
+  else if (w < 4) { const unsigned long long g = first_global + idx; record[w] = (uint32_t)(g >> (32 * (w - 2))); }
+  else if (w < 4 + kRes) record[w] = ((const uint32_t*)(results + idx))[w - 4];
+  else if (w < 4 + kRes + kTraj) record[w] = ((const uint32_t*)(trajs + idx))[w - 4 - kRes];
+}
+
 }  // namespace
+
+cudaError_t eg_launch_pack_best(const eg_result* results, const eg_traj* trajs, uint32_t n, const double* best_score,
+                                const unsigned long long* best_index, unsigned long long first_global, void* record, cudaStream_t stream) {
+  static_assert(sizeof(eg_result) % 4 == 0 && sizeof(eg_traj) % 4 == 0, "record is copied in 32-bit words");
+  eg_stats_pack_best_kernel<<<1, 320, 0, stream>>>(results, trajs, n, best_score, best_index, first_global, (uint32_t*)record);
+  return cudaGetLastError();
+}
 
 cudaError_t eg_launch_stats(const EgStatsParams& p, cudaStream_t stream) {
   eg_stats_reset_kernel<<<1, 1, 0, stream>>>(p.best_score, p.best_index);

@@ -103,21 +103,13 @@ class BatchTrainer:
         self.ctx.rollout_device(self.n, self.seed, first, self.d_results, self.d_traj, self.d_sites, None, self.cfg)
 
     def launch_stats(self):
-        with _torch().cuda.stream(self.stream):
-            self.d_stats.zero_()
+        self.ctx.update_stats_clear_device(self.d_stats)
         self.ctx.update_stats_device(self.weights, self.n, self.d_results, self.d_traj, self.d_stats, self.d_best_score,
                                      self.d_best_index)
 
     def _pack_best(self):
-        torch = _torch()
-        rb, tb = _abi.RESULT_DTYPE.itemsize, _abi.TRAJ_DTYPE.itemsize
-        with torch.cuda.stream(self.stream):
-            idx = self.d_best_index.clamp(0, self.n - 1)
-            gidx = idx + (self.next_episode + self.rank * self.n)
-            self.d_rec[0:8] = self.d_best_score.view(torch.uint8)
-            self.d_rec[8:16] = gidx.view(torch.uint8)
-            self.d_rec[16:16 + rb] = self.d_results.view(self.n, rb).index_select(0, idx).view(-1)
-            self.d_rec[16 + rb:] = self.d_traj.view(self.n, tb).index_select(0, idx).view(-1)
+        self.ctx.update_pack_best_device(self.n, self.d_results, self.d_traj, self.d_best_score, self.d_best_index,
+                                         self.next_episode + self.rank * self.n, self.d_rec)
 
     def reduce_stats(self):
         """Sum the statistics table over ranks (the path's only exchange step)."""

@@ -265,6 +265,15 @@ int eg_update_stats_device(eg_ctx* ctx, const eg_weights* w, const eg_result* d_
                            int64_t* d_stats /* EG_STATS_WORDS, accumulated (not cleared) */,
                            double* d_best_score /* [1] max score of the shard */,
                            unsigned long long* d_best_index /* [1] lowest index with that score */);
+/* Zero the statistics table on the ctx stream (start of a batch). */
+int eg_update_stats_clear_device(eg_ctx* ctx, int64_t* d_stats);
+/* This rank's candidate for the batch winner as one flat record on the device, ready for the all-gather:
+ * [best score f64 | global episode id i64 | eg_result | eg_traj] (EG_BEST_RECORD_BYTES). d_best_score / d_best_index are
+ * the outputs of eg_update_stats_device; global id = first_global_episode + index. */
+#define EG_BEST_RECORD_BYTES (16 + sizeof(eg_result) + sizeof(eg_traj))
+int eg_update_pack_best_device(eg_ctx* ctx, const eg_result* d_results, const eg_traj* d_trajs, uint32_t n,
+                               const double* d_best_score, const unsigned long long* d_best_index,
+                               uint64_t first_global_episode, void* d_record);
 int eg_update_apply_stats(eg_weights* w, const int64_t* stats, uint64_t n_total,
                           const eg_result* batch_best_result, const eg_traj* batch_best_traj,
                           int64_t batch_best_index, eg_update_stats* stats_out);
