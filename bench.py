@@ -61,7 +61,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.02)
 
     def __enter__(self):
         self.t.start()
@@ -142,13 +142,16 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--episodes", type=int, default=65536, help="episodes in flight per GPU per step")
     ap.add_argument("--impl", default="eirgrid_b200")
     ap.add_argument("--seed", type=int, default=20250101)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", choices=["ireland", "scaled10"], default="ireland",
+                    help="ireland: shipped map, 65,536 episodes in flight per GPU (BASELINE configs[2] batch shape, the headline); "
+                         "scaled10: synthetic 10x scaled grid of configs[3] (eirgrid_b200/synthetic.py)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -163,7 +166,11 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    tr = T.BatchTrainer(args.episodes, seed=args.seed, device=local, asset_dir=ASSETS, distributed=world > 1)
+    map_arrays = None
+    if args.workload == "scaled10":
+        from eirgrid_b200 import synthetic
+        map_arrays = synthetic.scaled_map(ASSETS, factor=10)
+    tr = T.BatchTrainer(args.episodes, seed=args.seed, device=local, asset_dir=ASSETS, map_arrays=map_arrays, distributed=world > 1)
     n_total = args.episodes * world
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=tr.device)  # > 126 MB L2
 
@@ -255,6 +262,8 @@ def main():
     if os.path.exists(tp):
         try:
             prof = json.load(open(tp))
+            if args.workload != "ireland":
+                raise KeyError("profile is for the shipped map")
             if prof.get("episodes_per_launch") == args.episodes:
                 traffic = prof.get("dram_bytes_per_launch")
             # what binds instead of HBM: warp-instruction issue. Instructions per episode are a property of the code and
@@ -272,7 +281,11 @@ def main():
         "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "policy rollout + scoring + batch weight-update statistics, %d episodes in flight per GPU "
-                               "(BASELINE configs[2] batch shape), Irish map: 130 settlements, 59 existing plants, 2601 candidate sites" % args.episodes,
+                               "(BASELINE configs[2] batch shape), %s" % (args.episodes, "Irish map: 130 settlements, 59 existing plants, 2601 candidate sites"
+                                                                          if args.workload == "ireland" else
+                                                                          "synthetic 10x scaled grid (configs[3]): %d settlements, %d existing plants, %d candidate sites"
+                                                                          % (info["n_settlements"], info["n_existing"], ns)),
+                   "map": args.workload,
                    "episodes_per_gpu": args.episodes, "l2": "256 MiB buffer written between timed steps (L2 flush)",
                    "timing": "CUDA events on the launching stream per step, max over ranks",
                    "rollout_kernel_ms": rollout_ms},
@@ -289,7 +302,7 @@ def main():
                      "note": "the path moves ~1.2 KB per episode and is bound by warp-instruction issue/latency, not HBM: "
                              "see roofline.issue, DESIGN.md §4.1 and profiles/"},
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "ireland":
         threads = os.cpu_count() or 1
         rate, n_cpu, dt = cpu_reference_rate(args.cpu_seconds, threads, literal=True)
         rate_fast, n_fast, dt_fast = cpu_reference_rate(3.0, threads, mode_fast=True)
