@@ -501,6 +501,12 @@ struct Warp {
     if (y + 1 < EG_NY) prefetch_rows(y + 1);
 #endif
     rows_dirty = false; dw_dirty = false; sorted_valid = false; total_valid = false;
+    if (p.policy->iwi > 500) {  // the snapshot's sorted, scaled row of this year (host libm) for the stagnation sampler
+      double* scl = (double*)(smem + sb + kOffScratch);
+      for (int k = lane; k < EG_N_ACTIONS; k += 32) scl[k] = __ldg(&p.policy->scaled_sorted[y][k]);
+      ((uint16_t*)(smem + sb + kOffSortIdx))[lane] = __ldg((const uint16_t*)p.policy->sorted_idx[y] + lane);
+      __syncwarp();
+    }
   }
 
   __device__ __forceinline__ void update_deficit_weights(int y, int action, double improvement) {  // deficit.rs:82-135
@@ -613,33 +619,21 @@ struct Warp {
     }
     if (total <= 0.0) return kGasPeaker100;
     if (iwi > 500) {
-      const double* sc;
-      const uint8_t* idx;
-      if (rows_dirty) {
-        if (!sorted_valid) { sort_local(sb, sb + kOffRows + (uint32_t)(y & 1) * kRowBytes, lane, p.policy->stagnation_power); sorted_valid = true; }
-        double total_scaled = 0.0;
-        const double* scl = (const double*)(smem + sb + kOffScratch);
-        #pragma unroll 1
-        for (int k = 0; k < EG_N_ACTIONS; k++) total_scaled += scl[k];
-        double rv = f64() * total_scaled;
-        #pragma unroll 1
-        for (int k = 0; k < EG_N_ACTIONS; k++) {
-          rv -= scl[k];
-          if (rv <= 0.0) return (smem + sb + kOffSortIdx)[k];
-        }
-        return (smem + sb + kOffSortIdx)[0];
-      }
-      sc = p.policy->scaled_sorted[y]; idx = p.policy->sorted_idx[y];  // host libm, per snapshot
+      // stagnation branch (sampling.rs:190-220): weights^power in stable descending order. The sorted row lives in the
+      // scratch area: copied from the host-built snapshot row at the start of the year (load_rows), rebuilt on the
+      // device after this episode edited the year's weights (sort_local).
+      if (rows_dirty && !sorted_valid) { sort_local(sb, sb + kOffRows + (uint32_t)(y & 1) * kRowBytes, lane, p.policy->stagnation_power); sorted_valid = true; }
+      const double* scl = (const double*)(smem + sb + kOffScratch);
       double total_scaled = 0.0;
-      #pragma unroll 1
-      for (int k = 0; k < EG_N_ACTIONS; k++) total_scaled += __ldg(&sc[k]);
+      #pragma unroll 4
+      for (int k = 0; k < EG_N_ACTIONS; k++) total_scaled += scl[k];
       double rv = f64() * total_scaled;
-      #pragma unroll 1
+      #pragma unroll 4
       for (int k = 0; k < EG_N_ACTIONS; k++) {
-        rv -= __ldg(&sc[k]);
-        if (rv <= 0.0) return idx[k];
+        rv -= scl[k];
+        if (rv <= 0.0) return (smem + sb + kOffSortIdx)[k];
       }
-      return idx[0];
+      return (smem + sb + kOffSortIdx)[0];
     }
     double rv = f64() * total;
     #pragma unroll 4
