@@ -20,6 +20,7 @@ EXPORTS = [
     "eg_weights_set_table", "eg_weights_get_best", "eg_deficit_key_action", "eg_rollout_batch", "eg_weights_upload",
     "eg_rollout_batch_device", "eg_replay_batch", "eg_replay_batch_device", "eg_update", "eg_update_stats_device",
     "eg_update_apply_stats", "eg_location_analysis", "eg_update_stats_clear_device", "eg_update_pack_best_device",
+    "eg_train_batch_begin", "eg_train_batch_end", "eg_train_batch_results", "eg_update_combine_apply",
 ]
 
 
@@ -75,6 +76,10 @@ def lib():
     L.eg_update_stats_device.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp]
     L.eg_update_stats_clear_device.argtypes = [vp, vp]
     L.eg_update_pack_best_device.argtypes = [vp, vp, vp, u32, vp, vp, u64, vp]
+    L.eg_train_batch_begin.argtypes = [vp, vp, C.POINTER(_abi.RunCfg), u64, u64, u32]
+    L.eg_train_batch_end.argtypes = [vp, vp, vp]
+    L.eg_train_batch_results.argtypes = [vp, vp, vp]
+    L.eg_update_combine_apply.argtypes = [vp, vp, vp, u32, u64, u64, C.POINTER(_abi.UpdateStats)]
     L.eg_update_apply_stats.argtypes = [vp, vp, u64, vp, vp, i64, C.POINTER(_abi.UpdateStats)]
     L.eg_location_analysis.argtypes = [vp, C.c_int, C.c_int32, C.c_double, vp, u32, u32]
     _lib = L

@@ -55,6 +55,15 @@ struct eg_ctx {
   uint32_t* d_pop = nullptr;
   EgPolicyDevice* d_policy = nullptr;
   uint32_t* d_next_episode = nullptr;  // work counter of the persistent episode kernels
+  // eg_train_batch_*: statistics table, shard best, winner record (device) and their pinned host mirrors
+  int64_t* d_stats = nullptr;
+  double* d_best_score = nullptr;
+  unsigned long long* d_best_index = nullptr;
+  unsigned char* d_record = nullptr;
+  int64_t* h_stats = nullptr;
+  unsigned char* h_record = nullptr;
+  uint32_t train_n = 0;
+  bool train_pending = false;
   EgDeviceMap dmap{};
   // scratch for the host-buffer entry points
   size_t cap = 0;
@@ -241,7 +250,9 @@ void eg_destroy(eg_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   free_map(c);
-  void* ptrs[] = {c->d_policy, c->d_next_episode, c->s_out, c->s_traj, c->s_traj_in, c->s_sites, c->s_yearly};
+  if (c->h_stats) cudaFreeHost(c->h_stats);
+  if (c->h_record) cudaFreeHost(c->h_record);
+  void* ptrs[] = {c->d_policy, c->d_next_episode, c->d_stats, c->d_best_score, c->d_best_index, c->d_record, c->s_out, c->s_traj, c->s_traj_in, c->s_sites, c->s_yearly};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -420,6 +431,54 @@ int eg_update_pack_best_device(eg_ctx* c, const eg_result* d_results, const eg_t
   EG_CUDA(cudaSetDevice(c->device));
   EG_CUDA(eg_launch_pack_best(d_results, d_trajs, n, d_best_score, d_best_index, first_global_episode, d_record, c->stream));
   c->launches++;
+  return EG_OK;
+}
+
+int eg_train_batch_begin(eg_ctx* c, const eg_weights* w, const eg_run_cfg* cfg, uint64_t seed, uint64_t first_episode, uint32_t n) {
+  int rc = check_cfg(c, cfg);
+  if (rc) return rc;
+  if (!w) return eg_fail(EG_ERR_INVALID, "eg_train_batch_begin: weights are NULL");
+  if (c->train_pending) return eg_fail(EG_ERR_STATE, "eg_train_batch_begin: a batch is already in flight on this context");
+  EG_CUDA(cudaSetDevice(c->device));
+  if (!c->d_stats) {
+    EG_CUDA(cudaMalloc((void**)&c->d_stats, EG_STATS_WORDS * sizeof(int64_t)));
+    EG_CUDA(cudaMalloc((void**)&c->d_best_score, sizeof(double)));
+    EG_CUDA(cudaMalloc((void**)&c->d_best_index, sizeof(unsigned long long)));
+    EG_CUDA(cudaMalloc((void**)&c->d_record, EG_BEST_RECORD_BYTES));
+    EG_CUDA(cudaMallocHost((void**)&c->h_stats, EG_STATS_WORDS * sizeof(int64_t)));
+    EG_CUDA(cudaMallocHost((void**)&c->h_record, EG_BEST_RECORD_BYTES));
+  }
+  if ((rc = eg_weights_upload(c, w))) return rc;
+  if ((rc = ensure_scratch(c, n, false, false, false))) return rc;
+  if ((rc = eg_rollout_batch_device(c, cfg, seed, first_episode, n, c->s_out, c->s_traj, nullptr, nullptr))) return rc;
+  if ((rc = eg_update_stats_clear_device(c, c->d_stats))) return rc;
+  if ((rc = eg_update_stats_device(c, w, c->s_out, c->s_traj, n, c->d_stats, c->d_best_score, c->d_best_index))) return rc;
+  if ((rc = eg_update_pack_best_device(c, c->s_out, c->s_traj, n, c->d_best_score, c->d_best_index, first_episode, c->d_record))) return rc;
+  EG_CUDA(cudaMemcpyAsync(c->h_stats, c->d_stats, EG_STATS_WORDS * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  EG_CUDA(cudaMemcpyAsync(c->h_record, c->d_record, EG_BEST_RECORD_BYTES, cudaMemcpyDeviceToHost, c->stream));
+  c->train_n = n;
+  c->train_pending = true;
+  return EG_OK;
+}
+
+int eg_train_batch_end(eg_ctx* c, int64_t* stats_out, void* record_out) {
+  if (!c || !stats_out || !record_out) return eg_fail(EG_ERR_INVALID, "eg_train_batch_end: NULL argument");
+  if (!c->train_pending) return eg_fail(EG_ERR_STATE, "eg_train_batch_end: no batch in flight");
+  EG_CUDA(cudaSetDevice(c->device));
+  c->train_pending = false;
+  EG_CUDA(cudaStreamSynchronize(c->stream));
+  std::memcpy(stats_out, c->h_stats, EG_STATS_WORDS * sizeof(int64_t));
+  std::memcpy(record_out, c->h_record, EG_BEST_RECORD_BYTES);
+  return EG_OK;
+}
+
+int eg_train_batch_results(eg_ctx* c, eg_result* out, eg_traj* traj_out) {
+  if (!c || !out) return eg_fail(EG_ERR_INVALID, "eg_train_batch_results: NULL argument");
+  if (c->train_pending || !c->train_n) return eg_fail(EG_ERR_STATE, "eg_train_batch_results: no finished batch");
+  EG_CUDA(cudaSetDevice(c->device));
+  EG_CUDA(cudaMemcpyAsync(out, c->s_out, (size_t)c->train_n * sizeof(eg_result), cudaMemcpyDeviceToHost, c->stream));
+  if (traj_out) EG_CUDA(cudaMemcpyAsync(traj_out, c->s_traj, (size_t)c->train_n * sizeof(eg_traj), cudaMemcpyDeviceToHost, c->stream));
+  EG_CUDA(cudaStreamSynchronize(c->stream));
   return EG_OK;
 }
 

@@ -697,4 +697,27 @@ int eg_update_apply_stats(eg_weights* w, const int64_t* stats, uint64_t n_total,
   return EG_OK;
 }
 
+int eg_update_combine_apply(eg_weights* w, const int64_t* stats_sum, const void* records, uint32_t n_records, uint64_t n_total,
+                            uint64_t first_episode, eg_update_stats* stats_out) {
+  if (!w || !stats_sum || (!records && n_records)) return eg_fail(EG_ERR_INVALID, "eg_update_combine_apply: NULL argument");
+  const unsigned char* rec = (const unsigned char*)records;
+  const unsigned char* win = nullptr;
+  double win_score = 0.0;
+  int64_t win_id = 0;
+  for (uint32_t r = 0; r < n_records; r++) {
+    const unsigned char* p = rec + (size_t)r * EG_BEST_RECORD_BYTES;
+    double score;
+    int64_t id;
+    std::memcpy(&score, p, 8);
+    std::memcpy(&id, p + 8, 8);
+    if (!win || score > win_score || (score == win_score && id < win_id)) { win = p; win_score = score; win_id = id; }
+  }
+  if (!win) return eg_update_apply_stats(w, stats_sum, n_total, nullptr, nullptr, -1, stats_out);
+  eg_result res;
+  eg_traj traj;
+  std::memcpy(&res, win + 16, sizeof(res));
+  std::memcpy(&traj, win + 16 + sizeof(res), sizeof(traj));
+  return eg_update_apply_stats(w, stats_sum, n_total, &res, &traj, win_id - (int64_t)first_episode, stats_out);
+}
+
 }  // extern "C"

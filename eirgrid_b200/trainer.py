@@ -37,17 +37,15 @@ def pack_record(score, global_index, result, traj):
 
 
 def combine_and_apply(weights, stats_sum, all_records, n_total, first_episode):
-    """Host side of the exchange step, identical on every rank: pick the batch winner among the per-rank
-    candidates (highest score, lowest episode id) and apply the summed statistics to the weights.
+    """Host side of the exchange step, identical on every rank (eg_update_combine_apply): pick the batch winner among
+    the per-rank candidates (highest score, lowest episode id) and apply the summed statistics to the weights.
     stats_sum: int64[STATS_WORDS] already summed over ranks; all_records: uint8[world, REC_BYTES]."""
-    rec = np.ascontiguousarray(all_records).reshape(-1, REC_BYTES)
-    scores = rec[:, 0:8].copy().view(np.float64).ravel()
-    gidx = rec[:, 8:16].copy().view(np.int64).ravel()
-    win = int(np.lexsort((gidx, -scores))[0])
-    rb = _abi.RESULT_DTYPE.itemsize
-    best_result = rec[win, 16:16 + rb].copy().view(_abi.RESULT_DTYPE)
-    best_traj = rec[win, 16 + rb:].copy().view(_abi.TRAJ_DTYPE)
-    return weights.apply_stats(np.asarray(stats_sum), n_total, best_result, best_traj, int(gidx[win] - first_episode))
+    rec = np.ascontiguousarray(all_records, dtype=np.uint8).reshape(-1, REC_BYTES)
+    stats = np.ascontiguousarray(stats_sum, dtype=np.int64)
+    st = _abi.UpdateStats()
+    _lib.check(_lib.lib().eg_update_combine_apply(weights.h, _abi.ptr(stats), _abi.ptr(rec), rec.shape[0], int(n_total),
+                                                  int(first_episode), C.byref(st)))
+    return st
 
 
 class BatchTrainer:

@@ -278,6 +278,20 @@ int eg_update_apply_stats(eg_weights* w, const int64_t* stats, uint64_t n_total,
                           const eg_result* batch_best_result, const eg_traj* batch_best_traj,
                           int64_t batch_best_index, eg_update_stats* stats_out);
 
+/* One training batch on one GPU, everything on the ctx stream (replaces the par_iter closure for a shard of the batch):
+ * weights snapshot H2D, rollout of episodes first_episode..+n, update statistics, the shard's winner record, both
+ * copied to pinned host memory. _begin returns once the work is queued (several contexts/GPUs can run concurrently from
+ * one host thread); _end waits and copies out the EG_STATS_WORDS int64 statistics (this shard only) and the
+ * EG_BEST_RECORD_BYTES winner record. Episode results stay on the device: eg_train_batch_results copies them out. */
+int eg_train_batch_begin(eg_ctx* ctx, const eg_weights* w, const eg_run_cfg* cfg, uint64_t seed, uint64_t first_episode, uint32_t n);
+int eg_train_batch_end(eg_ctx* ctx, int64_t* stats_out, void* record_out);
+int eg_train_batch_results(eg_ctx* ctx, eg_result* out, eg_traj* traj_out /* nullable */);
+/* Host side of the exchange step, identical on every rank/GPU: `stats_sum` = element-wise sum of the shards' statistics,
+ * `records` = n_records winner records back to back; the winner is the highest score, lowest global episode id among
+ * equals; then eg_update_apply_stats. first_episode = global id of the batch's first episode. */
+int eg_update_combine_apply(eg_weights* w, const int64_t* stats_sum, const void* records, uint32_t n_records,
+                            uint64_t n_total, uint64_t first_episode, eg_update_stats* stats_out);
+
 /* ---- location suitability analysis (BASELINE config 5): replaces Map::analyze_locations →
  * LocationAnalysis::analyze_map (map_handler.rs:61-142) and calculate_generator_suitability
  * (map_handler.rs:1319-1396) / the unused MSL kernel computeSuitability (metal:239-258).
