@@ -305,7 +305,10 @@ int main(int argc, char** argv) {
   const double t_start = now_s();
   double t_progress = t_start;
   eg_update_stats st{};
+  double t_train = 0.0;        // wall time of the training batches (device statistics path)
+  uint64_t n_train = 0;
   while (completed < a.iterations) {
+    const double t_batch = now_s();
     const bool is_full_run = a.force_full_simulation || !cache_loaded || completed + final_full >= a.iterations;
     bool has_best = false;
     best_score_of(weights, &has_best);
@@ -329,6 +332,8 @@ int main(int argc, char** argv) {
       }
       done_now = (uint64_t)per_gpu * G;
       check(eg_update_combine_apply(weights, stats.data(), records.data(), (uint32_t)G, done_now, completed, &st), "eg_update_combine_apply");
+      t_train += now_s() - t_batch;
+      n_train += done_now;
     } else {
       // replay batches and the sequential mode: every episode's record comes to the host and the reference's per-episode
       // update is applied in episode order (it rebuilds the doubled records of replay iterations, quirk Q10)
@@ -359,9 +364,11 @@ int main(int argc, char** argv) {
   uint64_t launches = 0;
   for (size_t g = 0; g < G; g++) launches += eg_kernel_launches(ctx[g]);
   std::printf("{\"run_dir\": \"%s\", \"iterations\": %llu, \"start_iteration\": %llu, \"elapsed_s\": %.3f, \"episodes_per_s\": %.1f, "
+              "\"training_batches\": {\"episodes\": %llu, \"episodes_per_s\": %.1f}, "
               "\"best_score\": %s, \"iterations_without_improvement\": %u, \"n_gpus\": %zu, \"kernel_launches\": %llu}\n",
               run_dir.c_str(), (unsigned long long)completed, (unsigned long long)start_iteration, elapsed,
-              (double)(completed - start_iteration) / std::max(elapsed, 1e-9), has_best ? std::to_string(best).c_str() : "null",
+              (double)(completed - start_iteration) / std::max(elapsed, 1e-9), (unsigned long long)n_train, (double)n_train / std::max(t_train, 1e-9),
+              has_best ? std::to_string(best).c_str() : "null",
               st.iterations_without_improvement, G, (unsigned long long)launches);
   eg_weights_free(weights);
   for (eg_ctx* c : ctx) eg_destroy(c);
