@@ -195,7 +195,10 @@ int check_cfg(const eg_ctx* c, const eg_run_cfg* cfg) {
   if (!cfg) return eg_fail(EG_ERR_INVALID, "cfg is NULL");
   if (!c->map_ready) return eg_fail(EG_ERR_STATE, "no map loaded: call eg_map_load or eg_map_set first");
   if (cfg->enable_construction_delays)
-    return eg_fail(EG_ERR_INVALID, "enable_construction_delays=1 is not implemented on the device path (SURVEY.md §8(f) N1)");
+    return eg_fail(EG_ERR_INVALID,
+                   "enable_construction_delays=1 is rejected: with delays on the reference's deficit handler cannot terminate "
+                   "(a plant added in the loop is Planned, never active within the year, so remaining_deficit never shrinks; "
+                   "simulation.rs:358-486, generator.rs:451-521) — see DESIGN.md section 9");
   return EG_OK;
 }
 

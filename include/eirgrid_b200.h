@@ -130,7 +130,7 @@ typedef struct {
 typedef struct {
   uint32_t cost_only;                 /* --cost-only → optimization_mode Some("cost_only") for the driver-side score */
   uint32_t enable_energy_sales;       /* default 1 */
-  uint32_t enable_construction_delays;/* default 0; 1 is not implemented on the device path yet → EG_ERR_INVALID */
+  uint32_t enable_construction_delays;/* default 0; 1 → EG_ERR_INVALID: the reference's deficit loop does not terminate with delays on */
   uint32_t replay_best;               /* run_iteration's replay_best_strategy: force_best_actions */
   uint32_t same_stream_all_episodes;  /* quirk Q8 (--seed re-seeds every episode identically); 0 = one stream per episode id */
   uint32_t reserved[3];
