@@ -194,6 +194,9 @@ struct Warp {
                               // the same sums re-priced at year-1 live in the scalar area (kVGcostPrev, kVOcostPrev)
   double off_amount;          // calc_total_carbon_offset(year)
   uint32_t n_gens, n_offs, flags;
+#ifdef EG_WALK_STATS
+  uint32_t dbg_steps, dbg_evals, dbg_cands, dbg_pairs, dbg_inr;
+#endif
   bool rows_dirty, dw_dirty, sorted_valid, total_valid;
   // Philox: lane l holds draw number rbase + l of episode `rng_id`
   unsigned long long rng_id;
@@ -392,7 +395,16 @@ struct Warp {
         bound *= size_factor;
         cand = bound > 0.0 && !(bound < best_score);
       }
+#ifdef EG_WALK_STATS
+      dbg_steps++;
+      dbg_inr += __popc(__ballot_sync(kFull, inr));
+#endif
       if (__any_sync(kFull, cand)) {
+#ifdef EG_WALK_STATS
+        dbg_evals++;
+        dbg_cands += __popc(__ballot_sync(kFull, cand));
+        dbg_pairs += n_gens;
+#endif
         // survivors multiply their factors in plant order (== multiplication order of the reference), one site per lane
         double sc = pre;
         if (sizeof(NearT) == 1) {
@@ -656,6 +668,9 @@ struct Warp {
     rng_id = p.same_stream ? 0ull : p.first_episode + ep;
     draw = 0; rbase = 0x80000000u; rbuf = 0ull;
     n_gens = 0; n_offs = 0; flags = 0;
+#ifdef EG_WALK_STATS
+    dbg_steps = dbg_evals = dbg_cands = dbg_pairs = dbg_inr = 0;
+#endif
     gcost = 0.0; ocost = 0.0; gen0 = gen1 = gen2 = 0.0; co2 = 0.0;
     {
       // clear the nearest-plant map, 4 bytes per lane and step (n_sites entries, padded to 16 bytes by the launcher)
@@ -867,7 +882,12 @@ struct Warp {
         case 4: word = (unsigned long long)__double_as_longlong(r_rel); break;
         case 5: word = (unsigned long long)n_gens | ((unsigned long long)n_offs << 32); break;
         case 6: word = (unsigned long long)(n_def_total & 0xFFFFu) | ((unsigned long long)(n_add_total & 0xFFFFu) << 16) | ((unsigned long long)flags << 32); break;
+#ifdef EG_WALK_STATS
+        // debug build: walk statistics instead of the reserved word (steps | evaluation steps << 16 | candidates << 32 | plant iterations / 16 << 48)
+        default: word = (unsigned long long)(dbg_steps & 0xFFFF) | ((unsigned long long)(dbg_evals & 0xFFFF) << 16) | ((unsigned long long)(dbg_cands & 0xFFFF) << 32) | ((unsigned long long)((dbg_pairs >> 4) & 0xFFFF) << 48); break;
+#else
         default: word = 0ull; break;
+#endif
       }
       ((unsigned long long*)(p.out + ep))[lane] = word;
     }

@@ -11,6 +11,7 @@
 //             [183,198) occurrences of deficit key k in current_deficit_actions
 // Integer sums make the result independent of the reduction order and of the number of GPUs.
 #include "stats.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -40,17 +41,34 @@ __global__ void eg_stats_reset_kernel(double* best_score, unsigned long long* be
   *best_index = ~0ull;
 }
 
+// One episode per WARP: its ~40 recorded actions are dealt out to the lanes (a thread- or year-per-lane mapping runs at
+// 1-3 active lanes because 2025 holds a third of an episode's actions), each lane folds its action into the block's
+// shared accumulator. Grid-stride over the batch.
 __global__ void __launch_bounds__(256) eg_stats_kernel(const EgStatsParams p) {
   __shared__ unsigned long long acc[EG_STATS_WORDS];
+  __shared__ unsigned long long best_mask[EG_NY];                      // actions that occur in best(y) = best_actions ++ best_deficit
+  __shared__ uint8_t best_cat[EG_NY][EG_MAX_ACTIONS_PER_YEAR * 3];     // that concatenation, by position
+  __shared__ uint8_t best_len[EG_NY];
   for (int i = threadIdx.x; i < EG_STATS_WORDS; i += blockDim.x) acc[i] = 0ull;
+  if (threadIdx.x < EG_NY) {
+    const int y = threadIdx.x;
+    const int nb = p.policy->n_best[y], nbd = p.policy->n_best_deficit[y];
+    unsigned long long m = 0ull;
+    for (int b = 0; b < nb; b++) { const int a = p.policy->best[y][b]; best_cat[y][b] = (uint8_t)a; m |= 1ull << a; }
+    for (int b = 0; b < nbd; b++) { const int a = p.policy->best_deficit[y][b]; best_cat[y][nb + b] = (uint8_t)a; m |= 1ull << a; }
+    best_mask[y] = m;
+    best_len[y] = (uint8_t)(nb + nbd);
+  }
   __syncthreads();
-  const uint32_t ep = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ep < p.n) {
-    const eg_result r = p.results[ep];
-    const eg_traj* t = p.trajs + ep;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+  double warp_best = -1.0;
+  for (uint32_t ep = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ep < p.n; ep += warps_total) {
+    const eg_result* rp = p.results + ep;
+    eg_result r;  // every lane reads the same 40 bytes (one broadcast transaction)
+    r.net_emissions = rp->net_emissions; r.public_opinion = rp->public_opinion; r.total_cost = rp->total_cost;
     const double score = default_score(r, p.ln100);
-    atomicMax((long long*)p.best_score, __double_as_longlong(score));  // scores are >= 0: bit order == value order
-    atomicAdd(&acc[0], 1ull);
+    warp_best = fmax(warp_best, score);
     bool pass = false;
     long long log_pen = 0, log_mild = 0;
     if (p.consts.has_best) {
@@ -67,35 +85,58 @@ __global__ void __launch_bounds__(256) eg_stats_kernel(const EgStatsParams p) {
           log_pen = llrint(log(penalty) * EG_STATS_FIXED_SCALE);
           log_mild = llrint(log(mild) * EG_STATS_FIXED_SCALE);
         }
-        atomicAdd(&acc[1], 1ull);
       }
     }
-    for (int y = 0; y < EG_NY; y++) {
+    if (lane == 0) {
+      atomicAdd(&acc[0], 1ull);
+      if (pass) atomicAdd(&acc[1], 1ull);
+    }
+    // The episode's records: current_run_actions ++ current_deficit_actions of every year, ~40 items in all, most of them
+    // in 2025. Lane y holds year y's counts; the items are numbered through all years (warp prefix sum) and dealt out 32 at
+    // a time, each lane finding its item's year by binary search over the prefix sums.
+    const eg_traj* t = p.trajs + ep;
+    int nd = 0, nrun = 0;
+    if (lane < EG_NY) {
+      nd = min((int)t->n_deficit[lane], EG_MAX_ACTIONS_PER_YEAR);
+      nrun = nd + min((int)t->n_additional[lane], EG_MAX_ACTIONS_PER_YEAR - nd);
+    }
+    const int cnt = nrun + nd;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    for (int base = 0; base < total; base += 32) {
+      const int q = base + lane;
+      int y = 0;  // number of years whose items all come before item q
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int v = __shfl_sync(0xFFFFFFFFu, incl, y + step - 1);
+        if (v <= q) y += step;
+      }
+      const int y_incl = __shfl_sync(0xFFFFFFFFu, incl, y), y_cnt = __shfl_sync(0xFFFFFFFFu, cnt, y);
+      const int y_nrun = __shfl_sync(0xFFFFFFFFu, nrun, y);
+      if (q >= total) continue;
+      const int i = q - (y_incl - y_cnt);
+      const int a = t->actions[y][i < y_nrun ? i : i - y_nrun];
+      if (a >= EG_N_ACTIONS) continue;  // not an action code (records are produced by the episode kernels; defensive)
       unsigned long long* ys = acc + EG_STATS_HEADER + y * EG_STATS_YEAR_STRIDE;
-      const int nd = min((int)t->n_deficit[y], EG_MAX_ACTIONS_PER_YEAR);
-      const int na = min((int)t->n_additional[y], EG_MAX_ACTIONS_PER_YEAR - nd);
-      const int nrun = nd + na, ncur = nrun + nd;  // current_run_actions ++ current_deficit_actions
-      const int nb = p.policy->n_best[y], nbd = p.policy->n_best_deficit[y], nbest = nb + nbd;
-      for (int i = 0; i < ncur; i++) {
-        const int a = i < nrun ? t->actions[y][i] : t->actions[y][i - nrun];
-        if (i < nrun) atomicAdd(&ys[2 * EG_N_ACTIONS + a], 1ull);
-        else {
-          const int k = deficit_key_of_action(a);
-          if (k >= 0) atomicAdd(&ys[3 * EG_N_ACTIONS + k], 1ull);
-        }
-        if (!pass) continue;
-        bool in_best = false;
-        for (int b = 0; b < nb && !in_best; b++) in_best = p.policy->best[y][b] == a;
-        for (int b = 0; b < nbd && !in_best; b++) in_best = p.policy->best_deficit[y][b] == a;
-        if (!in_best) {
-          atomicAdd(&ys[a], (unsigned long long)log_pen);
-        } else if (i < nbest) {
-          const int bi = i < nb ? p.policy->best[y][i] : p.policy->best_deficit[y][i - nb];
-          if (bi != a) atomicAdd(&ys[EG_N_ACTIONS + a], (unsigned long long)log_mild);
-        }
+      if (i < y_nrun) atomicAdd(&ys[2 * EG_N_ACTIONS + a], 1ull);
+      else {
+        const int k = deficit_key_of_action(a);
+        if (k >= 0) atomicAdd(&ys[3 * EG_N_ACTIONS + k], 1ull);
+      }
+      if (!pass) continue;
+      if (!((best_mask[y] >> a) & 1ull)) {
+        atomicAdd(&ys[a], (unsigned long long)log_pen);
+      } else if (i < (int)best_len[y]) {
+        if (best_cat[y][i] != a) atomicAdd(&ys[EG_N_ACTIONS + a], (unsigned long long)log_mild);
       }
     }
   }
+  if (lane == 0 && warp_best >= 0.0) atomicMax((long long*)p.best_score, __double_as_longlong(warp_best));  // scores are >= 0: bit order == value order
   __syncthreads();
   for (int i = threadIdx.x; i < EG_STATS_WORDS; i += blockDim.x)
     if (acc[i]) atomicAdd((unsigned long long*)&p.stats[i], acc[i]);
@@ -134,7 +175,11 @@ cudaError_t eg_launch_stats(const EgStatsParams& p, cudaStream_t stream) {
   eg_stats_reset_kernel<<<1, 1, 0, stream>>>(p.best_score, p.best_index);
   if (p.n == 0) return cudaGetLastError();
   const uint32_t blocks = (p.n + 255) / 256;
-  eg_stats_kernel<<<blocks, 256, 0, stream>>>(p);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const uint32_t stat_blocks = std::min<uint32_t>((uint32_t)sms * 4u, (p.n + 7) / 8);  // 8 warps (episodes) per block, grid-stride
+  eg_stats_kernel<<<stat_blocks, 256, 0, stream>>>(p);
   eg_stats_argbest_kernel<<<blocks, 256, 0, stream>>>(p);
   return cudaGetLastError();
 }
