@@ -111,11 +111,13 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     w = O.World.ireland(fast=True)
     ow = O.Weights()
-    # size one step at ~2 s of CPU work
+    # size one step so that the whole run (warm-up + K steps) is about a minute of CPU work, at most 2 s per step
     probe = max(threads, 4)
     t0 = time.perf_counter()
     w.rollout(ow, probe, seed=20250101, mode=O.FAITHFUL, literal_scan=True, threads=threads, want_sites=False, want_yearly=False)
-    per_step = max(probe, int(probe / (time.perf_counter() - t0) * 2.0))
+    step_seconds = min(2.0, 60.0 / max(args.steps + args.warmup, 1))
+    per_step = max(probe, int(probe / (time.perf_counter() - t0) * step_seconds))
+    per_step = max(2 * threads, (per_step + threads - 1) // threads * threads)  # whole rounds of the thread pool
     first = probe
     for _ in range(args.warmup):
         w.rollout(ow, per_step, seed=20250101, first_episode=first, mode=O.FAITHFUL, literal_scan=True, threads=threads, want_sites=False, want_yearly=False)
