@@ -707,8 +707,11 @@ struct Warp {
         if (deficit_mode) {
           if (remaining > 0.0) {                             // simulation.rs:358
             attempts++;
-            if (REPLAY) action = n_def < in_def ? in->actions[y][n_def] : kBattery100;
+            if (REPLAY) { action = replay_def < in_def ? in->actions[y][replay_def] : kBattery100; replay_def++; }
             else action = attempts < 5 ? sample_deficit_action(y, &replay_def) : kBattery100;
+            // "Only add a generator if the sampled action is an AddGenerator" (simulation.rs:396-397): anything else is
+            // neither applied nor recorded and the loop tries again (recorded trajectories can contain such entries)
+            if (action >= 45) continue;
             is_def = true;
           } else {                                           // simulation.rs:490-519
             if (learn) {
@@ -753,7 +756,7 @@ struct Warp {
           const int ot = a / 3;
           add_offset(ot, a - 3 * ot, y);
         }                                                    // 57..60: no generator id matches / DoNothing (Q4)
-        if (is_def && site < 0 && action < 45) { remaining = 0.0; continue; }  // no site with score > 0: flagged, loop left
+        if (is_def && site < 0) { remaining = 0.0; continue; }  // no site with score > 0: flagged, loop left
         record(n_def + n_add, action, site);
         if (is_def) {
           n_def++;
