@@ -20,7 +20,7 @@ EXPORTS = [
     "eg_weights_set_table", "eg_weights_get_best", "eg_deficit_key_action", "eg_rollout_batch", "eg_weights_upload",
     "eg_rollout_batch_device", "eg_replay_batch", "eg_replay_batch_device", "eg_update", "eg_update_stats_device",
     "eg_update_apply_stats", "eg_location_analysis", "eg_update_stats_clear_device", "eg_update_pack_best_device",
-    "eg_train_batch_begin", "eg_train_batch_end", "eg_train_batch_results", "eg_update_combine_apply",
+    "eg_export_best_run_csv", "eg_train_batch_begin", "eg_train_batch_end", "eg_train_batch_results", "eg_update_combine_apply",
 ]
 
 
@@ -76,6 +76,7 @@ def lib():
     L.eg_update_stats_device.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp]
     L.eg_update_stats_clear_device.argtypes = [vp, vp]
     L.eg_update_pack_best_device.argtypes = [vp, vp, vp, u32, vp, vp, u64, vp]
+    L.eg_export_best_run_csv.argtypes = [vp, vp, C.POINTER(_abi.RunCfg), C.c_char_p, C.c_char_p]
     L.eg_train_batch_begin.argtypes = [vp, vp, C.POINTER(_abi.RunCfg), u64, u64, u32]
     L.eg_train_batch_end.argtypes = [vp, vp, vp]
     L.eg_train_batch_results.argtypes = [vp, vp, vp]
@@ -287,6 +288,13 @@ class Context:
     def update_pack_best_device(self, n, d_results, d_traj, d_best_score, d_best_index, first_global_episode, d_record):
         check(self.L.eg_update_pack_best_device(self.h, _dev_ptr(d_results), _dev_ptr(d_traj), n, _dev_ptr(d_best_score),
                                                 _dev_ptr(d_best_index), first_global_episode, _dev_ptr(d_record)))
+
+    def export_best_run_csv(self, weights, output_dir, cfg=None):
+        """CsvExporter::export_simulation_results for the best strategy in `weights`; returns the directory written."""
+        cfg = cfg or _abi.RunCfg()
+        buf = C.create_string_buffer(512)
+        check(self.L.eg_export_best_run_csv(self.h, weights.h, C.byref(cfg), os.fsencode(output_dir), buf))
+        return buf.value.decode()
 
     def location_analysis(self, use_loaded_map, half_steps=25, step=2000.0, first_point=0, n_points=None):
         side = 2 * half_steps + 1

@@ -3,7 +3,12 @@
 // EG_ERR_NO_DEVICE / EG_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
 #include <cmath>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 #include "common.hpp"
@@ -482,6 +487,158 @@ int eg_train_batch_results(eg_ctx* c, eg_result* out, eg_traj* traj_out) {
   EG_CUDA(cudaMemcpyAsync(out, c->s_out, (size_t)c->train_n * sizeof(eg_result), cudaMemcpyDeviceToHost, c->stream));
   if (traj_out) EG_CUDA(cudaMemcpyAsync(traj_out, c->s_traj, (size_t)c->train_n * sizeof(eg_traj), cudaMemcpyDeviceToHost, c->stream));
   EG_CUDA(cudaStreamSynchronize(c->stream));
+  return EG_OK;
+}
+
+// ---- CSV export of the best run (utils/csv_export.rs) ------------------------------------------------------------
+namespace {
+
+const char* const kCsvGenNames[EG_NT] = {"OnshoreWind", "OffshoreWind", "DomesticSolar", "CommercialSolar", "UtilitySolar", "Nuclear", "CoalPlant",
+                                         "GasCombinedCycle", "GasPeaker", "Biomass", "HydroDam", "PumpedStorage", "BatteryStorage",
+                                         "TidalGenerator", "WaveEnergy"};
+const char* const kCsvOffsetNames[EG_N_OFFSET_TYPES] = {"Forest", "Wetland", "ActiveCapture", "CarbonCredit"};
+
+// Rust's `{}` for f64: shortest digits that round-trip, never scientific notation
+std::string rust_display(double v) {
+  char buf[400];
+  for (int prec = 1; prec <= 17; prec++) {
+    std::snprintf(buf, sizeof(buf), "%.*g", prec, v);
+    if (std::strtod(buf, nullptr) == v) break;
+  }
+  if (!std::strpbrk(buf, "eE")) return buf;
+  // re-print without exponent: enough fixed digits to round-trip
+  for (int prec = 0; prec <= 340; prec++) {
+    std::snprintf(buf, sizeof(buf), "%.*f", prec, v);
+    if (std::strtod(buf, nullptr) == v) break;
+  }
+  return buf;
+}
+
+std::string fixed(double v, int prec) {
+  char buf[400];
+  std::snprintf(buf, sizeof(buf), "%.*f", prec, v);
+  return buf;
+}
+
+bool mkdir_p(const std::string& p) {
+  std::string cur;
+  for (size_t i = 0; i <= p.size(); i++) {
+    if ((i == p.size() || p[i] == '/') && !cur.empty()) {
+      struct stat st;
+      if (stat(cur.c_str(), &st) != 0 && mkdir(cur.c_str(), 0777) != 0 && stat(cur.c_str(), &st) != 0) return false;
+    }
+    if (i < p.size()) cur += p[i];
+  }
+  return true;
+}
+
+}  // namespace
+
+int eg_export_best_run_csv(eg_ctx* c, const eg_weights* w, const eg_run_cfg* cfg, const char* output_dir, char* written_dir) {
+  int rc = check_cfg(c, cfg);
+  if (rc) return rc;
+  if (!w || !output_dir) return eg_fail(EG_ERR_INVALID, "eg_export_best_run_csv: NULL argument");
+  if (!w->has_best) return eg_fail(EG_ERR_STATE, "eg_export_best_run_csv: the weights hold no best strategy yet");
+  // the best run as a record: best_actions[y] = deficit actions followed by the additional actions (Appendix C of SURVEY.md)
+  eg_traj traj;
+  std::memset(&traj, 0, sizeof(traj));
+  for (int y = 0; y < EG_NY; y++) {
+    const size_t nd = std::min<size_t>(w->best_deficit_actions[y].size(), EG_MAX_ACTIONS_PER_YEAR);
+    const size_t n = std::min<size_t>(w->best_actions[y].size(), EG_MAX_ACTIONS_PER_YEAR);
+    traj.n_deficit[y] = (uint8_t)std::min(nd, n);
+    traj.n_additional[y] = (uint8_t)(n - traj.n_deficit[y]);
+    for (size_t i = 0; i < n; i++) traj.actions[y][i] = w->best_actions[y][i];
+  }
+  eg_result res;
+  static eg_yearly yearly;
+  eg_run_cfg rcfg = *cfg;
+  rcfg.replay_best = 0;
+  if ((rc = eg_replay_batch(c, &rcfg, &traj, 1, &res, nullptr, &yearly))) return rc;
+
+  char ts[32];
+  const std::time_t t = std::time(nullptr);
+  std::tm tmv;
+  localtime_r(&t, &tmv);
+  std::strftime(ts, sizeof(ts), "%Y%m%d_%H%M%S", &tmv);  // CsvExporter::new, csv_export.rs:114-128
+  const std::string dir = std::string(output_dir) + "/" + ts;
+  if (!mkdir_p(dir + "/yearly_details")) return eg_fail(EG_ERR_IO, "cannot create " + dir);
+  const EgSmallTables& T = c->htab.small;
+
+  {  // simulation_summary.csv, csv_export.rs:215-432
+    std::FILE* f = std::fopen((dir + "/simulation_summary.csv").c_str(), "w");
+    if (!f) return eg_fail(EG_ERR_IO, "cannot write simulation_summary.csv in " + dir);
+    std::fprintf(f, "Simulation Summary\nTimestamp,%s\n\n", ts);
+    std::fprintf(f, "Final Metrics\nFinal Net Emissions (tonnes CO2),%s\n", rust_display(res.net_emissions).c_str());
+    std::fprintf(f, "Average Public Opinion (%%),%s\n", fixed(res.public_opinion * 100.0, 2).c_str());
+    std::fprintf(f, "Total Cost (\xE2\x82\xAC),%s\n", fixed(res.total_cost, 2).c_str());
+    std::fprintf(f, "Power Reliability (%%),%s\n\n", fixed(res.power_reliability * 100.0, 2).c_str());
+    std::fprintf(f, "Actions Taken\nYear,Action Type,Generator Type,Generator ID,Operation %%,Offset Type,Estimated Cost (\xE2\x82\xAC)\n");
+    for (int y = 0; y < EG_NY; y++) {
+      // SimulationResult.actions holds the additional actions only (simulation.rs:193, iteration.rs:90)
+      for (int i = traj.n_deficit[y]; i < traj.n_deficit[y] + traj.n_additional[y]; i++) {
+        const int a = traj.actions[y][i];
+        const int year = EG_BASE_YEAR + y;
+        if (a < 45) {
+          const int tp = a / 3, m = a % 3;
+          // calc_generator_cost(type, base_cost(year), year, can_be_urban, requires_water, requires_water) * multiplier / 100
+          const double cost = c->htab.plant_terms[(size_t)EG_OPC_INDEX(y, tp, 0, y) * 2 + 1] * T.mult[m];
+          std::fprintf(f, "%d,AddGenerator,%s,,,,%s\n", year, kCsvGenNames[tp], fixed(cost, 2).c_str());
+        } else if (a < 57) {
+          const int o = (a - 45) / 3, m = (a - 45) % 3;
+          const double cost = (T.off_base_cost[o] * T.year[y].inflation) * T.mult[m];
+          std::fprintf(f, "%d,AddCarbonOffset,,,,%s,%s\n", year, kCsvOffsetNames[o], fixed(cost, 2).c_str());
+        } else if (a == EG_ACT_UPGRADE) std::fprintf(f, "%d,UpgradeEfficiency,,,,,0.00\n", year);   // empty id: no generator found
+        else if (a == EG_ACT_ADJUST) std::fprintf(f, "%d,AdjustOperation,,,0,,0.00\n", year);
+        else if (a == EG_ACT_CLOSE) std::fprintf(f, "%d,CloseGenerator,,,,,0.00\n", year);
+        else std::fprintf(f, "%d,DoNothing,,,,,0.00\n", year);
+      }
+    }
+    std::fprintf(f, "\nYearly Summary Metrics\n");
+    std::fprintf(f, "Year,Population,PowerUsage,PowerGeneration,PowerBalance,PublicOpinion,YearlyCapitalCost,TotalCapitalCost,Inflation,CO2Emissions,"
+                    "CarbonOffset,NetEmissions,YearlyRevenue,TotalRevenue,ActiveGenerators,YearlyUpgradeCosts,YearlyClosureCosts,YearlyTotalCost,TotalCost\n");
+    for (int y = 0; y < EG_NY; y++) {
+      const eg_year_metrics& m = yearly.y[y];
+      std::fprintf(f, "%d,%u,%.2f,%.2f,%.2f,%.4f,%.2f,%.2f,%.4f,%.2f,%.2f,%.2f,%.2f,%.2f,%u,%.2f,%.2f,%.2f,%.2f\n", EG_BASE_YEAR + y, m.total_population,
+                   m.total_power_usage, m.total_power_generation, m.power_balance, m.average_public_opinion, m.yearly_capital_cost,
+                   m.total_capital_cost, m.inflation_factor, m.total_co2_emissions, m.total_carbon_offset, m.net_co2_emissions,
+                   m.yearly_carbon_credit_revenue, m.total_carbon_credit_revenue, m.active_generators, 0.0, 0.0, m.yearly_total_cost, m.total_cost);
+    }
+    std::fclose(f);
+  }
+  if (!w->history.empty()) {  // improvement_history.csv, csv_export.rs:155-212
+    std::FILE* f = std::fopen((dir + "/improvement_history.csv").c_str(), "w");
+    if (!f) return eg_fail(EG_ERR_IO, "cannot write improvement_history.csv in " + dir);
+    std::fprintf(f, "Iteration,Score,Net Emissions (tonnes),Total Cost (\xE2\x82\xAC),Public Opinion (%%),Power Reliability (%%),Score Improvement (%%),Timestamp\n");
+    double prev = 0.0;
+    for (size_t i = 0; i < w->history.size(); i++) {
+      const EgImprovement& h = w->history[i];
+      const double imp = (i > 0 && prev > 0.0) ? ((h.score - prev) / prev) * 100.0 : 0.0;
+      std::fprintf(f, "%u,%.6f,%.2f,%.2f,%.2f,%.2f,%.2f,%s\n", h.iteration, h.score, h.net_emissions, h.total_cost, h.public_opinion * 100.0,
+                   h.power_reliability * 100.0, imp, h.timestamp.c_str());
+      prev = h.score;
+    }
+    std::fclose(f);
+  }
+  {  // yearly_details/settlements.csv, csv_export.rs:456-530 (population and usage re-derived from the 2025 values, as there)
+    std::FILE* f = std::fopen((dir + "/yearly_details/settlements.csv").c_str(), "w");
+    if (!f) return eg_fail(EG_ERR_IO, "cannot write settlements.csv in " + dir);
+    std::fprintf(f, "Year,Name,Longitude,Latitude,Population,PowerUsage\n");
+    const EgHostMap& m = c->hmap;
+    for (int y = 0; y < EG_NY; y++) {
+      // f64::powi lowers to repeated squaring (compiler-rt __powidf2); reproduce it for 1.01^n and 1.02^n
+      auto powi = [](double a, int b) { double r = 1.0; bool recip = b < 0; for (;;) { if (b & 1) r *= a; b /= 2; if (b == 0) break; a *= a; } return recip ? 1.0 / r : r; };
+      for (size_t s = 0; s < m.sx.size(); s++) {
+        const double xv = std::min(std::max(m.sx[s], 0.0), 50000.0), yv = std::min(std::max(m.sy[s], 0.0), 50000.0);
+        const double lon = -10.6 + ((-5.9 - -10.6) * (xv / 50000.0)), lat = 51.4 + ((55.4 - 51.4) * (yv / 50000.0));  // transform_grid_to_lat_lon, csv_export.rs:42-83
+        const uint32_t pop = (uint32_t)std::round((double)m.spop[s] * powi(1.01, y));
+        const double usage = ((double)m.spop[s] * 0.001) * powi(1.02, y);  // settlement power usage of the loader: population x 1 kW in MW
+        std::fprintf(f, "%d,%s,%.6f,%.6f,%u,%s\n", EG_BASE_YEAR + y, s < m.sname.size() ? m.sname[s].c_str() : ("Settlement_" + std::to_string(s)).c_str(),
+                     lon, lat, pop, rust_display(usage).c_str());
+      }
+    }
+    std::fclose(f);
+  }
+  if (written_dir) std::snprintf(written_dir, 512, "%s", dir.c_str());
   return EG_OK;
 }
 

@@ -153,6 +153,8 @@ int eg_host_map_load(EgHostMap* m, const char* settlements_json, const char* gen
       m->sx.push_back(x);
       m->sy.push_back(y);
       m->spop.push_back((uint32_t)pop->num);
+      const egjson::Value* name = s.get("name");
+      m->sname.push_back(name && name->kind == egjson::Value::String ? name->str : "Settlement_" + std::to_string(m->sname.size()));
     }
   } catch (const std::exception& ex) {
     return eg_fail(EG_ERR_IO, std::string(settlements_json) + ": " + ex.what());

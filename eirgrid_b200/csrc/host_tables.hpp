@@ -1,12 +1,14 @@
 // host_tables.hpp — host-side map (as loaded) and the small host-built tables.
 #pragma once
 #include <cstdint>
+#include <string>
 #include <vector>
 #include "tables.h"
 
 struct EgHostMap {
   std::vector<double> sx, sy;      // settlements, grid metres
   std::vector<uint32_t> spop;      // 2025 population
+  std::vector<std::string> sname;  // settlement names (CSV export only; empty for maps set through eg_map_set)
   std::vector<double> ex, ey, ecap;  // plants existing before the simulation
   std::vector<uint8_t> etype;
   std::vector<double> cx, cy;      // coastline polygon

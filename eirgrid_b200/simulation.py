@@ -191,13 +191,17 @@ def run_multi_simulation(asset_dir, num_iterations, parallel=True, continue_from
                                     "best_score": _best_score(weights) or 0.0})
                     json.dump(history, open(os.path.join(run_dir, "weight_history.json"), "w"), indent=2)
     elapsed = time.time() - t_start
+    csv_dir = None
     if rank == 0:
         weights.save_to_file(os.path.join(run_dir, "best_weights.json"))  # multi_simulation.rs:1161-1163
+        if enable_csv_export and weights.has_best_actions():  # multi_simulation.rs:852-925
+            csv_dir = trainer.ctx.export_best_run_csv(weights, os.path.join(run_dir, "enhanced_csv"),
+                                                      _abi.RunCfg(cost_only=optimization_mode == "cost_only", enable_energy_sales=enable_energy_sales))
     t = weights.table()
     summary = {"run_dir": run_dir, "iterations": completed, "start_iteration": start_iteration, "elapsed_s": elapsed,
                "episodes_per_s": (completed - start_iteration) / max(elapsed, 1e-9), "best_score": _best_score(weights),
                "best_metrics": {"final_net_emissions": t.best_metrics[0], "average_public_opinion": t.best_metrics[1],
                                 "total_cost": t.best_metrics[2], "power_reliability": t.best_metrics[3]} if t.has_best else None,
-               "iterations_without_improvement": t.iterations_without_improvement, "n_gpus": world}
+               "iterations_without_improvement": t.iterations_without_improvement, "n_gpus": world, "csv_dir": csv_dir}
     trainer.close()
     return summary

@@ -86,7 +86,7 @@ void usage() {
       "  -v, --verbose-state-logging\n"
       "      --cost-only                 Optimize for cost only\n"
       "      --enable-energy-sales       (always on)\n"
-      "      --enable-csv-export         (accepted; CSV export is out of scope)\n"
+      "      --enable-csv-export         (always on: summary, improvement history and settlements CSVs of the best run)\n"
       "      --debug-logging, --debug-weights, --track-weight-history\n"
       "      --enable-construction-delays\n"
       "additions: --assets <DIR> --batch-size <N> --update-mode batch|sequential --master-seed <S> --devices 0,1,..");
@@ -361,6 +361,14 @@ int main(int argc, char** argv) {
   check(eg_weights_save_json(weights, (run_dir + "/best_weights.json").c_str()), "eg_weights_save_json");  // multi_simulation.rs:1161-1163
   bool has_best = false;
   const double best = best_score_of(weights, &has_best);
+  if (a.enable_csv_export && has_best) {  // multi_simulation.rs:852-925: <run_dir>/enhanced_csv/<timestamp>/
+    eg_run_cfg cfg{};
+    cfg.cost_only = a.cost_only;
+    cfg.enable_energy_sales = a.enable_energy_sales;
+    char written[512];
+    check(eg_export_best_run_csv(ctx[0], weights, &cfg, (run_dir + "/enhanced_csv").c_str(), written), "eg_export_best_run_csv");
+    std::printf("Enhanced simulation results exported to: %s\n", written);
+  }
   uint64_t launches = 0;
   for (size_t g = 0; g < G; g++) launches += eg_kernel_launches(ctx[g]);
   std::printf("{\"run_dir\": \"%s\", \"iterations\": %llu, \"start_iteration\": %llu, \"elapsed_s\": %.3f, \"episodes_per_s\": %.1f, "

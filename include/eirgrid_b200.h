@@ -292,6 +292,16 @@ int eg_train_batch_results(eg_ctx* ctx, eg_result* out, eg_traj* traj_out /* nul
 int eg_update_combine_apply(eg_weights* w, const int64_t* stats_sum, const void* records, uint32_t n_records,
                             uint64_t n_total, uint64_t first_episode, eg_update_stats* stats_out);
 
+/* ---- CSV export of the best run (utils/csv_export.rs:114-432,456-530 and the call site
+ * core/multi_simulation.rs:852-925). The best strategy stored in `w` is replayed on the GPU (eg_replay_batch) and written as
+ *   <output_dir>/<%Y%m%d_%H%M%S>/simulation_summary.csv     final metrics, actions taken with estimated costs, yearly summary
+ *   <output_dir>/<%Y%m%d_%H%M%S>/improvement_history.csv    the weights' improvement history
+ *   <output_dir>/<%Y%m%d_%H%M%S>/yearly_details/settlements.csv
+ * in the reference's column order and number formats. generators.csv, carbon_offsets.csv and the operation logs of the
+ * reference's exporter are NOT written (per-plant lifetime/operating-cost bookkeeping is off the hot path, Appendix B).
+ * `written_dir` (nullable, >= 512 bytes) receives the directory. Returns EG_ERR_STATE if `w` has no best strategy. */
+int eg_export_best_run_csv(eg_ctx* ctx, const eg_weights* w, const eg_run_cfg* cfg, const char* output_dir, char* written_dir);
+
 /* ---- location suitability analysis (BASELINE config 5): replaces Map::analyze_locations →
  * LocationAnalysis::analyze_map (map_handler.rs:61-142) and calculate_generator_suitability
  * (map_handler.rs:1319-1396) / the unused MSL kernel computeSuitability (metal:239-258).

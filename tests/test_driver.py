@@ -44,7 +44,7 @@ def test_checkpointed_run_and_resume(tmp_path):
     s1 = S.run_multi_simulation(ASSETS, 4096, checkpoint_dir=ck, checkpoint_interval=5, cache_dir=str(tmp_path / "cache"),
                                 force_full_simulation=False, batch_size=2048, master_seed=3, log=lambda *a: None)
     d = s1["run_dir"]
-    assert sorted(os.listdir(d)) == ["best_weights.json", "checkpoint_iteration.txt", "latest_weights.json"]
+    assert sorted(os.listdir(d)) == ["best_weights.json", "checkpoint_iteration.txt", "enhanced_csv", "latest_weights.json"]
     assert open(os.path.join(d, "checkpoint_iteration.txt")).read() == "4096"
     w = json.load(open(os.path.join(d, "latest_weights.json")))
     assert w["iteration_count"] == 4096 and w["best_metrics"] is not None
