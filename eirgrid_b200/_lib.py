@@ -20,7 +20,7 @@ EXPORTS = [
     "eg_weights_set_table", "eg_weights_get_best", "eg_deficit_key_action", "eg_rollout_batch", "eg_weights_upload",
     "eg_rollout_batch_device", "eg_replay_batch", "eg_replay_batch_device", "eg_update", "eg_update_stats_device",
     "eg_update_apply_stats", "eg_location_analysis", "eg_update_stats_clear_device", "eg_update_pack_best_device",
-    "eg_export_best_run_csv", "eg_train_batch_begin", "eg_train_batch_end", "eg_train_batch_results", "eg_update_combine_apply",
+    "eg_export_best_run_csv", "eg_weights_history_append", "eg_train_batch_begin", "eg_train_batch_end", "eg_train_batch_results", "eg_update_combine_apply",
 ]
 
 
@@ -76,6 +76,7 @@ def lib():
     L.eg_update_stats_device.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp]
     L.eg_update_stats_clear_device.argtypes = [vp, vp]
     L.eg_update_pack_best_device.argtypes = [vp, vp, vp, u32, vp, vp, u64, vp]
+    L.eg_weights_history_append.argtypes = [vp, u64, C.c_char_p]
     L.eg_export_best_run_csv.argtypes = [vp, vp, C.POINTER(_abi.RunCfg), C.c_char_p, C.c_char_p]
     L.eg_train_batch_begin.argtypes = [vp, vp, C.POINTER(_abi.RunCfg), u64, u64, u32]
     L.eg_train_batch_end.argtypes = [vp, vp, vp]
@@ -129,6 +130,9 @@ class Weights:
         h = C.c_void_p()
         check(self.L.eg_weights_clone(self.h, C.byref(h)))
         return Weights(h)
+
+    def history_append(self, iteration, path):  # save_weight_history, multi_simulation.rs:179-207
+        check(self.L.eg_weights_history_append(self.h, int(iteration), os.fsencode(path)))
 
     def update_weights_from(self, other):  # ActionWeights::update_weights_from
         check(self.L.eg_weights_merge(self.h, other.h))

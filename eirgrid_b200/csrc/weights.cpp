@@ -697,6 +697,74 @@ int eg_update_apply_stats(eg_weights* w, const int64_t* stats, uint64_t n_total,
   return EG_OK;
 }
 
+int eg_weights_history_append(const eg_weights* w, uint64_t iteration, const char* history_path) {
+  if (!w || !history_path) return eg_fail(EG_ERR_INVALID, "eg_weights_history_append: NULL argument");
+  auto action_display = [](int code) -> std::string {  // impl Display for GridAction, ai/actions/grid_action.rs:18-41
+    if (code < 45) return std::string("AddGenerator(") + kGenNames[code / 3] + ", " + std::to_string(kMultPercent[code % 3]) + "%)";
+    if (code < 57) return std::string("AddCarbonOffset(") + kOffsetNames[(code - 45) / 3] + ", " + std::to_string(kMultPercent[(code - 45) % 3]) + "%)";
+    if (code == EG_ACT_UPGRADE) return "UpgradeEfficiency()";
+    if (code == EG_ACT_ADJUST) return "AdjustOperation(, 0%)";
+    if (code == EG_ACT_CLOSE) return "CloseGenerator()";
+    return "DoNothing";
+  };
+  const double best_score = w->has_best ? eg_score(w->best_metrics, w->optimization_mode == "cost_only") : 0.0;
+  char ts[48];
+  {
+    const std::time_t t = std::time(nullptr);
+    std::tm tmv;
+    localtime_r(&t, &tmv);
+    char tz[8];
+    std::strftime(ts, sizeof(ts), "%Y-%m-%dT%H:%M:%S", &tmv);
+    std::strftime(tz, sizeof(tz), "%z", &tmv);  // +hhmm -> +hh:mm
+    std::string z = tz;
+    if (z.size() == 5) z.insert(3, ":");
+    std::snprintf(ts + std::strlen(ts), sizeof(ts) - std::strlen(ts), "%s", z.c_str());
+  }
+  const std::string i2 = "    ", i3 = "      ", i4 = "        ";
+  std::string o = "  {\n    \"iteration\": " + std::to_string(iteration) + ",\n    \"timestamp\": \"" + ts + "\",\n    \"weights\": {\n";
+  auto rows = [&](const char* name, int n_keys, const double* table, auto key_name, bool present) {
+    o += i3 + "\"" + name + "\": {";
+    if (present) {
+      for (int y = 0; y < EG_NY; y++) {
+        o += std::string(y ? "," : "") + "\n" + i4 + "\"" + std::to_string(EG_BASE_YEAR + y) + "\": {";
+        for (int k = 0; k < n_keys; k++)
+          o += std::string(k ? "," : "") + "\n" + i4 + "  \"" + key_name(k) + "\": " + egjson::fmt_double(table[(size_t)y * n_keys + k]);
+        o += "\n" + i4 + "}";
+      }
+      o += "\n" + i3;
+    }
+    o += "}";
+  };
+  rows("weights", EG_N_ACTIONS, &w->w[0][0], [&](int k) { return action_display(k); }, true);
+  o += ",\n";
+  rows("action_count_weights", EG_N_COUNT_KEYS, &w->cw[0][0], [&](int k) { return std::to_string(k); }, w->has_count_weights);
+  o += ",\n" + i3 + "\"learning_rate\": " + egjson::fmt_double(w->learning_rate);
+  o += ",\n" + i3 + "\"iteration_count\": " + std::to_string(w->iteration_count);
+  o += ",\n" + i3 + "\"iterations_without_improvement\": " + std::to_string(w->iwi);
+  o += ",\n" + i3 + "\"exploration_rate\": " + egjson::fmt_double(w->exploration_rate);
+  o += ",\n" + i3 + "\"force_best_actions\": false";
+  o += ",\n";
+  rows("deficit_weights", EG_N_DEFICIT_KEYS, &w->dw[0][0], [&](int k) { return action_display(k < 14 ? 3 * kDeficitKeyType[k] : EG_ACT_DO_NOTHING); }, true);
+  o += ",\n" + i3 + "\"guaranteed_best_actions\": false";
+  o += ",\n" + i3 + "\"optimization_mode\": " + (w->optimization_mode.empty() ? std::string("null") : "\"" + w->optimization_mode + "\"");
+  o += ",\n" + i3 + "\"best_score\": " + egjson::fmt_double(best_score) + "\n" + i2 + "},\n";
+  o += i2 + "\"best_score\": " + egjson::fmt_double(best_score) + "\n  }";
+  // append to the array without re-parsing it: the file is only ever written by this function (or is "[]" / missing)
+  std::string text;
+  egjson::read_file(history_path, &text);
+  size_t end = text.find_last_of(']');
+  std::string head = end == std::string::npos ? "[" : text.substr(0, end);
+  while (!head.empty() && (head.back() == ' ' || head.back() == '\n' || head.back() == '\t' || head.back() == '\r')) head.pop_back();
+  const bool first = head.empty() || head == "[";
+  if (head.empty()) head = "[";
+  const std::string out = head + (first ? "\n" : ",\n") + o + "\n]";
+  std::FILE* f = std::fopen(history_path, "w");
+  if (!f) return eg_fail(EG_ERR_IO, std::string("cannot write ") + history_path);
+  std::fwrite(out.data(), 1, out.size(), f);
+  std::fclose(f);
+  return EG_OK;
+}
+
 int eg_update_combine_apply(eg_weights* w, const int64_t* stats_sum, const void* records, uint32_t n_records, uint64_t n_total,
                             uint64_t first_episode, eg_update_stats* stats_out) {
   if (!w || !stats_sum || (!records && n_records)) return eg_fail(EG_ERR_INVALID, "eg_update_combine_apply: NULL argument");

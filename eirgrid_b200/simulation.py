@@ -185,11 +185,7 @@ def run_multi_simulation(asset_dir, num_iterations, parallel=True, continue_from
                 weights.save_to_file(os.path.join(run_dir, "latest_weights.json"))
                 open(os.path.join(run_dir, "checkpoint_iteration.txt"), "w").write(str(min(completed, num_iterations)))
                 if track_weight_history:
-                    t = weights.table()
-                    history.append({"iteration": completed, "timestamp": datetime.datetime.now().astimezone().isoformat(),
-                                    "weights": {str(2025 + y): {_abi.action_name(k): t.weights[y][k] for k in range(_abi.N_ACTIONS)} for y in range(26)},
-                                    "best_score": _best_score(weights) or 0.0})
-                    json.dump(history, open(os.path.join(run_dir, "weight_history.json"), "w"), indent=2)
+                    weights.history_append(completed, os.path.join(run_dir, "weight_history.json"))
     elapsed = time.time() - t_start
     csv_dir = None
     if rank == 0:

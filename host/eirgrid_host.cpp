@@ -355,6 +355,8 @@ int main(int argc, char** argv) {
       next_checkpoint = (completed / a.checkpoint_interval + 1) * a.checkpoint_interval;
       check(eg_weights_save_json(weights, (run_dir + "/latest_weights.json").c_str()), "eg_weights_save_json");
       std::ofstream(run_dir + "/checkpoint_iteration.txt") << std::min(completed, a.iterations);
+      if (a.track_weight_history)
+        check(eg_weights_history_append(weights, completed, (run_dir + "/weight_history.json").c_str()), "eg_weights_history_append");
     }
   }
   const double elapsed = now_s() - t_start;

@@ -214,6 +214,10 @@ int eg_weights_clone(const eg_weights* src, eg_weights** out);
 int eg_weights_load_json(const char* path, eg_weights** out);
 int eg_weights_save_json(const eg_weights* w, const char* path);
 int eg_weights_merge(eg_weights* dst, const eg_weights* other);
+/* --track-weight-history: append one snapshot {iteration, timestamp (RFC 3339), weights: ActionWeights::to_json(), best_score}
+ * to the JSON array in `history_path` (created if missing) — save_weight_history, core/multi_simulation.rs:179-207, with
+ * to_json of weights/serialization.rs:495-540: the file aiSimulator/tools/visualization/weight_history_animation.py reads. */
+int eg_weights_history_append(const eg_weights* w, uint64_t iteration, const char* history_path);
 int eg_weights_get_table(const eg_weights* w, eg_weights_table* out);
 int eg_weights_set_table(eg_weights* w, const eg_weights_table* in);
 /* best strategy lists (best_actions / best_deficit_actions, Option<HashMap<u32, Vec<GridAction>>>):

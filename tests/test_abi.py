@@ -126,3 +126,29 @@ def test_load_errors_are_reported(tmp_path):
     t = w.table()
     assert t.weights[0][60] == 0.25 and t.weights[0][15] == 0.03 and t.iteration_count == 7
     assert t.deficit_weights[0][0] == 0.15  # defaults when the file has none (weights/serialization.rs:266-283)
+
+
+def test_weight_history_file_is_what_the_animation_tool_reads(tmp_path, oracle_world):
+    """save_weight_history (multi_simulation.rs:179-207): a JSON array of {iteration, timestamp, weights: to_json(), best_score};
+    tools/visualization/weight_history_animation.py reads entry['weights']['weights'][year][action] and the learning rates."""
+    w = _lib.Weights()
+    path = str(tmp_path / "weight_history.json")
+    open(path, "w").write("[]")
+    w.history_append(5, path)
+    eres, etraj, _, _ = oracle_world.rollout(O.Weights(), 16, seed=5)
+    w.update(eres, etraj)
+    w.history_append(10, path)
+    hist = json.load(open(path))
+    assert [h["iteration"] for h in hist] == [5, 10]
+    assert hist[0]["best_score"] == 0.0 and hist[1]["best_score"] > 1.0
+    assert re.match(r"\d{4}-\d\d-\d\dT\d\d:\d\d:\d\d[+-]\d\d:\d\d$", hist[0]["timestamp"])
+    inner = hist[1]["weights"]
+    for key in ("weights", "action_count_weights", "learning_rate", "iteration_count", "iterations_without_improvement",
+                "exploration_rate", "force_best_actions", "deficit_weights", "guaranteed_best_actions", "optimization_mode", "best_score"):
+        assert key in inner, key
+    assert set(inner["weights"].keys()) == {str(y) for y in range(2025, 2051)}
+    row = inner["weights"]["2025"]
+    assert len(row) == 61 and row["AddGenerator(OnshoreWind, 100%)"] == w.table().weights[0][0]
+    assert "AddCarbonOffset(Forest, 150%)" in row and "DoNothing" in row and "UpgradeEfficiency()" in row
+    assert len(inner["deficit_weights"]["2030"]) == 15 and len(inner["action_count_weights"]["2040"]) == 21
+    assert inner["learning_rate"] == 0.2 and inner["iteration_count"] == 16
