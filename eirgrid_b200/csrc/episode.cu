@@ -492,20 +492,17 @@ struct Warp {
   // asynchronous copy of the policy rows of year y (w[y] | dw[y] | cw[y]) into the buffer of that year's parity
   __device__ __forceinline__ void prefetch_rows(int y) {
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem) + sb + kOffRows + (uint32_t)(y & 1) * kRowBytes;
-    for (int k = lane; k < EG_N_ACTIONS + EG_N_DEFICIT_KEYS + EG_N_COUNT_KEYS; k += 32) {
-      const double* src = k < EG_N_ACTIONS ? &p.policy->w[y][k]
-                          : (k < EG_N_ACTIONS + EG_N_DEFICIT_KEYS ? &p.policy->dw[y][k - EG_N_ACTIONS] : &p.policy->cw[y][k - EG_N_ACTIONS - EG_N_DEFICIT_KEYS]);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * (uint32_t)k), "l"(src) : "memory");
-    }
+    static_assert(kRowDoubles == EG_POLICY_ROW && kRowBytes % 16 == 0, "the row is copied in 16-byte pieces");
+    const char* src = (const char*)&p.policy->rows[y][0];
+    for (int k = lane; k < kRowBytes / 16; k += 32)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (uint32_t)k), "l"(src + 16 * k) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   // the rows of year y are complete (requested a year earlier); request those of year y+1
   __device__ __forceinline__ void load_rows(int y) {
 #ifdef EG_ROWS_SYNC
     double* lw = LW(y);
-    for (int k = lane; k < EG_N_ACTIONS; k += 32) lw[k] = __ldg(&p.policy->w[y][k]);
-    if (lane < EG_N_DEFICIT_KEYS) LDW(y)[lane] = __ldg(&p.policy->dw[y][lane]);
-    if (lane < EG_N_COUNT_KEYS) LCW(y)[lane] = __ldg(&p.policy->cw[y][lane]);
+    for (int k = lane; k < EG_POLICY_ROW; k += 32) lw[k] = __ldg(&p.policy->rows[y][k]);
     __syncwarp();
 #else
     asm volatile("cp.async.wait_group 0;" ::: "memory");

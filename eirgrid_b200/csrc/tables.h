@@ -86,10 +86,12 @@ struct EgDeviceMap {      // device pointers + sizes, passed by value to the ker
   int near_wide;
 };
 
+#define EG_POLICY_ROW (EG_N_ACTIONS + EG_N_DEFICIT_KEYS + EG_N_COUNT_KEYS + 1)  // 98 doubles = 784 bytes, a multiple of 16
+
 struct EgPolicyDevice {   // weights snapshot + the per-batch constants of update_weights (learning.rs:36-55)
-  double w[EG_NY][EG_N_ACTIONS];
-  double dw[EG_NY][EG_N_DEFICIT_KEYS];
-  double cw[EG_NY][EG_N_COUNT_KEYS];
+  // one contiguous row per year: [61 regular | 15 deficit | 21 count weights | pad] — what an episode copies into its
+  // private buffer with 16-byte asynchronous copies at the start of the year
+  double rows[EG_NY][EG_POLICY_ROW];
   double learning_rate;
   double exploration_rate;
   double relative_improvement;    // learning.rs:40-49 (0 whenever a best strategy with positive score exists)

@@ -351,9 +351,11 @@ eg_weights::eg_weights() {  // ActionWeights::new, weights/core.rs:25-250
 
 void eg_weights_fill_policy(const eg_weights& W, EgPolicyDevice* out) {
   std::memset(out, 0, sizeof(*out));
-  std::memcpy(out->w, W.w, sizeof(W.w));
-  std::memcpy(out->dw, W.dw, sizeof(W.dw));
-  std::memcpy(out->cw, W.cw, sizeof(W.cw));
+  for (int y = 0; y < EG_NY; y++) {
+    std::memcpy(&out->rows[y][0], W.w[y], sizeof(W.w[y]));
+    std::memcpy(&out->rows[y][EG_N_ACTIONS], W.dw[y], sizeof(W.dw[y]));
+    std::memcpy(&out->rows[y][EG_N_ACTIONS + EG_N_DEFICIT_KEYS], W.cw[y], sizeof(W.cw[y]));
+  }
   out->learning_rate = W.learning_rate;
   out->exploration_rate = W.exploration_rate;
   // update_weights (learning.rs:36-49): final_impact_score and best_score are both score(best_metrics)
