@@ -198,6 +198,7 @@ struct Warp {
   uint32_t dbg_steps, dbg_evals, dbg_cands, dbg_pairs, dbg_inr;
 #endif
   bool rows_dirty, dw_dirty, sorted_valid, total_valid;
+  bool folded;                // this year's plant/offset sums (op_sum, gcost, ocost, off_amount) are valid
   // Philox: lane l holds draw number rbase + l of episode `rng_id`
   unsigned long long rng_id;
   uint32_t draw, rbase;
@@ -274,6 +275,14 @@ struct Warp {
         co2 += __ldg(&T->co2[t]);
       }
     }
+  }
+
+  // The year-dependent sums over the episode's plants and offsets (opinion, capital cost, offset amount and cost). They are
+  // read only by the deficit handler's state evaluations, by the yearly-metrics output and by the 2050 result, so the
+  // episode re-folds them only in years that need them: every fold starts from the tabulated prefix and runs over the whole
+  // list in order, so skipping a year changes nothing in the years that do fold.
+  __device__ __forceinline__ void year_folds(int y) {
+    const EgYearRow& yr = T->year[y];
     op_sum = __ldg(&yr.ex_opinion_sum);
     if (lane == 0) { VARS()[kVGcostPrev] = gcost; VARS()[kVOcostPrev] = ocost; }
     gcost = 0.0;
@@ -472,20 +481,24 @@ struct Warp {
     gen1 += cls == EG_ACC_INTERMITTENT ? mw : 0.0;
     gen2 += cls == EG_ACC_STORAGE ? mw : 0.0;
     co2 += __ldg(&T->co2[t]);
-    const double2 pt = plant_terms(t, m, y, y);
-    op_sum += gen_opinion(site, t, y, pt.x);
-    gcost += pt.y;
-    if (y > 0 && lane == 0) VARS()[kVGcostPrev] += gen_cost(t, m, y, y - 1);
+    if (folded) {  // keep this year's folded sums current
+      const double2 pt = plant_terms(t, m, y, y);
+      op_sum += gen_opinion(site, t, y, pt.x);
+      gcost += pt.y;
+      if (y > 0 && lane == 0) VARS()[kVGcostPrev] += gen_cost(t, m, y, y - 1);
+    }
   }
   __device__ __forceinline__ void add_offset(int ot, int m, int y) {
     if (n_offs >= EG_MAX_OFFSETS) { flags |= EG_FLAG_OFFSET_OVERFLOW; return; }
     if (lane == 0) OFFS()[n_offs] = (uint16_t)(ot | (m << 2) | (y << 4));
     n_offs++;
     __syncwarp();
-    const double maturity = __ldg(&T->natural_offset[ot]) ? __ldg(&T->maturity[0]) : 1.0;
-    off_amount += __ldg(&T->off_amount[ot]) * maturity;
-    ocost += off_cost(ot, m, y);
-    if (y > 0 && lane == 0) VARS()[kVOcostPrev] += off_cost(ot, m, y - 1);
+    if (folded) {  // keep this year's folded sums current
+      const double maturity = __ldg(&T->natural_offset[ot]) ? __ldg(&T->maturity[0]) : 1.0;
+      off_amount += __ldg(&T->off_amount[ot]) * maturity;
+      ocost += off_cost(ot, m, y);
+      if (y > 0 && lane == 0) VARS()[kVOcostPrev] += off_cost(ot, m, y - 1);
+    }
   }
 
   // ---- episode-local learning (the deficit handler edits this year's rows of its private weights) ----------
@@ -687,9 +700,16 @@ struct Warp {
 
     for (int y = 0; y < EG_NY; y++) {
       year_start(y);
-      if (!REPLAY) load_rows(y);
-      State cur = state(y);                                  // state of the map after the latest change
-      bool deficit_mode = cur.balance < 0.0;                 // simulation.rs:137
+      bool deficit_mode = ((gen0 + gen1 + gen2) - __ldg(&T->year[y].usage_total)) < 0.0;  // simulation.rs:137
+      folded = deficit_mode || p.yearly != nullptr || y == EG_NY - 1;
+      State cur;                                             // state of the map after the latest change (deficit years)
+      cur.net = cur.opinion = cur.cost = 0.0;
+      cur.balance = 0.0;
+      if (folded) {
+        year_folds(y);
+        cur = state(y);
+      }
+      if (!REPLAY) load_rows(y);  // after the folds: both stage data in the scratch area
       if (deficit_mode && lane == 0) {                       // initial state of handle_power_deficit, simulation.rs:341-356
         vars[kVInitNet] = cur.net; vars[kVInitOpinion] = cur.opinion; vars[kVInitBalance] = cur.balance; vars[kVInitCost] = cur.cost;
       }
