@@ -36,6 +36,14 @@ extern __shared__ __align__(16) unsigned char smem[];  // dynamic shared memory 
 namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
+
+// -DEG_DEBUG_BOUNDS: index checks on the shared-memory structures; a violation sets bit 30 of eg_result.flags, which makes
+// every parity test fail (compute-sanitizer is not available on the GPU pool). Compiled out otherwise.
+#ifdef EG_DEBUG_BOUNDS
+#define EG_CHECK(cond) do { if (!(cond)) flags |= 0x40000000u; } while (0)
+#else
+#define EG_CHECK(cond) do { } while (0)
+#endif
 constexpr int kBattery100 = 3 * 12;   // AddGenerator(BatteryStorage, 100 %), simulation.rs:376
 constexpr int kGasPeaker100 = 3 * 8;  // sampling fallbacks, sampling.rs:185,237,321,377
 constexpr double kMinWeight = 0.0001, kMaxWeight = 0.999;   // ai/learning/constants.rs:14-15
@@ -293,6 +301,7 @@ struct Warp {
       if (i < n_gens) {
         const uint32_t xy = GXY()[i], at = GAT()[i];
         const int gj = xy & 0xFF, gi = xy >> 8, t = at & 0xF, m = (at >> 4) & 0x3, b = at >> 6;
+        EG_CHECK(t < EG_NT && m < EG_N_MULTS && b <= y && gi < n && gj < n);
         const double2 pt = plant_terms(t, m, b, y);
         scr[lane] = make_double2(gen_opinion(gi * n + gj, t, y, pt.x), pt.y);
       }
@@ -312,6 +321,7 @@ struct Warp {
       if (i < n_offs) {
         const uint32_t o = OFFS()[i];
         const int ot = o & 3, m = (o >> 2) & 3, b = (o >> 4) & 0x1F;
+        EG_CHECK(b <= y && y - b < EG_NY);
         const double maturity = __ldg(&T->natural_offset[ot]) ? __ldg(&T->maturity[y - b]) : 1.0;
         scr[lane] = make_double2(__ldg(&T->off_amount[ot]) * maturity, off_cost(ot, m, y));
       }
@@ -339,8 +349,10 @@ struct Warp {
 
   // MetalLocationSearch::find_suitable_location (CPU branch) as a 32-wide walk down the pre-sorted site list.
   __device__ __forceinline__ int place(int t, int y) {
+    EG_CHECK(t >= 0 && t < EG_NT);
     const int pc = __ldg(&T->pclass[t]);
     const int rc = __ldg(&T->rclass_of_pclass[pc]);
+    EG_CHECK(pc < EG_N_PCLASS && rc < EG_N_RCLASS);
     const bool water = __ldg(&T->water_of_pclass[pc]) != 0;
     const int ns = p.map.n_sites, n = p.map.grid_n;
     const int r2lim = __ldg(&p.map.r2_limit[rc]);  // cell offsets with d2 < r2lim are inside the penalty radius
@@ -382,6 +394,7 @@ struct Warp {
       bool inr = false;
       int d2n = 0;
       if (live) {
+        EG_CHECK((packed >> 8) < n && (packed & 0xFF) < n && (packed >> 8) * nstride + (packed & 0xFF) < n * nstride);
         d2n = nearest[(packed >> 8) * nstride + (packed & 0xFF)];
         inr = d2n < r2lim;
       }
@@ -422,6 +435,7 @@ struct Warp {
           for (uint32_t g = 0; g < n_gens; g++) {
             const uint32_t v = (spo - gxy[g]) ^ 0x8080u;
             const int d2 = __dp4a((int)v, (int)v, 0);
+            EG_CHECK(d2 >= 0 && d2 <= 2 * 127 * 127);
             if (cand && d2 < r2lim) sc *= lds_f64(nf_s + 8u * (uint32_t)d2);  // score *= distance / penalty_radius
           }
         } else {
@@ -453,6 +467,7 @@ struct Warp {
     if (n_gens >= EG_MAX_NEW_GENERATORS) { flags |= EG_FLAG_GEN_OVERFLOW; return; }
     const int n = p.map.grid_n;
     const int gi = site / n, gj = site - gi * n;
+    EG_CHECK(gi >= 0 && gi < n && gj >= 0 && gj < n && n_gens < EG_MAX_NEW_GENERATORS && t < EG_NT && m < EG_N_MULTS && y < EG_NY);
     if (lane == 0) { GXY()[n_gens] = (uint16_t)((gi << 8) | gj); GAT()[n_gens] = (uint16_t)pack_attr(t, m, y); }
     n_gens++;
     // nearest-plant map: squared cell distance to the closest plant built in this episode. One 32-bit word (4 or 2
@@ -468,6 +483,7 @@ struct Warp {
       for (int it = lane; it < items; it += 32) {
         const int i = gi - R + (it >> wl), jw = w0 + (it & ((1 << wl) - 1));
         if (i >= 0 && i < n && jw >= 0 && jw < nstride_w) {
+          EG_CHECK(i * nstride_w + jw < n * nstride_w && it < ((4 / (int)sizeof(NearT)) * rows << wl));
           uint32_t* cell = near_w + i * nstride_w + jw;
           const uint32_t pw = __ldg(&pat[it]);
           *cell = sizeof(NearT) == 1 ? __vminu4(*cell, pw) : __vminu2(*cell, pw);
