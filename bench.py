@@ -158,6 +158,14 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly one JSON line: libraries that print to fd 1 (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     import torch
     import torch.distributed as dist
     from eirgrid_b200 import trainer as T
@@ -312,7 +320,7 @@ def main():
                                 "sample": "%d episodes in %.1f s, oracle in reference-cost mode (literal 100x100 placement scan, per-evaluation opinion sums), %d threads"
                                           % (n_cpu, dt, threads),
                                 "fast_mode": {"value": rate_fast, "sample": "%d episodes in %.1f s with the exact table restructurings" % (n_fast, dt_fast)}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
