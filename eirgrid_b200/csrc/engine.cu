@@ -46,6 +46,8 @@ struct eg_ctx {
   EgSmallTables* d_small = nullptr;
   double* d_plant_terms = nullptr;
   uint32_t* d_stamp = nullptr;
+  double* d_near_q = nullptr;
+  int* d_q_limit = nullptr;
   double* d_site_opinion = nullptr;
   double* d_coast = nullptr;
   double* d_prefix = nullptr;          // [6][26][ns]
@@ -83,11 +85,11 @@ struct eg_ctx {
 namespace {
 
 void free_map(eg_ctx* c) {
-  void* ptrs[] = {c->d_small, c->d_plant_terms, c->d_stamp, c->d_site_opinion, c->d_coast, c->d_prefix, c->d_static_unsorted, c->d_order,
+  void* ptrs[] = {c->d_small, c->d_plant_terms, c->d_stamp, c->d_near_q, c->d_q_limit, c->d_site_opinion, c->d_coast, c->d_prefix, c->d_static_unsorted, c->d_order,
                   c->d_static_sorted, c->d_prefix_sorted, c->d_walk, c->d_near, c->d_r2_limit, c->d_sx, c->d_sy, c->d_ex, c->d_ey, c->d_cx, c->d_cy, c->d_pop};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  c->d_small = nullptr; c->d_plant_terms = nullptr; c->d_stamp = nullptr; c->d_site_opinion = nullptr; c->d_coast = nullptr; c->d_prefix = nullptr;
+  c->d_small = nullptr; c->d_plant_terms = nullptr; c->d_stamp = nullptr; c->d_near_q = nullptr; c->d_q_limit = nullptr; c->d_site_opinion = nullptr; c->d_coast = nullptr; c->d_prefix = nullptr;
   c->d_static_unsorted = nullptr; c->d_order = nullptr; c->d_static_sorted = nullptr; c->d_prefix_sorted = nullptr; c->d_walk = nullptr;
   c->d_near = nullptr; c->d_r2_limit = nullptr; c->d_sx = c->d_sy = c->d_ex = c->d_ey = c->d_cx = c->d_cy = nullptr; c->d_pop = nullptr;
   c->map_ready = false;
@@ -112,6 +114,8 @@ int build_device_map(eg_ctx* c) {
   if ((rc = upload(&c->d_small, &c->htab.small, 1, s))) return rc;
   if ((rc = upload(&c->d_plant_terms, c->htab.plant_terms.data(), c->htab.plant_terms.size(), s))) return rc;
   if ((rc = upload(&c->d_stamp, c->htab.stamp.data(), c->htab.stamp.size(), s))) return rc;
+  if ((rc = upload(&c->d_near_q, c->htab.near_factor_q.data(), c->htab.near_factor_q.size(), s))) return rc;
+  if ((rc = upload(&c->d_q_limit, c->htab.q_limit, (size_t)EG_N_RCLASS, s))) return rc;
   if ((rc = upload(&c->d_near, c->htab.near_factor.data(), c->htab.near_factor.size(), s))) return rc;
   if ((rc = upload(&c->d_r2_limit, c->htab.r2_limit, (size_t)(2 * EG_N_RCLASS + 1), s))) return rc;
   if ((rc = upload(&c->d_sx, m.sx.data(), m.sx.size(), s))) return rc;
@@ -149,6 +153,9 @@ int build_device_map(eg_ctx* c) {
   c->dmap.stamp_w_log2 = c->htab.stamp_w_log2;
   c->dmap.near_stride = c->htab.near_stride;
   c->dmap.near_wide = c->htab.near_wide;
+  c->dmap.near_shift = c->htab.near_shift;
+  c->dmap.near_factor_q = c->d_near_q;
+  c->dmap.q_limit = c->d_q_limit;
   c->dmap.site_opinion = c->d_site_opinion;
   c->dmap.coast_factor = c->d_coast;
   c->dmap.order = c->d_order;

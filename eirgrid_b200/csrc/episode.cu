@@ -189,7 +189,7 @@ __device__ __forceinline__ int deficit_key_action(int k) {
   return 3 * (int)((0xED325A4109BC78ull >> (4 * k)) & 0xF);
 }
 
-template <bool REPLAY, typename NearT>
+template <bool REPLAY, bool WIDE>
 struct Warp {
   const EgEpisodeParams& p;
   const EgSmallTables* __restrict__ T;
@@ -226,9 +226,8 @@ struct Warp {
   __device__ __forceinline__ uint16_t* YSITES() const { return (uint16_t*)(smem + sb + kOffYearSites); }
   __device__ __forceinline__ uint8_t* YACT() const { return smem + sb + kOffYearActions; }
   __device__ __forceinline__ uint8_t* COUNTS() const { return smem + sb + kOffCounts; }
-  __device__ __forceinline__ NearT* NEAR() const { return (NearT*)(smem + sb + kOffNear); }
+  __device__ __forceinline__ uint8_t* NEAR() const { return smem + sb + kOffNear; }
 
-  static constexpr NearT kFar = (NearT)~(NearT)0;
 
   // ---- random draws ---------------------------------------------------------------------------------------
   __device__ __forceinline__ unsigned long long u64() {
@@ -365,7 +364,8 @@ struct Warp {
     const uint32_t nf_s = opaque((uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)__ldg(&p.map.r2_limit[EG_N_RCLASS + rc]) * 8u);
     const int nstride = p.map.near_stride;
     const double size_factor = __ldg(&T->size_factor);
-    const NearT* nearest = NEAR();
+    const uint8_t* nearest = NEAR();
+    const int inr_lim = WIDE ? __ldg(&p.map.q_limit[rc]) : r2lim;  // cell values below it may have a plant in range
     const uint16_t* gxy = GXY();
     double best_score = 0.0;
     int best_site = -1;
@@ -396,7 +396,7 @@ struct Warp {
       if (live) {
         EG_CHECK((packed >> 8) < n && (packed & 0xFF) < n && (packed >> 8) * nstride + (packed & 0xFF) < n * nstride);
         d2n = nearest[(packed >> 8) * nstride + (packed & 0xFF)];
-        inr = d2n < r2lim;
+        inr = d2n < inr_lim;
       }
       // sites out of range of every new plant keep their static score; in list order the first one is the best of them
       // (descending scores, equal scores in scan order)
@@ -412,7 +412,7 @@ struct Warp {
       // nearest plant's factor alone bounds the true score from above
       bool cand = false;
       if (inr) {
-        double bound = pre * (sizeof(NearT) == 1 ? lds_f64(nf_s + 8u * (uint32_t)d2n) : __ldg(&nf[d2n]));
+        double bound = pre * (WIDE ? __ldg(&p.map.near_factor_q[rc * 256 + d2n]) : lds_f64(nf_s + 8u * (uint32_t)d2n));
         if (water) bound *= __ldg(&p.map.coast_factor[site]);
         bound *= size_factor;
         cand = bound > 0.0 && !(bound < best_score);
@@ -429,7 +429,7 @@ struct Warp {
 #endif
         // survivors multiply their factors in plant order (== multiplication order of the reference), one site per lane
         double sc = pre;
-        if (sizeof(NearT) == 1) {
+        if (!WIDE) {
           // coordinates < 128: both byte differences at once, no borrow between the bytes, then di*di + dj*dj by IDP.4A
           const uint32_t spo = (uint32_t)packed | 0x8080u;
           for (uint32_t g = 0; g < n_gens; g++) {
@@ -473,7 +473,7 @@ struct Warp {
     // nearest-plant map: squared cell distance to the closest plant built in this episode. One 32-bit word (4 or 2
     // cells) per lane: packed minimum of the map word and the host-built pattern word for this column alignment.
     {
-      constexpr int cpw = 4 / (int)sizeof(NearT);
+      constexpr int cpw = 4;
       const int R = p.map.kmax - 1, rows = 2 * R + 1, wl = p.map.stamp_w_log2, nstride_w = p.map.near_stride / cpw;
       const int a = gj % cpw;
       const int w0 = (gj - a - (R + cpw - 1) / cpw * cpw) / cpw;  // first word column of the pattern (may be negative)
@@ -483,10 +483,10 @@ struct Warp {
       for (int it = lane; it < items; it += 32) {
         const int i = gi - R + (it >> wl), jw = w0 + (it & ((1 << wl) - 1));
         if (i >= 0 && i < n && jw >= 0 && jw < nstride_w) {
-          EG_CHECK(i * nstride_w + jw < n * nstride_w && it < ((4 / (int)sizeof(NearT)) * rows << wl));
+          EG_CHECK(i * nstride_w + jw < n * nstride_w && it < (4 * rows << wl));
           uint32_t* cell = near_w + i * nstride_w + jw;
           const uint32_t pw = __ldg(&pat[it]);
-          *cell = sizeof(NearT) == 1 ? __vminu4(*cell, pw) : __vminu2(*cell, pw);
+          *cell = __vminu4(*cell, pw);
         }
       }
     }
@@ -701,7 +701,7 @@ struct Warp {
     {
       // clear the nearest-plant map, 4 bytes per lane and step (n_sites entries, padded to 16 bytes by the launcher)
       uint32_t* nw = (uint32_t*)(smem + sb + kOffNear);
-      const int words = (p.map.grid_n * p.map.near_stride * (int)sizeof(NearT) + 3) / 4;
+      const int words = (p.map.grid_n * p.map.near_stride + 3) / 4;
 #pragma unroll 2
       for (int i = lane; i < words; i += 32) nw[i] = 0xFFFFFFFFu;
     }
@@ -936,10 +936,10 @@ struct Warp {
   }
 };
 
-template <bool REPLAY, typename NearT>
+template <bool REPLAY, bool WIDE>
 __global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) eg_episode_kernel(const __grid_constant__ EgEpisodeParams p, int slice_bytes, int table_bytes) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (sizeof(NearT) == 1) {  // block-shared copy of the distance/radius factors at the start of the shared memory
+  if (!WIDE) {  // block-shared copy of the distance/radius factors at the start of the shared memory
     double* nf_s = (double*)smem;  // compact: class rc holds its r2_limit[rc] entries from offset r2_limit[6 + rc]
     for (int rc = 0; rc < EG_N_RCLASS; rc++) {
       const int cnt = __ldg(&p.map.r2_limit[rc]), off = __ldg(&p.map.r2_limit[EG_N_RCLASS + rc]);
@@ -947,7 +947,7 @@ __global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) 
     }
     __syncthreads();
   }
-  Warp<REPLAY, NearT> w(p, opaque((uint32_t)(table_bytes + warp * slice_bytes)), lane);
+  Warp<REPLAY, WIDE> w(p, opaque((uint32_t)(table_bytes + warp * slice_bytes)), lane);
   // persistent warps: every warp fetches the next unclaimed episode of the batch until none is left, so a short
   // episode never leaves its warp idle while the block's longest one finishes
   for (;;) {
@@ -959,10 +959,10 @@ __global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) 
   }
 }
 
-template <bool REPLAY, typename NearT>
+template <bool REPLAY, bool WIDE>
 cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
-  const bool wide = sizeof(NearT) == 2;
-  const int near_bytes = p.map.grid_n * p.map.near_stride * (int)sizeof(NearT);
+  const bool wide = WIDE;
+  const int near_bytes = p.map.grid_n * p.map.near_stride;
   const int slice = (kOffNear + near_bytes + 15) & ~15;
   const int shared_tab = wide ? 0 : (p.nf_entries * (int)sizeof(double) + 15) & ~15;
   // as many warps per block as keep several blocks resident in the 227 KB of an SM
@@ -970,30 +970,30 @@ cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
   while (warps > 1 && warps * slice + shared_tab > 100 * 1024) warps >>= 1;
   const size_t smem_bytes = (size_t)warps * slice + shared_tab;
   if (smem_bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
-  cudaError_t err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, NearT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  cudaError_t err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (err != cudaSuccess) return err;
   // shared-memory carveout: room for as many blocks as the register budget allows, the rest stays L1
   const int resident_want = (int)std::min<size_t>(EG_EPISODE_MIN_BLOCKS * (EG_EPISODE_WARPS / warps), (227 * 1024) / (smem_bytes + 1024));
   const int carveout = std::min(100, (int)((resident_want * (smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
-  cudaFuncSetAttribute(eg_episode_kernel<REPLAY, NearT>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+  cudaFuncSetAttribute(eg_episode_kernel<REPLAY, WIDE>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
   // grid = every block the device can hold at once (a multiple of the SM count), never more warps than episodes
   int dev = 0, sms = 0, per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eg_episode_kernel<REPLAY, NearT>, 32 * warps, smem_bytes);
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eg_episode_kernel<REPLAY, WIDE>, 32 * warps, smem_bytes);
   if (err != cudaSuccess) return err;
   if (per_sm < 1) return cudaErrorInvalidConfiguration;
   const uint32_t blocks = std::min<uint32_t>((uint32_t)(sms * per_sm), (p.n + warps - 1) / warps);
   err = cudaMemsetAsync(p.next_episode, 0, sizeof(uint32_t), stream);
   if (err != cudaSuccess) return err;
-  eg_episode_kernel<REPLAY, NearT><<<blocks, 32 * warps, smem_bytes, stream>>>(p, slice, shared_tab);
+  eg_episode_kernel<REPLAY, WIDE><<<blocks, 32 * warps, smem_bytes, stream>>>(p, slice, shared_tab);
   return cudaGetLastError();
 }
 
 template <bool REPLAY>
 cudaError_t launch(const EgEpisodeParams& p, cudaStream_t stream) {
   if (p.n == 0) return cudaSuccess;
-  return p.map.near_wide ? launch_as<REPLAY, uint16_t>(p, stream) : launch_as<REPLAY, uint8_t>(p, stream);
+  return p.map.near_wide ? launch_as<REPLAY, true>(p, stream) : launch_as<REPLAY, false>(p, stream);
 }
 
 }  // namespace

@@ -392,7 +392,18 @@ void eg_host_build_tables(const EgHostMap& m, EgHostTables* out) {
   // ---- stamp pattern of the nearest-plant map (episode.cu add_generator)
   // squared cell distances do not fit a byte, or site coordinates do not fit 7 bits (packed byte arithmetic in place())
   out->near_wide = (stride > 255 || m.grid_n > 128) ? 1 : 0;
-  const int cpw = out->near_wide ? 2 : 4;                     // cells per 32-bit word
+  const int cpw = 4;                                          // cells per 32-bit word (uint8 cells)
+  out->near_shift = 0;
+  while (((stride - 1) >> out->near_shift) > 254) out->near_shift++;  // quantisation of the cell value on wide maps
+  const int qs = out->near_shift;
+  out->near_factor_q.assign((size_t)EG_N_RCLASS * 256, 1.0);
+  for (int rc = 0; rc < EG_N_RCLASS; rc++) {
+    out->q_limit[rc] = (out->r2_limit[rc] + (1 << qs) - 1) >> qs;
+    for (int q = 0; q < 256; q++) {
+      const long d2_up = ((long)q << qs) + (1 << qs) - 1;  // the largest squared distance a cell value q can stand for
+      if (d2_up < out->r2_limit[rc]) out->near_factor_q[(size_t)rc * 256 + q] = out->near_factor[(size_t)rc * stride + d2_up];
+    }
+  }
   const int R = kmax - 1, rows = 2 * R + 1;
   const int Rp = (R + cpw - 1) / cpw * cpw;                   // pattern starts at column gj - (gj mod cpw) - Rp: word aligned
   out->near_stride = (m.grid_n + cpw - 1) / cpw * cpw;
@@ -408,9 +419,8 @@ void eg_host_build_tables(const EgHostMap& m, EgHostTables* out) {
         for (int b = 0; b < cpw; b++) {
           const int di = r - R, dj = w * cpw + b - Rp - a;
           const long d2 = (long)di * di + (long)dj * dj;
-          const uint32_t far = out->near_wide ? 0xFFFFu : 0xFFu;
-          const uint32_t v = (std::abs(dj) <= R && d2 < stride) ? (uint32_t)d2 : far;  // only cells inside the largest radius matter
-          word |= v << (b * (32 / cpw));
+          const uint32_t v = (std::abs(dj) <= R && d2 < stride) ? (uint32_t)(d2 >> qs) : 0xFFu;  // only cells inside the largest radius matter
+          word |= v << (b * 8);
         }
         out->stamp[((size_t)a * rows + r) * Wp + w] = word;
       }

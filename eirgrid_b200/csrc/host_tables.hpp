@@ -28,6 +28,9 @@ struct EgHostTables {
   int stamp_w_log2 = 0;
   int near_stride = 0;
   int near_wide = 0;
+  int near_shift = 0;
+  std::vector<double> near_factor_q;  // [6][256]
+  int q_limit[EG_N_RCLASS] = {0};
 };
 
 int eg_host_map_load(EgHostMap* m, const char* settlements_json, const char* generators_csv, const char* coastline_json);

@@ -62,13 +62,14 @@ def main():
     cubin = [f for f in os.listdir(tmp) if f.startswith("episode")][0]
     sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
     # pick the function whose mangled name matches the kernel's template arguments
-    want_replay = "(bool)1" in kname
-    want_wide = "unsigned short" in kname
+    m_args = re.search(r"eg_episode_kernel<\(bool\)(\d), \(bool\)(\d)>|eg_episode_kernel<(\d), (\d)>", kname)
+    a_ = [g for g in m_args.groups() if g is not None] if m_args else ["0", "0"]
+    want_replay, want_wide = a_[0] == "1", a_[1] == "1"
     fn_ok, line, m = False, None, {}
     for l in sass.split("\n"):
         s = l.strip()
         if s.startswith(".text."):
-            fn_ok = ("eg_episode_kernel" in s) and (("ILb1" in s) == want_replay) and (("tE" in s.split("eg_episode_kernel")[1][:12]) == want_wide)
+            fn_ok = ("eg_episode_kernelILb%dELb%dEE" % (want_replay, want_wide)) in s
         mm = re.match(r'//## File "(.*)", line (\d+)', s)
         if mm:
             line = int(mm.group(2)) if mm.group(1).endswith("episode.cu") else -1

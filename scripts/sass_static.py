@@ -27,7 +27,7 @@ cnt, byfn, on, line = collections.Counter(), collections.Counter(), False, None
 for l in dis.split("\n"):
     s = l.strip()
     if s.startswith(".text."):
-        on = "eg_episode_kernelILb0EhEE" in s
+        on = "eg_episode_kernelILb0ELb0EE" in s
     m = re.match(r'//## File "([^"]+)", line (\d+)', s)
     if m:
         line = (os.path.basename(m.group(1)), int(m.group(2)))
