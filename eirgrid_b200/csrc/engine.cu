@@ -46,6 +46,7 @@ struct eg_ctx {
   EgSmallTables* d_small = nullptr;
   double* d_plant_terms = nullptr;
   uint32_t* d_stamp = nullptr;
+  uint16_t* d_stamp_pos = nullptr;
   double* d_near_q = nullptr;
   int* d_q_limit = nullptr;
   double* d_site_opinion = nullptr;
@@ -85,11 +86,11 @@ struct eg_ctx {
 namespace {
 
 void free_map(eg_ctx* c) {
-  void* ptrs[] = {c->d_small, c->d_plant_terms, c->d_stamp, c->d_near_q, c->d_q_limit, c->d_site_opinion, c->d_coast, c->d_prefix, c->d_static_unsorted, c->d_order,
+  void* ptrs[] = {c->d_small, c->d_plant_terms, c->d_stamp, c->d_stamp_pos, c->d_near_q, c->d_q_limit, c->d_site_opinion, c->d_coast, c->d_prefix, c->d_static_unsorted, c->d_order,
                   c->d_static_sorted, c->d_prefix_sorted, c->d_walk, c->d_near, c->d_r2_limit, c->d_sx, c->d_sy, c->d_ex, c->d_ey, c->d_cx, c->d_cy, c->d_pop};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  c->d_small = nullptr; c->d_plant_terms = nullptr; c->d_stamp = nullptr; c->d_near_q = nullptr; c->d_q_limit = nullptr; c->d_site_opinion = nullptr; c->d_coast = nullptr; c->d_prefix = nullptr;
+  c->d_small = nullptr; c->d_plant_terms = nullptr; c->d_stamp = nullptr; c->d_stamp_pos = nullptr; c->d_near_q = nullptr; c->d_q_limit = nullptr; c->d_site_opinion = nullptr; c->d_coast = nullptr; c->d_prefix = nullptr;
   c->d_static_unsorted = nullptr; c->d_order = nullptr; c->d_static_sorted = nullptr; c->d_prefix_sorted = nullptr; c->d_walk = nullptr;
   c->d_near = nullptr; c->d_r2_limit = nullptr; c->d_sx = c->d_sy = c->d_ex = c->d_ey = c->d_cx = c->d_cy = nullptr; c->d_pop = nullptr;
   c->map_ready = false;
@@ -114,6 +115,7 @@ int build_device_map(eg_ctx* c) {
   if ((rc = upload(&c->d_small, &c->htab.small, 1, s))) return rc;
   if ((rc = upload(&c->d_plant_terms, c->htab.plant_terms.data(), c->htab.plant_terms.size(), s))) return rc;
   if ((rc = upload(&c->d_stamp, c->htab.stamp.data(), c->htab.stamp.size(), s))) return rc;
+  if ((rc = upload(&c->d_stamp_pos, c->htab.stamp_pos.data(), c->htab.stamp_pos.size(), s))) return rc;
   if ((rc = upload(&c->d_near_q, c->htab.near_factor_q.data(), c->htab.near_factor_q.size(), s))) return rc;
   if ((rc = upload(&c->d_q_limit, c->htab.q_limit, (size_t)EG_N_RCLASS, s))) return rc;
   if ((rc = upload(&c->d_near, c->htab.near_factor.data(), c->htab.near_factor.size(), s))) return rc;
@@ -150,7 +152,8 @@ int build_device_map(eg_ctx* c) {
   c->dmap.small = c->d_small;
   c->dmap.plant_terms = c->d_plant_terms;
   c->dmap.stamp = c->d_stamp;
-  c->dmap.stamp_w_log2 = c->htab.stamp_w_log2;
+  c->dmap.stamp_pos = c->d_stamp_pos;
+  c->dmap.stamp_items = c->htab.stamp_items;
   c->dmap.near_stride = c->htab.near_stride;
   c->dmap.near_wide = c->htab.near_wide;
   c->dmap.near_shift = c->htab.near_shift;

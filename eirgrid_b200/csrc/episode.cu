@@ -474,18 +474,19 @@ struct Warp {
     // cells) per lane: packed minimum of the map word and the host-built pattern word for this column alignment.
     {
       constexpr int cpw = 4;
-      const int R = p.map.kmax - 1, rows = 2 * R + 1, wl = p.map.stamp_w_log2, nstride_w = p.map.near_stride / cpw;
+      const int R = p.map.kmax - 1, items = p.map.stamp_items, nstride_w = p.map.near_stride / cpw;
       const int a = gj % cpw;
       const int w0 = (gj - a - (R + cpw - 1) / cpw * cpw) / cpw;  // first word column of the pattern (may be negative)
-      const uint32_t* __restrict__ pat = p.map.stamp + (uint32_t)((a * rows) << wl);
+      const uint32_t* __restrict__ pat = p.map.stamp + (uint32_t)(a * items);
+      const uint16_t* __restrict__ pos = p.map.stamp_pos + (uint32_t)(a * items);
       uint32_t* near_w = (uint32_t*)(smem + sb + kOffNear);
-      const int items = rows << wl;
-      for (int it = lane; it < items; it += 32) {
-        const int i = gi - R + (it >> wl), jw = w0 + (it & ((1 << wl) - 1));
+      for (int it = lane; it < items; it += 32) {  // only the pattern words that touch the largest radius
+        const uint32_t ps = __ldg(&pos[it]);
+        const uint32_t pw = __ldg(&pat[it]);
+        const int i = gi - R + (int)(ps >> 8), jw = w0 + (int)(ps & 0xFF);
         if (i >= 0 && i < n && jw >= 0 && jw < nstride_w) {
-          EG_CHECK(i * nstride_w + jw < n * nstride_w && it < (4 * rows << wl));
+          EG_CHECK(i * nstride_w + jw < n * nstride_w);
           uint32_t* cell = near_w + i * nstride_w + jw;
-          const uint32_t pw = __ldg(&pat[it]);
           *cell = __vminu4(*cell, pw);
         }
       }

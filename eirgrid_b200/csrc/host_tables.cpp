@@ -408,21 +408,32 @@ void eg_host_build_tables(const EgHostMap& m, EgHostTables* out) {
   const int Rp = (R + cpw - 1) / cpw * cpw;                   // pattern starts at column gj - (gj mod cpw) - Rp: word aligned
   out->near_stride = (m.grid_n + cpw - 1) / cpw * cpw;
   const int words = (Rp + cpw - 1 + R + 1 + cpw - 1) / cpw;   // words covering columns up to gj + R
-  out->stamp_w_log2 = 0;
-  while ((1 << out->stamp_w_log2) < words) out->stamp_w_log2++;
-  const int Wp = 1 << out->stamp_w_log2;                      // padded row (padding = far: a no-op minimum)
-  out->stamp.assign((size_t)cpw * rows * Wp, 0xFFFFFFFFu);
+  std::vector<std::vector<uint32_t>> pw(cpw);
+  std::vector<std::vector<uint16_t>> pp(cpw);
   for (int a = 0; a < cpw; a++)
     for (int r = 0; r < rows; r++)
       for (int w = 0; w < words; w++) {
         uint32_t word = 0;
+        bool any = false;
         for (int b = 0; b < cpw; b++) {
           const int di = r - R, dj = w * cpw + b - Rp - a;
           const long d2 = (long)di * di + (long)dj * dj;
-          const uint32_t v = (std::abs(dj) <= R && d2 < stride) ? (uint32_t)(d2 >> qs) : 0xFFu;  // only cells inside the largest radius matter
-          word |= v << (b * 8);
+          const bool in = std::abs(dj) <= R && d2 < stride;  // only cells inside the largest radius matter
+          any = any || in;
+          word |= (in ? (uint32_t)(d2 >> qs) : 0xFFu) << (b * 8);
         }
-        out->stamp[((size_t)a * rows + r) * Wp + w] = word;
+        if (any) { pw[a].push_back(word); pp[a].push_back((uint16_t)((r << 8) | w)); }
       }
+  size_t items = 0;
+  for (int a = 0; a < cpw; a++) items = std::max(items, pw[a].size());
+  items = (items + 31) / 32 * 32;
+  out->stamp_items = (int)items;
+  out->stamp.assign((size_t)cpw * items, 0xFFFFFFFFu);   // padding: a minimum with 0xFF.. changes nothing
+  out->stamp_pos.assign((size_t)cpw * items, (uint16_t)((R << 8) | (Rp / cpw)));  // ... at the plant's own word
+  for (int a = 0; a < cpw; a++)
+    for (size_t k = 0; k < pw[a].size(); k++) {
+      out->stamp[(size_t)a * items + k] = pw[a][k];
+      out->stamp_pos[(size_t)a * items + k] = pp[a][k];
+    }
   (void)kRadius;
 }

@@ -25,7 +25,8 @@ struct EgHostTables {
   int r2_stride = 0;
   int kmax = 0;
   std::vector<uint32_t> stamp;       // [cells per word][2*(kmax-1)+1][stamp_w]
-  int stamp_w_log2 = 0;
+  std::vector<uint16_t> stamp_pos;   // [4][stamp_items]
+  int stamp_items = 0;
   int near_stride = 0;
   int near_wide = 0;
   int near_shift = 0;

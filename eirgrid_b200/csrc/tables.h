@@ -79,15 +79,16 @@ struct EgDeviceMap {      // device pointers + sizes, passed by value to the ker
   // nearest-plant map of an episode (shared memory): rows padded to near_stride cells (a multiple of 4) so that rows start
   // on 32-bit words; cells are uint8: the squared cell distance d2 to the nearest plant built in the episode, or, on maps
   // whose d2 exceeds 254 (near_wide), d2 >> near_shift. A new plant is stamped into it with packed minima (4 cells per
-  // word) against this pattern: [4 column alignments][2*(kmax-1)+1 rows][1 << stamp_w_log2 words].
+  // word) against a host-built pattern of the squared distances around a plant, one version per column alignment (stamp).
   // With quantised cells the map still decides exactly "no plant in range" ((q << shift) >= r2_limit) and gives an upper
   // bound of the nearest plant's factor: near_factor_q[rc][q] = factor at the largest d2 the cell can stand for (1.0 if
   // that is out of range); q_limit[rc] = first q that is certainly out of range.
   const double* near_factor_q;    // [6][256]
   const int* q_limit;             // [6]
   int near_shift;
-  const uint32_t* stamp;
-  int stamp_w_log2;               // pattern rows are padded to 1 << stamp_w_log2 words
+  const uint32_t* stamp;          // [4][stamp_items] pattern words that hold at least one cell inside the largest radius
+  const uint16_t* stamp_pos;      // [4][stamp_items] (row << 8) | word column of that pattern word
+  int stamp_items;                // per alignment, padded with no-op items (word 0xFFFFFFFF at position 0)
   int near_stride;
   int near_wide;
 };
