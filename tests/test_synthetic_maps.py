@@ -1,6 +1,6 @@
 """Synthetic maps (BASELINE config 4): generator determinism on the CPU, and GPU parity with the oracle on maps other
-than the shipped one — a coarse grid (narrow nearest-plant map, uint8), a fine grid (wide map, uint16: cell distances
-above 255) and the 10x scaled map itself. Same bar as test_gpu_parity.py: everything bit-exact, score within 1e-12.
+than the shipped one — a coarse grid (exact one-byte nearest-plant map), a fine grid (wide instantiation: cell distances
+above 254, quantised map) and the 10x scaled map itself. Same bar as test_gpu_parity.py: everything bit-exact, score within 1e-12.
 """
 import os
 
@@ -93,7 +93,7 @@ def test_odd_grid_narrow_map():
 
 @pytest.mark.gpu
 def test_fine_grid_wide_map():
-    # 500 m cells: 12 km = 24 cells, squared cell distances up to 575 -> uint16 map, 16-bit packed minima
+    # 500 m cells: 12 km = 24 cells, squared cell distances up to 575 -> quantised map (shift 2)
     _compare(_subset_map(40, 12, 101, 500, seed=9), 96, seed=13)
 
 
