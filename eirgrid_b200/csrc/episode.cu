@@ -70,7 +70,7 @@ constexpr int kOffNear = (kOffCounts + 2 * EG_NY + 15) & ~15;   // nearest-plant
 static_assert(kOffScratch % 16 == 0 && kOffVars % 8 == 0 && kOffGxy % 8 == 0 && kOffOffs % 4 == 0 && kOffYearSites % 4 == 0 && kOffYearActions % 4 == 0, "alignment");
 
 // slots of the per-warp scalar area: values every lane agrees on that are touched a few times per year
-enum { kVTotalCost = 0, kVTotalCredit, kVTotalSales, kVGcostPrev, kVOcostPrev, kVLwTotal, kVInitNet, kVInitOpinion, kVInitBalance, kVInitCost };
+enum { kVTotalCost = 0, kVTotalCredit, kVTotalSales, kVGcostPrev, kVOcostPrev, kVLwTotal, kVInitNet, kVInitOpinion, kVInitBalance, kVInitCost, kVScaledTotal };
 
 // ---- Philox4x32-10, counter = (episode lo, episode hi, draw, stream 0), key = seed ------------------------
 __device__ __noinline__ unsigned long long philox_u64(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2) {
@@ -661,11 +661,17 @@ struct Warp {
       // stagnation branch (sampling.rs:190-220): weights^power in stable descending order. The sorted row lives in the
       // scratch area: copied from the host-built snapshot row at the start of the year (load_rows), rebuilt on the
       // device after this episode edited the year's weights (sort_local).
-      if (rows_dirty && !sorted_valid) { sort_local(sb, sb + kOffRows + (uint32_t)(y & 1) * kRowBytes, lane, p.policy->stagnation_power); sorted_valid = true; }
       const double* scl = (const double*)(smem + sb + kOffScratch);
-      double total_scaled = 0.0;
-      #pragma unroll 4
-      for (int k = 0; k < EG_N_ACTIONS; k++) total_scaled += scl[k];
+      if (rows_dirty && !sorted_valid) {
+        sort_local(sb, sb + kOffRows + (uint32_t)(y & 1) * kRowBytes, lane, p.policy->stagnation_power);
+        sorted_valid = true;
+        double t = 0.0;  // left-to-right sum of the scaled row, once per edit of the row
+        #pragma unroll 4
+        for (int k = 0; k < EG_N_ACTIONS; k++) t += scl[k];
+        if (lane == 0) VARS()[kVScaledTotal] = t;
+        __syncwarp();
+      }
+      const double total_scaled = rows_dirty ? VARS()[kVScaledTotal] : __ldg(&p.policy->scaled_total[y]);
       double rv = f64() * total_scaled;
       #pragma unroll 4
       for (int k = 0; k < EG_N_ACTIONS; k++) {

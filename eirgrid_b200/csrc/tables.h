@@ -108,6 +108,7 @@ struct EgPolicyDevice {   // weights snapshot + the per-batch constants of updat
   double dw_total[EG_NY];         // sample_additional_actions compute them (sampling.rs:182,352-355,406)
   double cw_total[EG_NY];
   double scaled_sorted[EG_NY][EG_N_ACTIONS];  // weight^power in stable descending weight order
+  double scaled_total[EG_NY];     // their left-to-right sums (sampling.rs:199)
   uint32_t iwi;                   // iterations_without_improvement
   uint32_t has_count_weights;
   uint32_t noop_boost;            // learning.rs:82: best is net-zero but costs > 8 * MAX_ACCEPTABLE_COST

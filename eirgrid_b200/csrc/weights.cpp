@@ -382,6 +382,9 @@ void eg_weights_fill_policy(const eg_weights& W, EgPolicyDevice* out) {
         out->sorted_idx[y][k] = (uint8_t)idx[k];
         out->scaled_sorted[y][k] = std::pow(W.w[y][idx[k]], out->stagnation_power);
       }
+      double t = 0.0;
+      for (int k = 0; k < EG_N_ACTIONS; k++) t += out->scaled_sorted[y][k];
+      out->scaled_total[y] = t;
     }
   }
   out->iwi = W.iwi;
