@@ -63,6 +63,8 @@ struct eg_ctx {
   uint32_t* d_pop = nullptr;
   EgPolicyDevice* d_policy = nullptr;
   uint32_t* d_next_episode = nullptr;  // work counter of the persistent episode kernels
+  unsigned char* d_near_ws = nullptr;  // wide maps: nearest-plant maps of the resident warps
+  uint32_t near_ws_stride = 0, near_ws_slots = 0;
   // eg_train_batch_*: statistics table, shard best, winner record (device) and their pinned host mirrors
   int64_t* d_stats = nullptr;
   double* d_best_score = nullptr;
@@ -155,6 +157,14 @@ int build_device_map(eg_ctx* c) {
   c->dmap.stamp_pos = c->d_stamp_pos;
   c->dmap.stamp_items = c->htab.stamp_items;
   c->dmap.near_stride = c->htab.near_stride;
+  if (c->d_near_ws) { cudaFree(c->d_near_ws); c->d_near_ws = nullptr; c->near_ws_stride = c->near_ws_slots = 0; }
+  if (c->htab.near_wide) {
+    int sms = 0;
+    EG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    c->near_ws_stride = (uint32_t)((m.grid_n * c->htab.near_stride + 15) & ~15);
+    c->near_ws_slots = (uint32_t)sms * 32u;  // more than the register file lets be resident
+    EG_CUDA(cudaMalloc((void**)&c->d_near_ws, (size_t)c->near_ws_stride * c->near_ws_slots));
+  }
   c->dmap.near_wide = c->htab.near_wide;
   c->dmap.near_shift = c->htab.near_shift;
   c->dmap.near_factor_q = c->d_near_q;
@@ -230,6 +240,9 @@ EgEpisodeParams make_params(const eg_ctx* c, const eg_run_cfg* cfg, uint64_t see
   p.replay_best = cfg->replay_best;
   p.ln100 = std::log(50000000000.0 * 100.0 / 50000000000.0);
   p.next_episode = c->d_next_episode;
+  p.near_ws = c->d_near_ws;
+  p.near_ws_stride = c->near_ws_stride;
+  p.near_ws_slots = c->near_ws_slots;
   p.nf_entries = c->htab.r2_limit[2 * EG_N_RCLASS];
   return p;
 }
@@ -270,7 +283,7 @@ void eg_destroy(eg_ctx* c) {
   free_map(c);
   if (c->h_stats) cudaFreeHost(c->h_stats);
   if (c->h_record) cudaFreeHost(c->h_record);
-  void* ptrs[] = {c->d_policy, c->d_next_episode, c->d_stats, c->d_best_score, c->d_best_index, c->d_record, c->s_out, c->s_traj, c->s_traj_in, c->s_sites, c->s_yearly};
+  void* ptrs[] = {c->d_policy, c->d_near_ws, c->d_next_episode, c->d_stats, c->d_best_score, c->d_best_index, c->d_record, c->s_out, c->s_traj, c->s_traj_in, c->s_sites, c->s_yearly};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->own_stream) cudaStreamDestroy(c->stream);

@@ -226,7 +226,8 @@ struct Warp {
   __device__ __forceinline__ uint16_t* YSITES() const { return (uint16_t*)(smem + sb + kOffYearSites); }
   __device__ __forceinline__ uint8_t* YACT() const { return smem + sb + kOffYearActions; }
   __device__ __forceinline__ uint8_t* COUNTS() const { return smem + sb + kOffCounts; }
-  __device__ __forceinline__ uint8_t* NEAR() const { return smem + sb + kOffNear; }
+  uint8_t* near_g;            // wide maps: this warp's slot of the global workspace
+  __device__ __forceinline__ uint8_t* NEAR() const { return WIDE ? near_g : smem + sb + kOffNear; }
 
 
   // ---- random draws ---------------------------------------------------------------------------------------
@@ -479,7 +480,7 @@ struct Warp {
       const int w0 = (gj - a - (R + cpw - 1) / cpw * cpw) / cpw;  // first word column of the pattern (may be negative)
       const uint32_t* __restrict__ pat = p.map.stamp + (uint32_t)(a * items);
       const uint16_t* __restrict__ pos = p.map.stamp_pos + (uint32_t)(a * items);
-      uint32_t* near_w = (uint32_t*)(smem + sb + kOffNear);
+      uint32_t* near_w = (uint32_t*)NEAR();
       for (int it = lane; it < items; it += 32) {  // only the pattern words that touch the largest radius
         const uint32_t ps = __ldg(&pos[it]);
         const uint32_t pw = __ldg(&pat[it]);
@@ -707,10 +708,16 @@ struct Warp {
     gcost = 0.0; ocost = 0.0; gen0 = gen1 = gen2 = 0.0; co2 = 0.0;
     {
       // clear the nearest-plant map, 4 bytes per lane and step (n_sites entries, padded to 16 bytes by the launcher)
-      uint32_t* nw = (uint32_t*)(smem + sb + kOffNear);
-      const int words = (p.map.grid_n * p.map.near_stride + 3) / 4;
+      if (WIDE) {
+        uint4* nw = (uint4*)NEAR();
+        const int quads = (p.map.grid_n * p.map.near_stride + 15) / 16;
+        for (int i = lane; i < quads; i += 32) nw[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+      } else {
+        uint32_t* nw = (uint32_t*)NEAR();
+        const int words = (p.map.grid_n * p.map.near_stride + 3) / 4;
 #pragma unroll 2
-      for (int i = lane; i < words; i += 32) nw[i] = 0xFFFFFFFFu;
+        for (int i = lane; i < words; i += 32) nw[i] = 0xFFFFFFFFu;
+      }
     }
     __syncwarp();
     const eg_traj* in = REPLAY ? p.replay_in + ep : nullptr;
@@ -955,6 +962,7 @@ __global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) 
     __syncthreads();
   }
   Warp<REPLAY, WIDE> w(p, opaque((uint32_t)(table_bytes + warp * slice_bytes)), lane);
+  w.near_g = WIDE ? p.near_ws + (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * p.near_ws_stride : nullptr;
   // persistent warps: every warp fetches the next unclaimed episode of the batch until none is left, so a short
   // episode never leaves its warp idle while the block's longest one finishes
   for (;;) {
@@ -969,8 +977,9 @@ __global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) 
 template <bool REPLAY, bool WIDE>
 cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
   const bool wide = WIDE;
-  const int near_bytes = p.map.grid_n * p.map.near_stride;
+  const int near_bytes = wide ? 0 : p.map.grid_n * p.map.near_stride;  // wide maps keep it in the global workspace
   const int slice = (kOffNear + near_bytes + 15) & ~15;
+  if (wide && (!p.near_ws || p.near_ws_stride < (uint32_t)((p.map.grid_n * p.map.near_stride + 15) & ~15))) return cudaErrorInvalidValue;
   const int shared_tab = wide ? 0 : (p.nf_entries * (int)sizeof(double) + 15) & ~15;
   // as many warps per block as keep several blocks resident in the 227 KB of an SM
   int warps = EG_EPISODE_WARPS;
@@ -990,7 +999,9 @@ cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
   err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eg_episode_kernel<REPLAY, WIDE>, 32 * warps, smem_bytes);
   if (err != cudaSuccess) return err;
   if (per_sm < 1) return cudaErrorInvalidConfiguration;
-  const uint32_t blocks = std::min<uint32_t>((uint32_t)(sms * per_sm), (p.n + warps - 1) / warps);
+  uint32_t blocks = std::min<uint32_t>((uint32_t)(sms * per_sm), (p.n + warps - 1) / warps);
+  if (wide) blocks = std::min<uint32_t>(blocks, p.near_ws_slots / warps);  // one workspace slot per resident warp
+  if (blocks == 0) return cudaErrorInvalidConfiguration;
   err = cudaMemsetAsync(p.next_episode, 0, sizeof(uint32_t), stream);
   if (err != cudaSuccess) return err;
   eg_episode_kernel<REPLAY, WIDE><<<blocks, 32 * warps, smem_bytes, stream>>>(p, slice, shared_tab);
