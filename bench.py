@@ -134,8 +134,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "policy rollout + scoring + weight update on the Irish map (130 settlements, 59 plants), CPU oracle port of the reference loop",
-                       "episodes_per_step": per_step},
+            "config": {"workload": "policy rollout + scoring + batch weight-update statistics, %d episodes in flight per GPU "
+                                   "(BASELINE configs[2] batch shape), Irish map: 130 settlements, 59 existing plants, 2601 candidate sites" % args.episodes,
+                       "map": "ireland", "episodes_per_step": per_step,
+                       "reference_arm": "CPU oracle port of the reference loop (the Rust reference cannot be built here): literal 100x100 placement "
+                                        "scan, per-evaluation opinion sums, sequential per-episode weight update; each step is a bounded sample of the workload"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
