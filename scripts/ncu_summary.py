@@ -24,7 +24,13 @@ WANT = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "smsp__warps_eligible.avg.per_cycle_active",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed_op_shared_ld.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sass__inst_executed_local_loads",
-        "launch__shared_mem_per_block_dynamic", "sm__maximum_warps_per_active_cycle_pct", "launch__occupancy_limit_warps"]
+        "launch__shared_mem_per_block_dynamic", "sm__maximum_warps_per_active_cycle_pct", "launch__occupancy_limit_warps",
+        # throughput of the units the path actually leans on, as % of peak
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+        "lts__t_sectors.sum.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum.per_second", "l1tex__t_bytes.sum.per_second",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "derived__memory_l1_wavefronts_shared_excessive",
+        "sm__warps_active.avg.per_cycle_active", "achieved_occupancy", "sm__cycles_active.avg"]
 
 
 def ncu(args):
