@@ -287,6 +287,12 @@ def main():
             issue = {"warp_instructions_per_episode": ipe, "achieved_ginst_s": ipe * args.episodes / (rollout_ms / 1e3) / 1e9,
                      "peak_ginst_s": peak_issue / 1e9, "frac": ipe * args.episodes / (rollout_ms / 1e3) / peak_issue,
                      "source": "profiles/rollout_traffic.json (ncu smsp__inst_executed.sum) x live kernel time"}
+            # FP64 ceiling without FMA (the path is compiled --fmad=false), measured live; the kernel's share of it from ncu
+            import ctypes
+            peak64 = ctypes.c_double()
+            if T._lib.lib().eg_microbench_fp64(local, ctypes.byref(peak64)) == 0:
+                issue["fp64_peak_tflops_no_fma"] = peak64.value
+                issue["fp64_pipe_active_pct"] = prof.get("fp64_pipe_pct")
         except Exception:
             traffic, issue = None, None
     line = {

@@ -20,7 +20,7 @@ EXPORTS = [
     "eg_weights_set_table", "eg_weights_get_best", "eg_deficit_key_action", "eg_rollout_batch", "eg_weights_upload",
     "eg_rollout_batch_device", "eg_replay_batch", "eg_replay_batch_device", "eg_update", "eg_update_stats_device",
     "eg_update_apply_stats", "eg_location_analysis", "eg_update_stats_clear_device", "eg_update_pack_best_device",
-    "eg_export_best_run_csv", "eg_weights_history_append", "eg_train_batch_begin", "eg_train_batch_end", "eg_train_batch_results", "eg_update_combine_apply",
+    "eg_microbench_fp64", "eg_export_best_run_csv", "eg_weights_history_append", "eg_train_batch_begin", "eg_train_batch_end", "eg_train_batch_results", "eg_update_combine_apply",
 ]
 
 
@@ -77,6 +77,7 @@ def lib():
     L.eg_update_stats_clear_device.argtypes = [vp, vp]
     L.eg_update_pack_best_device.argtypes = [vp, vp, vp, u32, vp, vp, u64, vp]
     L.eg_weights_history_append.argtypes = [vp, u64, C.c_char_p]
+    L.eg_microbench_fp64.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.eg_export_best_run_csv.argtypes = [vp, vp, C.POINTER(_abi.RunCfg), C.c_char_p, C.c_char_p]
     L.eg_train_batch_begin.argtypes = [vp, vp, C.POINTER(_abi.RunCfg), u64, u64, u32]
     L.eg_train_batch_end.argtypes = [vp, vp, vp]

@@ -315,6 +315,10 @@ int eg_export_best_run_csv(eg_ctx* ctx, const eg_weights* w, const eg_run_cfg* c
 int eg_location_analysis(eg_ctx* ctx, int use_loaded_map, int32_t half_steps, double step,
                          double* scores_out, uint32_t first_point, uint32_t n_points);
 
+/* ---- measurement aid (not on the path): double-precision multiply+add issue rate of `device` in TFLOP/s WITHOUT fused
+ * multiply-add — the arithmetic ceiling of kernels compiled with --fmad=false like the episode kernel. */
+int eg_microbench_fp64(int device, double* tflops_out);
+
 #ifdef __cplusplus
 }
 #endif
