@@ -646,6 +646,17 @@ int eg_update_apply_stats(eg_weights* w, const int64_t* stats, uint64_t n_total,
         w->w[y][k] = v;
       }
     }
+    // randomisation branch of apply_contrast_learning (learning.rs:267-280): the reference perturbs every weight by
+    // U(0.75, 1.25) on each iteration once iterations_without_improvement > 1200; the batch rule does it once per batch.
+    // The stream is keyed by the iteration count, so every rank draws the same factors.
+    if (w->iwi > 1200) {
+      UpdateRng rng{0x41424745u, 0x21484354u, w->iteration_count, 0u};
+      for (int y = 0; y < EG_NY; y++)
+        for (int k = 0; k < EG_N_ACTIONS; k++) {
+          const double f = 1.0 + 0.25 * (rng.f64() * 2.0 - 1.0);
+          w->w[y][k] = std::min(std::max(w->w[y][k] * f, kMinWeight), kMaxWeight);
+        }
+    }
   }
   // best bookkeeping with the batch winner
   bool improved = false;
@@ -693,6 +704,14 @@ int eg_update_apply_stats(eg_weights* w, const int64_t* stats, uint64_t n_total,
           else if (hist[k] > 0) v = std::fmax(v * std::pow(penalty, (double)hist[k]), kMinWeight);
           w->dw[y][k] = v;
         }
+      }
+      if (w->iwi > 1200) {  // learning.rs:358-370, once per batch like above
+        UpdateRng rng{0x41424745u, 0x44484354u, w->iteration_count, 0u};
+        for (int y = 0; y < EG_NY; y++)
+          for (int k = 0; k < EG_N_DEFICIT_KEYS; k++) {
+            const double f = 1.0 + 0.25 * (rng.f64() * 2.0 - 1.0);
+            w->dw[y][k] = std::min(std::max(w->dw[y][k] * f, kMinWeight), kMaxWeight);
+          }
       }
     }
   }
