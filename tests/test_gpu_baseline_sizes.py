@@ -83,3 +83,26 @@ def test_config4_location_analysis_sharded_by_site(gpu_ctx):
         lo, hi = r * n // world, (r + 1) * n // world
         parts.append(gpu_ctx.location_analysis(True, first_point=lo, n_points=hi - lo))
     assert np.array_equal(np.concatenate(parts), full)
+
+
+def test_config0_reference_rule_training_run_equals_cpu_oracle(gpu_ctx, oracle_world):
+    """The reference's own loop shape end to end: 16 episodes per snapshot, per-episode update in order, last 10 % of the
+    iterations replaying the best strategy — on the GPU and on the CPU oracle from the same seed: identical weights."""
+    n_iter, chunk, seed = 480, 16, 20250101
+    final_full = n_iter * 10 // 100
+    ow, gw = O.Weights(), _lib.Weights()
+    done = 0
+    while done < n_iter:
+        replay = done >= n_iter - final_full and gw.has_best_actions()
+        assert replay == (done >= n_iter - final_full and bool(ow.best()[0]))
+        cfg = _abi.RunCfg(replay_best=int(replay))
+        eres, etraj, _, _ = oracle_world.rollout(ow, chunk, seed=seed, first_episode=done, cfg=cfg, want_sites=False, want_yearly=False)
+        res, traj, _, _ = gpu_ctx.rollout(gw, chunk, seed=seed, first_episode=done, cfg=cfg)
+        assert traj.tobytes() == etraj.tobytes()
+        ow.update(eres, etraj, replay=replay)
+        gw.update(res, traj, replay_best=replay)
+        done += chunk
+    assert bytes(ow.table()) == bytes(gw.table())
+    ho, nbo, bo, ndo, do_ = ow.best()
+    hg, nbg, bg, ndg, dg = gw.best()
+    assert ho and hg and np.array_equal(nbo, nbg) and np.array_equal(bo, bg) and np.array_equal(ndo, ndg) and np.array_equal(do_, dg)
