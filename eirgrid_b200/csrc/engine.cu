@@ -573,7 +573,7 @@ int eg_export_best_run_csv(eg_ctx* c, const eg_weights* w, const eg_run_cfg* cfg
     for (size_t i = 0; i < n; i++) traj.actions[y][i] = w->best_actions[y][i];
   }
   eg_result res;
-  static eg_yearly yearly;
+  eg_yearly yearly;
   eg_run_cfg rcfg = *cfg;
   rcfg.replay_best = 0;
   if ((rc = eg_replay_batch(c, &rcfg, &traj, 1, &res, nullptr, &yearly))) return rc;

@@ -248,7 +248,7 @@ eg_weights* load_initial_weights(const Args& a) {
 }
 
 double best_score_of(const eg_weights* w, bool* has_best) {
-  static eg_weights_table t;
+  eg_weights_table t;
   check(eg_weights_get_table(w, &t), "eg_weights_get_table");
   *has_best = t.has_best != 0;
   if (!t.has_best) return 0.0;
