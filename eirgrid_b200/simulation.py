@@ -162,6 +162,9 @@ def run_multi_simulation(asset_dir, num_iterations, parallel=True, continue_from
         trainer.cfg = _abi.RunCfg(cost_only=optimization_mode == "cost_only", enable_energy_sales=enable_energy_sales,
                                   enable_construction_delays=enable_construction_delays, replay_best=replay_best,
                                   same_stream_all_episodes=same_stream)
+        # never past the requested iteration count, nor past the start of the replay phase: the last batch is smaller
+        phase_end = num_iterations if (is_full_run or final_full >= num_iterations) else num_iterations - final_full
+        trainer.n = max(1, min(per_gpu, (phase_end - completed + world - 1) // world))
         if update_mode == "batch" and not replay_best:
             st = trainer.step()
         else:
@@ -174,7 +177,7 @@ def run_multi_simulation(asset_dir, num_iterations, parallel=True, continue_from
                 raise NotImplementedError("replay-best batches are single-GPU")
             st = weights.update(res, traj, replay_best=replay_best, rng_seed=rng_seed)
             trainer.next_episode += trainer.n
-        completed += per_gpu * world
+        completed += trainer.n * world
         if rank == 0:
             if time.time() - t_progress >= progress_interval:
                 t_progress = time.time()

@@ -154,8 +154,8 @@ class BatchTrainer:
         """Copy this rank's last batch to the host as structured arrays (results, trajectories)."""
         self.stream.synchronize()
         with _torch().cuda.stream(self.stream):
-            res = self.d_results.cpu().numpy().view(_abi.RESULT_DTYPE)
-            traj = self.d_traj.cpu().numpy().view(_abi.TRAJ_DTYPE)
+            res = self.d_results[:self.n * _abi.RESULT_DTYPE.itemsize].cpu().numpy().view(_abi.RESULT_DTYPE)
+            traj = self.d_traj[:self.n * _abi.TRAJ_DTYPE.itemsize].cpu().numpy().view(_abi.TRAJ_DTYPE)
         return res, traj
 
     def close(self):

@@ -323,25 +323,29 @@ int main(int argc, char** argv) {
     cfg.same_stream_all_episodes = same_stream;
     uint64_t done_now = 0;
     if (a.update_mode == "batch" && !cfg.replay_best) {
+      // never past the requested iteration count, nor past the start of the replay phase: the last batch is smaller
+      const uint64_t phase_end = (is_full_run || final_full >= a.iterations) ? a.iterations : a.iterations - final_full;
+      const uint32_t n_g = (uint32_t)std::min<uint64_t>(per_gpu, (phase_end - completed + G - 1) / G);
       for (size_t g = 0; g < G; g++)
-        check(eg_train_batch_begin(ctx[g], weights, &cfg, rng_seed, completed + g * per_gpu, per_gpu), "eg_train_batch_begin");
+        check(eg_train_batch_begin(ctx[g], weights, &cfg, rng_seed, completed + g * n_g, n_g), "eg_train_batch_begin");
       std::fill(stats.begin(), stats.end(), 0);
       for (size_t g = 0; g < G; g++) {
         check(eg_train_batch_end(ctx[g], shard_stats.data(), records.data() + g * EG_BEST_RECORD_BYTES), "eg_train_batch_end");
         for (size_t i = 0; i < stats.size(); i++) stats[i] += shard_stats[i];
       }
-      done_now = (uint64_t)per_gpu * G;
+      done_now = (uint64_t)n_g * G;
       check(eg_update_combine_apply(weights, stats.data(), records.data(), (uint32_t)G, done_now, completed, &st), "eg_update_combine_apply");
       t_train += now_s() - t_batch;
       n_train += done_now;
     } else {
       // replay batches and the sequential mode: every episode's record comes to the host and the reference's per-episode
       // update is applied in episode order (it rebuilds the doubled records of replay iterations, quirk Q10)
-      results.resize(per_gpu);
-      trajs.resize(per_gpu);
-      check(eg_rollout_batch(ctx[0], weights, &cfg, rng_seed, completed, per_gpu, results.data(), trajs.data(), nullptr, nullptr), "eg_rollout_batch");
-      check(eg_update(weights, results.data(), trajs.data(), per_gpu, cfg.replay_best, rng_seed, &st), "eg_update");
-      done_now = per_gpu;
+      const uint32_t n_s = (uint32_t)std::min<uint64_t>(per_gpu, a.iterations - completed);
+      results.resize(n_s);
+      trajs.resize(n_s);
+      check(eg_rollout_batch(ctx[0], weights, &cfg, rng_seed, completed, n_s, results.data(), trajs.data(), nullptr, nullptr), "eg_rollout_batch");
+      check(eg_update(weights, results.data(), trajs.data(), n_s, cfg.replay_best, rng_seed, &st), "eg_update");
+      done_now = n_s;
     }
     completed += done_now;
     const double t = now_s();

@@ -67,32 +67,40 @@ def test_host_run_checkpoint_and_resume(host_binary, tmp_path):
     assert r.returncode == 0, r.stderr
     s2 = json.loads(r.stdout.strip().split("\n")[-1])
     assert s2["start_iteration"] == 8192 and s2["iterations"] == 12288 and s2["run_dir"] != run1
+    # an iteration count that is no multiple of the batch size is honoured exactly (the last batches are smaller)
+    r = subprocess.run(cmd + ["-n", "5000", "--no-continue", "-c", str(tmp_path / "ck2")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    s3 = json.loads(r.stdout.strip().split("\n")[-1])
+    assert s3["iterations"] == 5000 and s3["training_batches"]["episodes"] == 4500
     assert s2["best_score"] >= s1["best_score"]
 
 
 @pytest.mark.gpu
-def test_host_batch_equals_python_trainer(host_binary, tmp_path):
-    """Same seed, same batches: the C++ driver's weights equal the Python BatchTrainer's bit for bit (both call the same
-    kernels and the same host update; this pins eg_train_batch_* + eg_update_combine_apply against the torch plumbing)."""
+def test_host_equals_python_driver(host_binary, tmp_path):
+    """Same arguments, same seed: the C++ driver and the Python driver (run_multi_simulation) end with bit-identical weights —
+    training batches through the device statistics path (eg_train_batch_* + eg_update_combine_apply vs the torch plumbing),
+    a shorter last training batch, then the replay phase through the sequential update."""
     import numpy as np
-    from eirgrid_b200 import trainer as T
-    ck = str(tmp_path / "ck")
+    from eirgrid_b200.simulation import run_multi_simulation
     cache = str(tmp_path / "cache")
     os.makedirs(cache)
     open(os.path.join(cache, "location_analysis.json"), "w").write("{}")
-    # 2 batches of 4096: 0 + 819 < 8192 and 4096 + 819 < 8192, so neither is a replay ("full run") batch
-    r = subprocess.run([host_binary, "--assets", ASSETS, "-c", ck, "-C", cache, "--batch-size", "4096", "--master-seed", "11",
-                        "-n", "8192", "--no-continue", "-i", "100000"], capture_output=True, text=True)
+    # 8192 iterations, batch 4096: training batches of 4096 and 3277 (up to iteration 7373), then 819 replay iterations
+    r = subprocess.run([host_binary, "--assets", ASSETS, "-c", str(tmp_path / "ck_host"), "-C", cache, "--batch-size", "4096",
+                        "--master-seed", "11", "-n", "8192", "--no-continue", "-i", "100000"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     s = json.loads(r.stdout.strip().split("\n")[-1])
-    tr = T.BatchTrainer(4096, seed=11, device=0, asset_dir=ASSETS)
-    for _ in range(2):
-        tr.step()
-    want = tr.weights.table()
-    tr.close()
-    got = _lib.Weights.load_from_file(os.path.join(s["run_dir"], "latest_weights.json")).table()
-    assert got.iteration_count == want.iteration_count == 8192
-    assert got.iterations_without_improvement == want.iterations_without_improvement
-    assert np.array_equal(np.ctypeslib.as_array(got.weights), np.ctypeslib.as_array(want.weights))
-    assert np.array_equal(np.ctypeslib.as_array(got.deficit_weights), np.ctypeslib.as_array(want.deficit_weights))
-    assert list(got.best_metrics) == list(want.best_metrics)
+    assert s["iterations"] == 8192 and s["training_batches"]["episodes"] == 7373
+    py = run_multi_simulation(ASSETS, 8192, continue_from_checkpoint=False, checkpoint_dir=str(tmp_path / "ck_py"), checkpoint_interval=100000,
+                              cache_dir=cache, batch_size=4096, master_seed=11, device=0, log=lambda *a: None)
+    assert py["iterations"] == 8192
+    got = _lib.Weights.load_from_file(os.path.join(s["run_dir"], "latest_weights.json"))
+    want = _lib.Weights.load_from_file(os.path.join(py["run_dir"], "latest_weights.json"))
+    tg, tw = got.table(), want.table()
+    assert tg.iteration_count == tw.iteration_count == 8192
+    assert tg.iterations_without_improvement == tw.iterations_without_improvement
+    assert np.array_equal(np.ctypeslib.as_array(tg.weights), np.ctypeslib.as_array(tw.weights))
+    assert np.array_equal(np.ctypeslib.as_array(tg.deficit_weights), np.ctypeslib.as_array(tw.deficit_weights))
+    assert list(tg.best_metrics) == list(tw.best_metrics)
+    bg, bw = got.best(), want.best()
+    assert all(np.array_equal(x, y) for x, y in zip(bg[1:], bw[1:]))
