@@ -104,3 +104,25 @@ def test_host_equals_python_driver(host_binary, tmp_path):
     assert list(tg.best_metrics) == list(tw.best_metrics)
     bg, bw = got.best(), want.best()
     assert all(np.array_equal(x, y) for x, y in zip(bg[1:], bw[1:]))
+
+
+@pytest.mark.gpu
+def test_host_two_gpus_equal_one_gpu(host_binary, tmp_path):
+    """Sharding a batch over GPUs changes nothing: --devices 0,1 with half the per-GPU batch ends with the weights of one GPU."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cache = str(tmp_path / "cache")
+    os.makedirs(cache)
+    open(os.path.join(cache, "location_analysis.json"), "w").write("{}")
+    out = []
+    for devs, batch, ck in (("0", "4096", "ck1"), ("0,1", "2048", "ck2")):
+        r = subprocess.run([host_binary, "--assets", ASSETS, "-c", str(tmp_path / ck), "-C", cache, "--batch-size", batch, "--master-seed", "3",
+                            "-n", "16384", "--no-continue", "-i", "100000", "--devices", devs], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        s = json.loads(r.stdout.strip().split("\n")[-1])
+        out.append(_lib.Weights.load_from_file(os.path.join(s["run_dir"], "latest_weights.json")).table())
+    assert np.array_equal(np.ctypeslib.as_array(out[0].weights), np.ctypeslib.as_array(out[1].weights))
+    assert np.array_equal(np.ctypeslib.as_array(out[0].deficit_weights), np.ctypeslib.as_array(out[1].deficit_weights))
+    assert list(out[0].best_metrics) == list(out[1].best_metrics)
