@@ -310,7 +310,9 @@ def main():
                    "rollout_kernel_ms": rollout_ms},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": POLICY_BYTES, "d2h_bytes_per_step": tr.d2h_bytes_per_step,
                 "what": "BatchTrainer.step(): weights H2D from the host, rollout + statistics + winner-record kernels, statistics and "
-                        "winner record D2H (pinned), host-side weight update applied",
+                        "winner record D2H (pinned), host-side weight update applied. The weights learn during these steps (stagnation-mode "
+                        "tables sample ~20 % more actions and plants per episode), so the rollout itself is slower here than in `value`, "
+                        "which is timed on the initial table",
                 "with_all_results_to_host": {"value": args.episodes * world * K / full_s, "unit": UNIT,
                                              "d2h_bytes_per_step": args.episodes * (RESULT_BYTES + TRAJ_BYTES)}},
         "gpu_launches": int(launches),
