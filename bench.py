@@ -254,6 +254,25 @@ def main():
             tr.stream.synchronize()
         barrier()
         full_s = time.perf_counter() - t0
+
+        # ---- the device-resident step again on the table the e2e steps have trained (what explains e2e vs value) ---------
+        KT = min(K, 20)
+        tr.upload_weights()
+        evt = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(KT)]
+        barrier()
+        for k in range(KT):
+            with torch.cuda.stream(tr.stream):
+                flush.zero_()
+            evt[k][0].record(tr.stream)
+            tr.launch_rollout(first_episode=((W + K + k) * world + rank + 1000) * args.episodes)
+            tr.launch_stats()
+            tr.reduce_stats()
+            evt[k][1].record(tr.stream)
+        barrier()
+        t = torch.tensor([sum(evt[k][0].elapsed_time(evt[k][1]) for k in range(KT))], dtype=torch.float64, device=tr.device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        value_trained = n_total * KT / (float(t.item()) / 1e3)
     clock_summary = clocks.summary()
 
     if rank != 0:
@@ -307,7 +326,8 @@ def main():
                    "map": args.workload,
                    "episodes_per_gpu": args.episodes, "l2": "256 MiB buffer written between timed steps (L2 flush)",
                    "timing": "CUDA events on the launching stream per step, max over ranks",
-                   "rollout_kernel_ms": rollout_ms},
+                   "rollout_kernel_ms": rollout_ms,
+                   "value_on_trained_table": value_trained},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": POLICY_BYTES, "d2h_bytes_per_step": tr.d2h_bytes_per_step,
                 "what": "BatchTrainer.step(): weights H2D from the host, rollout + statistics + winner-record kernels, statistics and "
                         "winner record D2H (pinned), host-side weight update applied. The weights learn during these steps (stagnation-mode "
