@@ -20,7 +20,7 @@ EXPORTS = [
     "eg_weights_set_table", "eg_weights_get_best", "eg_deficit_key_action", "eg_rollout_batch", "eg_weights_upload",
     "eg_rollout_batch_device", "eg_replay_batch", "eg_replay_batch_device", "eg_update", "eg_update_stats_device",
     "eg_update_apply_stats", "eg_location_analysis", "eg_update_stats_clear_device", "eg_update_pack_best_device",
-    "eg_microbench_fp64", "eg_export_best_run_csv", "eg_weights_history_append", "eg_train_batch_begin", "eg_train_batch_end", "eg_train_batch_results", "eg_update_combine_apply",
+    "eg_location_analysis_year", "eg_microbench_fp64", "eg_export_best_run_csv", "eg_weights_history_append", "eg_train_batch_begin", "eg_train_batch_end", "eg_train_batch_results", "eg_update_combine_apply",
 ]
 
 
@@ -85,6 +85,7 @@ def lib():
     L.eg_update_combine_apply.argtypes = [vp, vp, vp, u32, u64, u64, C.POINTER(_abi.UpdateStats)]
     L.eg_update_apply_stats.argtypes = [vp, vp, u64, vp, vp, i64, C.POINTER(_abi.UpdateStats)]
     L.eg_location_analysis.argtypes = [vp, C.c_int, C.c_int32, C.c_double, vp, u32, u32]
+    L.eg_location_analysis_year.argtypes = [vp, C.c_int, u32, C.c_int32, C.c_double, vp, u32, u32]
     _lib = L
     return L
 
@@ -301,11 +302,11 @@ class Context:
         check(self.L.eg_export_best_run_csv(self.h, weights.h, C.byref(cfg), os.fsencode(output_dir), buf))
         return buf.value.decode()
 
-    def location_analysis(self, use_loaded_map, half_steps=25, step=2000.0, first_point=0, n_points=None):
+    def location_analysis(self, use_loaded_map, half_steps=25, step=2000.0, first_point=0, n_points=None, year_index=0):
         side = 2 * half_steps + 1
         n = side * side - first_point if n_points is None else n_points
         out = np.zeros((n, _abi.N_GEN_TYPES))
-        check(self.L.eg_location_analysis(self.h, int(use_loaded_map), half_steps, step, _abi.ptr(out), first_point, n))
+        check(self.L.eg_location_analysis_year(self.h, int(use_loaded_map), int(year_index), half_steps, step, _abi.ptr(out), first_point, n))
         return out
 
     def sync(self):

@@ -667,7 +667,13 @@ int eg_export_best_run_csv(eg_ctx* c, const eg_weights* w, const eg_run_cfg* cfg
 
 int eg_location_analysis(eg_ctx* c, int use_loaded_map, int32_t half_steps, double step, double* scores_out,
                          uint32_t first_point, uint32_t n_points) {
+  return eg_location_analysis_year(c, use_loaded_map, 0, half_steps, step, scores_out, first_point, n_points);
+}
+
+int eg_location_analysis_year(eg_ctx* c, int use_loaded_map, uint32_t year_index, int32_t half_steps, double step, double* scores_out,
+                              uint32_t first_point, uint32_t n_points) {
   if (!c || !scores_out) return eg_fail(EG_ERR_INVALID, "eg_location_analysis: NULL argument");
+  if (year_index >= EG_NY) return eg_fail(EG_ERR_INVALID, "eg_location_analysis_year: year_index out of range");
   if (!c->map_ready) return eg_fail(EG_ERR_STATE, "no map loaded (the coastline polygon is needed)");
   if (half_steps < 0 || half_steps > 1000) return eg_fail(EG_ERR_INVALID, "half_steps out of range");
   const uint32_t side = (uint32_t)(2 * half_steps + 1);
@@ -678,7 +684,7 @@ int eg_location_analysis(eg_ctx* c, int use_loaded_map, int32_t half_steps, doub
   EgSuitabilityParams p{};
   p.half = half_steps; p.step = step; p.first = first_point; p.n = n_points;
   p.n_settlements = use_loaded_map ? (int)c->hmap.sx.size() : 0;
-  p.sx = c->d_sx; p.sy = c->d_sy; p.pop = c->d_pop;  // pop[0][s] = 2025 populations
+  p.sx = c->d_sx; p.sy = c->d_sy; p.pop = c->d_pop + (size_t)year_index * c->hmap.sx.size();  // pop[y][s]: populations of that year
   p.n_generators = use_loaded_map ? (int)c->hmap.ex.size() : 0;
   p.gx = c->d_ex; p.gy = c->d_ey;
   p.n_coast = (int)c->hmap.cx.size(); p.cx = c->d_cx; p.cy = c->d_cy;

@@ -314,6 +314,10 @@ int eg_export_best_run_csv(eg_ctx* ctx, const eg_weights* w, const eg_run_cfg* c
  * use_loaded_map = 0 reproduces the shipped cache (empty map), 1 uses the loaded settlements/plants. */
 int eg_location_analysis(eg_ctx* ctx, int use_loaded_map, int32_t half_steps, double step,
                          double* scores_out, uint32_t first_point, uint32_t n_points);
+/* The same with the settlement populations of simulated year 2025 + year_index (they grow 1 % a year and decide the urban
+ * test and the nearby-population rule): BASELINE configs[4] asks for all sites x 15 types x 26 years. year_index 0 == above. */
+int eg_location_analysis_year(eg_ctx* ctx, int use_loaded_map, uint32_t year_index, int32_t half_steps, double step,
+                              double* scores_out, uint32_t first_point, uint32_t n_points);
 
 /* ---- measurement aid (not on the path): double-precision multiply+add issue rate of `device` in TFLOP/s WITHOUT fused
  * multiply-add — the arithmetic ceiling of kernels compiled with --fmad=false like the episode kernel. */

@@ -106,3 +106,24 @@ def test_config0_reference_rule_training_run_equals_cpu_oracle(gpu_ctx, oracle_w
     ho, nbo, bo, ndo, do_ = ow.best()
     hg, nbg, bg, ndg, dg = gw.best()
     assert ho and hg and np.array_equal(nbo, nbg) and np.array_equal(bo, bg) and np.array_equal(ndo, ndg) and np.array_equal(do_, dg)
+
+
+def test_config4_location_analysis_all_26_years(gpu_ctx, oracle_world):
+    """All sites x 15 types x 26 years: year y uses the settlements' populations of that year (round-half-away growth of 1 %).
+    Checked against the oracle's analysis of a world whose settlements carry those populations."""
+    from eirgrid_b200 import synthetic
+    import os
+    assets = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ireland_map")
+    sx, sy, spop, ex, ey, et, ec, cx, cy = synthetic.load_ireland_arrays(assets)
+    base = gpu_ctx.location_analysis(True)
+    assert np.array_equal(gpu_ctx.location_analysis(True, year_index=0), base)
+    pop = spop.astype(np.float64)
+    changed = 0
+    for y in range(1, 26):
+        pop = np.floor(pop * 1.01 + 0.5)  # f64::round of positive values
+        if y in (1, 12, 25):
+            w = O.World.from_arrays(sx, sy, pop.astype(np.uint32), ex, ey, et, ec, cx, cy, 51, 1000.0, fast=False)
+            got = gpu_ctx.location_analysis(True, year_index=y)
+            assert np.array_equal(got, w.location_analysis(True)), y
+            changed += int((got != base).sum())
+    assert changed > 0, "population growth must move at least one urban / nearby-population decision by 2050"
