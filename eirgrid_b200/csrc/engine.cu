@@ -45,10 +45,6 @@ struct eg_ctx {
   // device memory
   EgSmallTables* d_small = nullptr;
   double* d_plant_terms = nullptr;
-  uint32_t* d_stamp = nullptr;
-  uint16_t* d_stamp_pos = nullptr;
-  double* d_near_q = nullptr;
-  int* d_q_limit = nullptr;
   double* d_site_opinion = nullptr;
   double* d_coast = nullptr;
   double* d_prefix = nullptr;          // [6][26][ns]
@@ -63,8 +59,6 @@ struct eg_ctx {
   uint32_t* d_pop = nullptr;
   EgPolicyDevice* d_policy = nullptr;
   uint32_t* d_next_episode = nullptr;  // work counter of the persistent episode kernels
-  unsigned char* d_near_ws = nullptr;  // wide maps: nearest-plant maps of the resident warps
-  uint32_t near_ws_stride = 0, near_ws_slots = 0;
   // eg_train_batch_*: statistics table, shard best, winner record (device) and their pinned host mirrors
   int64_t* d_stats = nullptr;
   double* d_best_score = nullptr;
@@ -88,11 +82,11 @@ struct eg_ctx {
 namespace {
 
 void free_map(eg_ctx* c) {
-  void* ptrs[] = {c->d_small, c->d_plant_terms, c->d_stamp, c->d_stamp_pos, c->d_near_q, c->d_q_limit, c->d_site_opinion, c->d_coast, c->d_prefix, c->d_static_unsorted, c->d_order,
+  void* ptrs[] = {c->d_small, c->d_plant_terms, c->d_site_opinion, c->d_coast, c->d_prefix, c->d_static_unsorted, c->d_order,
                   c->d_static_sorted, c->d_prefix_sorted, c->d_walk, c->d_near, c->d_r2_limit, c->d_sx, c->d_sy, c->d_ex, c->d_ey, c->d_cx, c->d_cy, c->d_pop};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  c->d_small = nullptr; c->d_plant_terms = nullptr; c->d_stamp = nullptr; c->d_stamp_pos = nullptr; c->d_near_q = nullptr; c->d_q_limit = nullptr; c->d_site_opinion = nullptr; c->d_coast = nullptr; c->d_prefix = nullptr;
+  c->d_small = nullptr; c->d_plant_terms = nullptr; c->d_site_opinion = nullptr; c->d_coast = nullptr; c->d_prefix = nullptr;
   c->d_static_unsorted = nullptr; c->d_order = nullptr; c->d_static_sorted = nullptr; c->d_prefix_sorted = nullptr; c->d_walk = nullptr;
   c->d_near = nullptr; c->d_r2_limit = nullptr; c->d_sx = c->d_sy = c->d_ex = c->d_ey = c->d_cx = c->d_cy = nullptr; c->d_pop = nullptr;
   c->map_ready = false;
@@ -116,10 +110,6 @@ int build_device_map(eg_ctx* c) {
   cudaStream_t s = c->stream;
   if ((rc = upload(&c->d_small, &c->htab.small, 1, s))) return rc;
   if ((rc = upload(&c->d_plant_terms, c->htab.plant_terms.data(), c->htab.plant_terms.size(), s))) return rc;
-  if ((rc = upload(&c->d_stamp, c->htab.stamp.data(), c->htab.stamp.size(), s))) return rc;
-  if ((rc = upload(&c->d_stamp_pos, c->htab.stamp_pos.data(), c->htab.stamp_pos.size(), s))) return rc;
-  if ((rc = upload(&c->d_near_q, c->htab.near_factor_q.data(), c->htab.near_factor_q.size(), s))) return rc;
-  if ((rc = upload(&c->d_q_limit, c->htab.q_limit, (size_t)EG_N_RCLASS, s))) return rc;
   if ((rc = upload(&c->d_near, c->htab.near_factor.data(), c->htab.near_factor.size(), s))) return rc;
   if ((rc = upload(&c->d_r2_limit, c->htab.r2_limit, (size_t)(2 * EG_N_RCLASS + 1), s))) return rc;
   if ((rc = upload(&c->d_sx, m.sx.data(), m.sx.size(), s))) return rc;
@@ -153,22 +143,7 @@ int build_device_map(eg_ctx* c) {
   EG_CUDA(cudaStreamSynchronize(s));
   c->dmap.small = c->d_small;
   c->dmap.plant_terms = c->d_plant_terms;
-  c->dmap.stamp = c->d_stamp;
-  c->dmap.stamp_pos = c->d_stamp_pos;
-  c->dmap.stamp_items = c->htab.stamp_items;
-  c->dmap.near_stride = c->htab.near_stride;
-  if (c->d_near_ws) { cudaFree(c->d_near_ws); c->d_near_ws = nullptr; c->near_ws_stride = c->near_ws_slots = 0; }
-  if (c->htab.near_wide) {
-    int sms = 0;
-    EG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-    c->near_ws_stride = (uint32_t)((m.grid_n * c->htab.near_stride + 15) & ~15);
-    c->near_ws_slots = (uint32_t)sms * 32u;  // more than the register file lets be resident
-    EG_CUDA(cudaMalloc((void**)&c->d_near_ws, (size_t)c->near_ws_stride * c->near_ws_slots));
-  }
   c->dmap.near_wide = c->htab.near_wide;
-  c->dmap.near_shift = c->htab.near_shift;
-  c->dmap.near_factor_q = c->d_near_q;
-  c->dmap.q_limit = c->d_q_limit;
   c->dmap.site_opinion = c->d_site_opinion;
   c->dmap.coast_factor = c->d_coast;
   c->dmap.order = c->d_order;
@@ -240,9 +215,6 @@ EgEpisodeParams make_params(const eg_ctx* c, const eg_run_cfg* cfg, uint64_t see
   p.replay_best = cfg->replay_best;
   p.ln100 = std::log(50000000000.0 * 100.0 / 50000000000.0);
   p.next_episode = c->d_next_episode;
-  p.near_ws = c->d_near_ws;
-  p.near_ws_stride = c->near_ws_stride;
-  p.near_ws_slots = c->near_ws_slots;
   p.nf_entries = c->htab.r2_limit[2 * EG_N_RCLASS];
   return p;
 }
@@ -283,7 +255,7 @@ void eg_destroy(eg_ctx* c) {
   free_map(c);
   if (c->h_stats) cudaFreeHost(c->h_stats);
   if (c->h_record) cudaFreeHost(c->h_record);
-  void* ptrs[] = {c->d_policy, c->d_near_ws, c->d_next_episode, c->d_stats, c->d_best_score, c->d_best_index, c->d_record, c->s_out, c->s_traj, c->s_traj_in, c->s_sites, c->s_yearly};
+  void* ptrs[] = {c->d_policy, c->d_next_episode, c->d_stats, c->d_best_score, c->d_best_index, c->d_record, c->s_out, c->s_traj, c->s_traj_in, c->s_sites, c->s_yearly};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->own_stream) cudaStreamDestroy(c->stream);

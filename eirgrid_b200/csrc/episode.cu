@@ -16,16 +16,15 @@
 //    everything needing pow/exp is tabulated per year on the host. Per-plant TERMS are computed 32 at a time across
 //    the lanes, staged in shared memory and folded in sequentially from broadcast reads.
 //  * Episode state that is indexed dynamically lives in shared memory, one slice per warp, addressed through the
-//    shared window (LDS/STS, never generic loads): the list of plants and offsets built so far, this year's private
-//    copy of the weight rows, and a per-candidate-site map of the squared cell distance to the nearest plant built
-//    in this episode.
+//    shared window (LDS/STS, never generic loads): the list of plants and offsets built so far and this year's private
+//    copy of the weight rows.
 //  * The 100x100 placement scan becomes a walk, 32 candidates per step, down a per-(class, year) list of sites sorted
-//    by static score. A site farther than the penalty radius from every new plant keeps its static score. A site in
-//    range can only lose score, and (static prefix) x (factor of its nearest new plant) is an exact upper bound of
-//    its score (rounding is monotone). In-range sites of a step are examined best-bound-first: the lanes compute the
-//    factors of 32 PLANTS of one site at a time and only the in-range factors are multiplied in, in plant order;
-//    every evaluation raises the running best and prunes the remaining candidates by their bounds. The walk stops
-//    once static scores fall below the best found.
+//    by static score (the score when no simulation-built plant is in range). A plant in range can only lower a site's
+//    score (all factors < 1, rounding is monotone), so the walk stops once static scores fall below the best exact
+//    score found. Every site still in the race multiplies the factors of the plants in its range in plant order, one
+//    site per lane. (Round 1's earlier versions kept a per-site map of the distance to the nearest new plant to prune
+//    sites by an upper bound before evaluating them; once the evaluation loop was down to ~9 instructions per plant,
+//    maintaining the map cost more than it saved — 20 % on the shipped map, 45 % on the 10x map — and it was removed.)
 //  * Philox draws are produced 32 at a time (lane l computes draw base+l) and handed out by shuffle.
 //  * Compiled with --fmad=false: + - * / sqrt are the reference's IEEE operations, no contraction.
 #include "episode.cuh"
@@ -66,7 +65,7 @@ constexpr int kOffOffs = kOffGat + 2 * EG_MAX_NEW_GENERATORS;   // uint16[EG_MAX
 constexpr int kOffYearSites = kOffOffs + 2 * EG_MAX_OFFSETS;    // uint16[40]
 constexpr int kOffYearActions = kOffYearSites + 2 * EG_MAX_ACTIONS_PER_YEAR;  // uint8[40]
 constexpr int kOffCounts = kOffYearActions + EG_MAX_ACTIONS_PER_YEAR;         // uint8[26] deficit + uint8[26] additional
-constexpr int kOffNear = (kOffCounts + 2 * EG_NY + 15) & ~15;   // nearest-plant map, n_sites entries
+constexpr int kSliceBytes = (kOffCounts + 2 * EG_NY + 15) & ~15;  // 5.7 KB per warp
 static_assert(kOffScratch % 16 == 0 && kOffVars % 8 == 0 && kOffGxy % 8 == 0 && kOffOffs % 4 == 0 && kOffYearSites % 4 == 0 && kOffYearActions % 4 == 0, "alignment");
 
 // slots of the per-warp scalar area: values every lane agrees on that are touched a few times per year
@@ -203,7 +202,7 @@ struct Warp {
   double off_amount;          // calc_total_carbon_offset(year)
   uint32_t n_gens, n_offs, flags;
 #ifdef EG_WALK_STATS
-  uint32_t dbg_steps, dbg_evals, dbg_cands, dbg_pairs, dbg_inr;
+  uint32_t dbg_steps, dbg_evals, dbg_cands, dbg_pairs;
 #endif
   bool rows_dirty, dw_dirty, sorted_valid, total_valid;
   bool folded;                // this year's plant/offset sums (op_sum, gcost, ocost, off_amount) are valid
@@ -226,8 +225,6 @@ struct Warp {
   __device__ __forceinline__ uint16_t* YSITES() const { return (uint16_t*)(smem + sb + kOffYearSites); }
   __device__ __forceinline__ uint8_t* YACT() const { return smem + sb + kOffYearActions; }
   __device__ __forceinline__ uint8_t* COUNTS() const { return smem + sb + kOffCounts; }
-  uint8_t* near_g;            // wide maps: this warp's slot of the global workspace
-  __device__ __forceinline__ uint8_t* NEAR() const { return WIDE ? near_g : smem + sb + kOffNear; }
 
 
   // ---- random draws ---------------------------------------------------------------------------------------
@@ -363,22 +360,13 @@ struct Warp {
     // (the block-shared copy sits at the start of the dynamic shared memory)
     const double* __restrict__ nf = p.map.near_factor + rc * p.map.r2_stride;
     const uint32_t nf_s = opaque((uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)__ldg(&p.map.r2_limit[EG_N_RCLASS + rc]) * 8u);
-    const int nstride = p.map.near_stride;
     const double size_factor = __ldg(&T->size_factor);
-    const uint8_t* nearest = NEAR();
-    const int inr_lim = WIDE ? __ldg(&p.map.q_limit[rc]) : r2lim;  // cell values below it may have a plant in range
     const uint16_t* gxy = GXY();
     double best_score = 0.0;
     int best_site = -1;
     double2 sp_next = lane < ns ? __ldg(&walk[lane]) : make_double2(0.0, 0.0);   // (static score, prefix score)
     int packed_next = lane < ns ? (int)__ldg(&order[lane]) : 0;                  // (i << 8) | j of the candidate site
     for (int k0 = 0; k0 < ns; k0 += 32) {
-#ifdef EG_WALK_NOPIPE
-      if (k0 + lane < ns && k0 > 0) { sp_next = __ldg(&walk[k0 + lane]); packed_next = (int)__ldg(&order[k0 + lane]); }
-      else if (k0 > 0) sp_next = make_double2(0.0, 0.0);
-      const double s_static = sp_next.x, pre = sp_next.y;
-      const int packed = packed_next;
-#else
       const double s_static = sp_next.x, pre = sp_next.y;
       const int packed = packed_next;
       {  // entries of the next step: in flight while this step is examined
@@ -386,43 +374,17 @@ struct Warp {
         sp_next = make_double2(0.0, 0.0);
         if (kn < ns) { sp_next = __ldg(&walk[kn]); packed_next = (int)__ldg(&order[kn]); }
       }
-#endif
       const double s_first = shfl_f64(s_static, 0);
       // the list is sorted: nothing from here on can beat the best so far, and zero scores never win
       if (s_first < best_score || !(s_first > 0.0)) break;
       const bool live = s_static > 0.0 && !(s_static < best_score);
       const int site = (packed >> 8) * n + (packed & 0xFF);
-      bool inr = false;
-      int d2n = 0;
-      if (live) {
-        EG_CHECK((packed >> 8) < n && (packed & 0xFF) < n && (packed >> 8) * nstride + (packed & 0xFF) < n * nstride);
-        d2n = nearest[(packed >> 8) * nstride + (packed & 0xFF)];
-        inr = d2n < inr_lim;
-      }
-      // sites out of range of every new plant keep their static score; in list order the first one is the best of them
-      // (descending scores, equal scores in scan order)
-      const unsigned m_out = __ballot_sync(kFull, live && !inr);
-      if (m_out) {
-        const int f = __ffs(m_out) - 1;
-        const double sc = shfl_f64(s_static, f);
-        const int st = __shfl_sync(kFull, site, f);
-        // strict '>' in scan order (metal_location_search.rs:168): the maximum wins, equal scores keep the lower site
-        if (sc > best_score || (sc == best_score && st < best_site)) { best_score = sc; best_site = st; }
-      }
-      // in range of at least one new plant: all factors are < 1 and rounding is monotone, so the product with the
-      // nearest plant's factor alone bounds the true score from above
-      bool cand = false;
-      if (inr) {
-        double bound = pre * (WIDE ? __ldg(&p.map.near_factor_q[rc * 256 + d2n]) : lds_f64(nf_s + 8u * (uint32_t)d2n));
-        if (water) bound *= __ldg(&p.map.coast_factor[site]);
-        bound *= size_factor;
-        cand = bound > 0.0 && !(bound < best_score);
-      }
+      // every site still in the race is evaluated exactly
+      const bool cand = live;
 #ifdef EG_WALK_STATS
       dbg_steps++;
-      dbg_inr += __popc(__ballot_sync(kFull, inr));
 #endif
-      if (__any_sync(kFull, cand)) {
+      {  // (lane 0 holds the step's highest static score, which passed the test above: at least one lane is live)
 #ifdef EG_WALK_STATS
         dbg_evals++;
         dbg_cands += __popc(__ballot_sync(kFull, cand));
@@ -471,27 +433,6 @@ struct Warp {
     EG_CHECK(gi >= 0 && gi < n && gj >= 0 && gj < n && n_gens < EG_MAX_NEW_GENERATORS && t < EG_NT && m < EG_N_MULTS && y < EG_NY);
     if (lane == 0) { GXY()[n_gens] = (uint16_t)((gi << 8) | gj); GAT()[n_gens] = (uint16_t)pack_attr(t, m, y); }
     n_gens++;
-    // nearest-plant map: squared cell distance to the closest plant built in this episode. One 32-bit word (4 or 2
-    // cells) per lane: packed minimum of the map word and the host-built pattern word for this column alignment.
-    {
-      constexpr int cpw = 4;
-      const int R = p.map.kmax - 1, items = p.map.stamp_items, nstride_w = p.map.near_stride / cpw;
-      const int a = gj % cpw;
-      const int w0 = (gj - a - (R + cpw - 1) / cpw * cpw) / cpw;  // first word column of the pattern (may be negative)
-      const uint32_t* __restrict__ pat = p.map.stamp + (uint32_t)(a * items);
-      const uint16_t* __restrict__ pos = p.map.stamp_pos + (uint32_t)(a * items);
-      uint32_t* near_w = (uint32_t*)NEAR();
-      for (int it = lane; it < items; it += 32) {  // only the pattern words that touch the largest radius
-        const uint32_t ps = __ldg(&pos[it]);
-        const uint32_t pw = __ldg(&pat[it]);
-        const int i = gi - R + (int)(ps >> 8), jw = w0 + (int)(ps & 0xFF);
-        if (i >= 0 && i < n && jw >= 0 && jw < nstride_w) {
-          EG_CHECK(i * nstride_w + jw < n * nstride_w);
-          uint32_t* cell = near_w + i * nstride_w + jw;
-          *cell = __vminu4(*cell, pw);
-        }
-      }
-    }
     __syncwarp();
     const int cls = __ldg(&T->acc_class[t]);
     const double mw = __ldg(&T->net_mw[t]);
@@ -703,22 +644,9 @@ struct Warp {
     draw = 0; rbase = 0x80000000u; rbuf = 0ull;
     n_gens = 0; n_offs = 0; flags = 0;
 #ifdef EG_WALK_STATS
-    dbg_steps = dbg_evals = dbg_cands = dbg_pairs = dbg_inr = 0;
+    dbg_steps = dbg_evals = dbg_cands = dbg_pairs = 0;
 #endif
     gcost = 0.0; ocost = 0.0; gen0 = gen1 = gen2 = 0.0; co2 = 0.0;
-    {
-      // clear the nearest-plant map, 4 bytes per lane and step (n_sites entries, padded to 16 bytes by the launcher)
-      if (WIDE) {
-        uint4* nw = (uint4*)NEAR();
-        const int quads = (p.map.grid_n * p.map.near_stride + 15) / 16;
-        for (int i = lane; i < quads; i += 32) nw[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-      } else {
-        uint32_t* nw = (uint32_t*)NEAR();
-        const int words = (p.map.grid_n * p.map.near_stride + 3) / 4;
-#pragma unroll 2
-        for (int i = lane; i < words; i += 32) nw[i] = 0xFFFFFFFFu;
-      }
-    }
     __syncwarp();
     const eg_traj* in = REPLAY ? p.replay_in + ep : nullptr;
     uint32_t n_def_total = 0, n_add_total = 0;
@@ -962,7 +890,6 @@ __global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) 
     __syncthreads();
   }
   Warp<REPLAY, WIDE> w(p, opaque((uint32_t)(table_bytes + warp * slice_bytes)), lane);
-  w.near_g = WIDE ? p.near_ws + (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * p.near_ws_stride : nullptr;
   // persistent warps: every warp fetches the next unclaimed episode of the batch until none is left, so a short
   // episode never leaves its warp idle while the block's longest one finishes
   for (;;) {
@@ -977,9 +904,7 @@ __global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) 
 template <bool REPLAY, bool WIDE>
 cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
   const bool wide = WIDE;
-  const int near_bytes = wide ? 0 : p.map.grid_n * p.map.near_stride;  // wide maps keep it in the global workspace
-  const int slice = (kOffNear + near_bytes + 15) & ~15;
-  if (wide && (!p.near_ws || p.near_ws_stride < (uint32_t)((p.map.grid_n * p.map.near_stride + 15) & ~15))) return cudaErrorInvalidValue;
+  const int slice = kSliceBytes;
   const int shared_tab = wide ? 0 : (p.nf_entries * (int)sizeof(double) + 15) & ~15;
   // as many warps per block as keep several blocks resident in the 227 KB of an SM
   int warps = EG_EPISODE_WARPS;
@@ -1000,7 +925,6 @@ cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
   if (err != cudaSuccess) return err;
   if (per_sm < 1) return cudaErrorInvalidConfiguration;
   uint32_t blocks = std::min<uint32_t>((uint32_t)(sms * per_sm), (p.n + warps - 1) / warps);
-  if (wide) blocks = std::min<uint32_t>(blocks, p.near_ws_slots / warps);  // one workspace slot per resident warp
   if (blocks == 0) return cudaErrorInvalidConfiguration;
   err = cudaMemsetAsync(p.next_episode, 0, sizeof(uint32_t), stream);
   if (err != cudaSuccess) return err;

@@ -12,11 +12,6 @@ struct EgEpisodeParams {
   eg_sites* sites;               // nullable
   eg_yearly* yearly;             // nullable
   int nf_entries;                // size of the compact distance/radius table copied to shared memory (narrow maps)
-  // wide maps: the nearest-plant maps live in an L2-resident global workspace, one slot of near_ws_stride bytes per
-  // resident warp, instead of shared memory (which would cap an SM at 6 warps)
-  unsigned char* near_ws;
-  uint32_t near_ws_stride;
-  uint32_t near_ws_slots;
   uint32_t* next_episode;        // device counter the persistent warps claim episodes from (zeroed by the launcher)
   unsigned long long seed;
   unsigned long long first_episode;

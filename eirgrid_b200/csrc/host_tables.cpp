@@ -389,51 +389,8 @@ void eg_host_build_tables(const EgHostMap& m, EgHostTables* out) {
       const double distance = std::sqrt((double)d2 * m.step * m.step);
       out->near_factor[(size_t)rc * stride + d2] = distance / kRadii[rc];
     }
-  // ---- stamp pattern of the nearest-plant map (episode.cu add_generator)
-  // squared cell distances do not fit a byte, or site coordinates do not fit 7 bits (packed byte arithmetic in place())
-  out->near_wide = (stride > 255 || m.grid_n > 128) ? 1 : 0;
-  const int cpw = 4;                                          // cells per 32-bit word (uint8 cells)
-  out->near_shift = 0;
-  while (((stride - 1) >> out->near_shift) > 254) out->near_shift++;  // quantisation of the cell value on wide maps
-  const int qs = out->near_shift;
-  out->near_factor_q.assign((size_t)EG_N_RCLASS * 256, 1.0);
-  for (int rc = 0; rc < EG_N_RCLASS; rc++) {
-    out->q_limit[rc] = (out->r2_limit[rc] + (1 << qs) - 1) >> qs;
-    for (int q = 0; q < 256; q++) {
-      const long d2_up = ((long)q << qs) + (1 << qs) - 1;  // the largest squared distance a cell value q can stand for
-      if (d2_up < out->r2_limit[rc]) out->near_factor_q[(size_t)rc * 256 + q] = out->near_factor[(size_t)rc * stride + d2_up];
-    }
-  }
-  const int R = kmax - 1, rows = 2 * R + 1;
-  const int Rp = (R + cpw - 1) / cpw * cpw;                   // pattern starts at column gj - (gj mod cpw) - Rp: word aligned
-  out->near_stride = (m.grid_n + cpw - 1) / cpw * cpw;
-  const int words = (Rp + cpw - 1 + R + 1 + cpw - 1) / cpw;   // words covering columns up to gj + R
-  std::vector<std::vector<uint32_t>> pw(cpw);
-  std::vector<std::vector<uint16_t>> pp(cpw);
-  for (int a = 0; a < cpw; a++)
-    for (int r = 0; r < rows; r++)
-      for (int w = 0; w < words; w++) {
-        uint32_t word = 0;
-        bool any = false;
-        for (int b = 0; b < cpw; b++) {
-          const int di = r - R, dj = w * cpw + b - Rp - a;
-          const long d2 = (long)di * di + (long)dj * dj;
-          const bool in = std::abs(dj) <= R && d2 < stride;  // only cells inside the largest radius matter
-          any = any || in;
-          word |= (in ? (uint32_t)(d2 >> qs) : 0xFFu) << (b * 8);
-        }
-        if (any) { pw[a].push_back(word); pp[a].push_back((uint16_t)((r << 8) | w)); }
-      }
-  size_t items = 0;
-  for (int a = 0; a < cpw; a++) items = std::max(items, pw[a].size());
-  items = (items + 31) / 32 * 32;
-  out->stamp_items = (int)items;
-  out->stamp.assign((size_t)cpw * items, 0xFFFFFFFFu);   // padding: a minimum with 0xFF.. changes nothing
-  out->stamp_pos.assign((size_t)cpw * items, (uint16_t)((R << 8) | (Rp / cpw)));  // ... at the plant's own word
-  for (int a = 0; a < cpw; a++)
-    for (size_t k = 0; k < pw[a].size(); k++) {
-      out->stamp[(size_t)a * items + k] = pw[a][k];
-      out->stamp_pos[(size_t)a * items + k] = pp[a][k];
-    }
+  // the packed signed-byte cell distance of the kernel needs coordinates below 128; its shared-memory copy of the factor
+  // table holds the entries inside the radii (at most a few KB on maps with cells of 750 m or more)
+  out->near_wide = (m.grid_n > 128 || out->r2_limit[2 * EG_N_RCLASS] > 2048) ? 1 : 0;
   (void)kRadius;
 }

@@ -24,14 +24,7 @@ struct EgHostTables {
   int r2_limit[2 * EG_N_RCLASS + 1] = {0};  // limits, compact-table offsets, compact-table size
   int r2_stride = 0;
   int kmax = 0;
-  std::vector<uint32_t> stamp;       // [cells per word][2*(kmax-1)+1][stamp_w]
-  std::vector<uint16_t> stamp_pos;   // [4][stamp_items]
-  int stamp_items = 0;
-  int near_stride = 0;
-  int near_wide = 0;
-  int near_shift = 0;
-  std::vector<double> near_factor_q;  // [6][256]
-  int q_limit[EG_N_RCLASS] = {0};
+  int near_wide = 0;                 // coordinates above 127 or a factor table too large for shared memory
 };
 
 int eg_host_map_load(EgHostMap* m, const char* settlements_json, const char* generators_csv, const char* coastline_json);

@@ -76,21 +76,8 @@ struct EgDeviceMap {      // device pointers + sizes, passed by value to the ker
   int n_sites;
   int grid_n;
   int kmax;                       // plants farther than kmax-1 cells (in x or y) are outside every radius
-  // nearest-plant map of an episode (shared memory): rows padded to near_stride cells (a multiple of 4) so that rows start
-  // on 32-bit words; cells are uint8: the squared cell distance d2 to the nearest plant built in the episode, or, on maps
-  // whose d2 exceeds 254 (near_wide), d2 >> near_shift. A new plant is stamped into it with packed minima (4 cells per
-  // word) against a host-built pattern of the squared distances around a plant, one version per column alignment (stamp).
-  // With quantised cells the map still decides exactly "no plant in range" ((q << shift) >= r2_limit) and gives an upper
-  // bound of the nearest plant's factor: near_factor_q[rc][q] = factor at the largest d2 the cell can stand for (1.0 if
-  // that is out of range); q_limit[rc] = first q that is certainly out of range.
-  const double* near_factor_q;    // [6][256]
-  const int* q_limit;             // [6]
-  int near_shift;
-  const uint32_t* stamp;          // [4][stamp_items] pattern words that hold at least one cell inside the largest radius
-  const uint16_t* stamp_pos;      // [4][stamp_items] (row << 8) | word column of that pattern word
-  int stamp_items;                // per alignment, padded with no-op items (word 0xFFFFFFFF at position 0)
-  int near_stride;
-  int near_wide;
+  int near_wide;                  // 1: site coordinates above 127 or a factor table too large for shared memory — the kernel
+                                  // then uses plain integer cell distances and reads the factor table from global memory
 };
 
 #define EG_POLICY_ROW (EG_N_ACTIONS + EG_N_DEFICIT_KEYS + EG_N_COUNT_KEYS + 1)  // 98 doubles = 784 bytes, a multiple of 16
