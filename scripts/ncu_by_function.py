@@ -11,8 +11,8 @@ for i, l in enumerate(text, 1):
     m = re.match(r"\s*__device__ .*?\b(\w+)\(.*\{", l) or re.match(r"\s*__global__ .*?\b(\w+)\(", l)
     if m:
         marks.append((i, m.group(1)))
-    for pat, name in ((r"for \(int k0 = 0; k0 < ns", "place: walk step"), (r"if \(__any_sync\(kFull, cand\)\)", "place: survivors loop+reduce"),
-                      (r"nearest-plant map: squared cell distance", "add_generator: stamp"), (r"for \(int y = 0; y < EG_NY", "run: year loop"),
+    for pat, name in ((r"for \(int k0 = 0; k0 < ns", "place: walk step"), (r"lane 0 holds the step's highest static score", "place: evaluation loop+reduce"),
+                      (r"for \(int y = 0; y < EG_NY", "run: year loop"),
                       (r"calculate_yearly_metrics, analysis", "run: yearly metrics"), (r"SimulationMetrics from the 2050", "run: result"),
                       (r"const int cls = __ldg\(&T->acc_class\[t\]\);\s*$", "add_generator: sums")):
         if re.search(pat, l):
