@@ -95,7 +95,7 @@ class WeightsTable(C.Structure):
 class UpdateStats(C.Structure):
     _fields_ = [("n_episodes", C.c_uint32), ("n_improvements", C.c_uint32), ("n_contrast_applied", C.c_uint32),
                 ("iterations_without_improvement", C.c_uint32), ("best_score", C.c_double),
-                ("batch_best_score", C.c_double), ("batch_best_episode", C.c_int64)]
+                ("batch_best_score", C.c_double), ("batch_best_episode", C.c_int64), ("n_flagged", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 def action_name(code):

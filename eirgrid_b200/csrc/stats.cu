@@ -4,7 +4,7 @@
 // one episode at a time under a write lock (core/multi_simulation.rs:494-508). For a batch sampled from one frozen
 // snapshot and sharded over GPUs, the per-episode effect on the weight table is summarised here as a small integer
 // table that ranks sum with one NCCL allreduce:
-//   header[0] episodes, header[1] episodes whose deterioration passed the contrast threshold
+//   header[0] episodes, header[1] episodes whose deterioration passed the contrast threshold, header[2] flagged episodes
 //   per year: [0,61)    sum of ln(penalty_e)      over penalised occurrences of action k   (fixed point, 2^-24)
 //             [61,122)  sum of ln(mild_penalty_e) over mis-positioned occurrences of k      (fixed point)
 //             [122,183) occurrences of action k in current_run_actions
@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(256) eg_stats_kernel(const EgStatsParams p) {
     if (lane == 0) {
       atomicAdd(&acc[0], 1ull);
       if (pass) atomicAdd(&acc[1], 1ull);
+      if (rp->flags) atomicAdd(&acc[2], 1ull);  // capacity overflow / no site: counted so that a driver can report it
     }
     // The episode's records: current_run_actions ++ current_deficit_actions of every year, ~40 items in all, most of them
     // in 2025. Lane y holds year y's counts; the items are numbered through all years (warp prefix sum) and dealt out 32 at

@@ -613,6 +613,7 @@ int eg_update(eg_weights* w, const eg_result* results, const eg_traj* trajs, uin
     deficit_contrast(*w, rec, &rng);                       // apply_deficit_contrast_learning
     const double sc = eg_score_default(m);
     if (st.batch_best_episode < 0 || sc > st.batch_best_score) { st.batch_best_score = sc; st.batch_best_episode = i; }
+    if (results[i].flags) st.n_flagged++;
   }
   st.iterations_without_improvement = w->iwi;
   st.best_score = w->has_best ? eg_score_default(w->best_metrics) : 0.0;
@@ -632,6 +633,7 @@ int eg_update_apply_stats(eg_weights* w, const int64_t* stats, uint64_t n_total,
   const EgContrastConsts c = eg_contrast_consts(*w);
   const int64_t n_pass = stats[1];
   st.n_contrast_applied = (uint32_t)n_pass;
+  st.n_flagged = (uint32_t)stats[2];
   if (w->has_best && n_pass > 0) {
     for (int y = 0; y < EG_NY; y++) {
       const int64_t* ys = stats + EG_STATS_HEADER + (size_t)y * EG_STATS_YEAR_STRIDE;

@@ -153,6 +153,7 @@ def run_multi_simulation(asset_dir, num_iterations, parallel=True, continue_from
     t_start, t_progress = time.time(), time.time()
     next_checkpoint = (completed // checkpoint_interval + 1) * checkpoint_interval
     history = []
+    n_flagged = 0
     if rank == 0:
         log("Starting multi-simulation optimization with %d iterations (%d completed, %d remaining) in directory %s"
             % (num_iterations, start_iteration, num_iterations - start_iteration, run_dir))
@@ -178,6 +179,9 @@ def run_multi_simulation(asset_dir, num_iterations, parallel=True, continue_from
             st = weights.update(res, traj, replay_best=replay_best, rng_seed=rng_seed)
             trainer.next_episode += trainer.n
         completed += trainer.n * world
+        n_flagged += int(st.n_flagged)
+        if st.n_flagged and rank == 0:
+            log("warning: %d episodes of this batch exceeded a fixed capacity or found no site (eg_result.flags)" % st.n_flagged)
         if rank == 0:
             if time.time() - t_progress >= progress_interval:
                 t_progress = time.time()
@@ -201,6 +205,6 @@ def run_multi_simulation(asset_dir, num_iterations, parallel=True, continue_from
                "episodes_per_s": (completed - start_iteration) / max(elapsed, 1e-9), "best_score": _best_score(weights),
                "best_metrics": {"final_net_emissions": t.best_metrics[0], "average_public_opinion": t.best_metrics[1],
                                 "total_cost": t.best_metrics[2], "power_reliability": t.best_metrics[3]} if t.has_best else None,
-               "iterations_without_improvement": t.iterations_without_improvement, "n_gpus": world, "csv_dir": csv_dir}
+               "iterations_without_improvement": t.iterations_without_improvement, "n_gpus": world, "csv_dir": csv_dir, "flagged_episodes": n_flagged}
     trainer.close()
     return summary

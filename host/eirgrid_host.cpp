@@ -305,6 +305,7 @@ int main(int argc, char** argv) {
   const double t_start = now_s();
   double t_progress = t_start;
   eg_update_stats st{};
+  uint64_t n_flagged = 0;
   double t_train = 0.0;        // wall time of the training batches (device statistics path)
   uint64_t n_train = 0;
   while (completed < a.iterations) {
@@ -348,6 +349,10 @@ int main(int argc, char** argv) {
       done_now = n_s;
     }
     completed += done_now;
+    if (st.n_flagged) {
+      n_flagged += st.n_flagged;
+      std::fprintf(stderr, "warning: %u episodes of this batch exceeded a fixed capacity or found no site (eg_result.flags)\n", st.n_flagged);
+    }
     const double t = now_s();
     if (t - t_progress >= (double)a.progress_interval) {
       t_progress = t;
@@ -379,11 +384,11 @@ int main(int argc, char** argv) {
   for (size_t g = 0; g < G; g++) launches += eg_kernel_launches(ctx[g]);
   std::printf("{\"run_dir\": \"%s\", \"iterations\": %llu, \"start_iteration\": %llu, \"elapsed_s\": %.3f, \"episodes_per_s\": %.1f, "
               "\"training_batches\": {\"episodes\": %llu, \"episodes_per_s\": %.1f}, "
-              "\"best_score\": %s, \"iterations_without_improvement\": %u, \"n_gpus\": %zu, \"kernel_launches\": %llu}\n",
+              "\"best_score\": %s, \"iterations_without_improvement\": %u, \"flagged_episodes\": %llu, \"n_gpus\": %zu, \"kernel_launches\": %llu}\n",
               run_dir.c_str(), (unsigned long long)completed, (unsigned long long)start_iteration, elapsed,
               (double)(completed - start_iteration) / std::max(elapsed, 1e-9), (unsigned long long)n_train, (double)n_train / std::max(t_train, 1e-9),
               has_best ? std::to_string(best).c_str() : "null",
-              st.iterations_without_improvement, G, (unsigned long long)launches);
+              st.iterations_without_improvement, (unsigned long long)n_flagged, G, (unsigned long long)launches);
   eg_weights_free(weights);
   for (eg_ctx* c : ctx) eg_destroy(c);
   return 0;

@@ -176,6 +176,8 @@ typedef struct {
   double best_score;
   double batch_best_score;
   int64_t batch_best_episode;         /* index inside the batch, -1 if none */
+  uint32_t n_flagged;                 /* episodes of the batch with eg_result.flags != 0 (capacity overflow, no site found) */
+  uint32_t reserved;
 } eg_update_stats;
 
 /* ---- context ----------------------------------------------------------------------------------- */

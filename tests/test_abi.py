@@ -33,7 +33,7 @@ def test_struct_sizes_match_header():
     assert _abi.RESULT_DTYPE.itemsize == 64 and _abi.TRAJ_DTYPE.itemsize == 1092
     assert _abi.SITES_DTYPE.itemsize == 2080 and _abi.YEAR_DTYPE.itemsize == 144
     assert C.sizeof(_abi.WeightsTable) == 8 * (26 * (61 + 15 + 21) + 6) + 16
-    assert C.sizeof(_abi.RunCfg) == 32 and C.sizeof(_abi.UpdateStats) == 40
+    assert C.sizeof(_abi.RunCfg) == 32 and C.sizeof(_abi.UpdateStats) == 48
 
 
 def test_no_gpu_fails_loudly_without_fallback():

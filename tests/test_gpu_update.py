@@ -106,3 +106,31 @@ def test_batch_rule_score_distribution_matches_sequential_rule(gpu_ctx):
         tr.close()
     assert abs(np.mean(seq) - np.mean(bat)) < 0.01, (seq, bat)
     assert min(bat) > 1.88 and min(seq) > 1.88
+
+
+def test_flagged_episodes_are_counted(gpu_ctx):
+    """Episodes that exceed a fixed capacity (or find no site) are counted in the update statistics of both update paths."""
+    import torch
+    rs = np.random.RandomState(5)
+    n = 64
+    t = np.zeros(n, _abi.TRAJ_DTYPE)
+    t["n_additional"][:8, :] = 40
+    t["actions"][:8] = rs.randint(0, 45, (8, 26, 40))   # 1040 plants: over the 560-plant capacity
+    t["n_additional"][8:, 0] = 1
+    res, _, _ = gpu_ctx.replay(t)
+    assert int((res["flags"] != 0).sum()) == 8
+    w = _lib.Weights()
+    assert w.update(res, t).n_flagged == 8              # sequential path
+    dev = torch.device("cuda", 0)
+    d_res = torch.from_numpy(res.view(np.uint8).copy()).to(dev)
+    d_traj = torch.from_numpy(t.view(np.uint8).copy()).to(dev)
+    d_stats = torch.zeros(_abi.STATS_WORDS, dtype=torch.int64, device=dev)
+    d_bs = torch.zeros(1, dtype=torch.float64, device=dev)
+    d_bi = torch.zeros(1, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    w2 = _lib.Weights()
+    gpu_ctx.weights_upload(w2)
+    gpu_ctx.update_stats_device(w2, n, d_res, d_traj, d_stats, d_bs, d_bi)
+    gpu_ctx.sync()
+    stats = d_stats.cpu().numpy()
+    assert stats[0] == n and stats[2] == 8               # batch path: header word 2
