@@ -181,7 +181,8 @@ def run_multi_simulation(asset_dir, num_iterations, parallel=True, continue_from
         completed += trainer.n * world
         n_flagged += int(st.n_flagged)
         if st.n_flagged and rank == 0:
-            log("warning: %d episodes of this batch exceeded a fixed capacity or found no site (eg_result.flags)" % st.n_flagged)
+            log("warning: %d episodes of this batch carry eg_result.flags (replay-phase years with more than 40 recorded actions, "
+                "quirk Q10; or a capacity overflow)" % st.n_flagged)
         if rank == 0:
             if time.time() - t_progress >= progress_interval:
                 t_progress = time.time()

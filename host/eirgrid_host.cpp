@@ -351,7 +351,7 @@ int main(int argc, char** argv) {
     completed += done_now;
     if (st.n_flagged) {
       n_flagged += st.n_flagged;
-      std::fprintf(stderr, "warning: %u episodes of this batch exceeded a fixed capacity or found no site (eg_result.flags)\n", st.n_flagged);
+      std::fprintf(stderr, "warning: %u episodes of this batch carry eg_result.flags (replay-phase years with more than 40 recorded actions, quirk Q10; or a capacity overflow)\n", st.n_flagged);
     }
     const double t = now_s();
     if (t - t_progress >= (double)a.progress_interval) {
