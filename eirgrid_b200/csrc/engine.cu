@@ -515,6 +515,18 @@ std::string fixed(double v, int prec) {
   return buf;
 }
 
+// uniform in [0,1) for the exported offset coordinates: Philox4x32-10, counter (index, axis, 0, "CSVO")
+double csv_uniform(uint32_t index, uint32_t axis) {
+  uint32_t a0 = index, a1 = axis, a2 = 0u, a3 = 0x4353564Fu, x0 = 0x45495247u, x1 = 0x52494442u;
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * a0, p1 = (uint64_t)0xCD9E8D57u * a2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ a1 ^ x0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ a3 ^ x1, n3 = (uint32_t)p0;
+    a0 = n0; a1 = n1; a2 = n2; a3 = n3;
+    x0 += 0x9E3779B9u; x1 += 0xBB67AE85u;
+  }
+  return (double)(((uint64_t)a0 | ((uint64_t)a1 << 32)) >> 11) * (1.0 / 9007199254740992.0);
+}
+
 bool mkdir_p(const std::string& p) {
   std::string cur;
   for (size_t i = 0; i <= p.size(); i++) {
@@ -548,7 +560,8 @@ int eg_export_best_run_csv(eg_ctx* c, const eg_weights* w, const eg_run_cfg* cfg
   eg_yearly yearly;
   eg_run_cfg rcfg = *cfg;
   rcfg.replay_best = 0;
-  if ((rc = eg_replay_batch(c, &rcfg, &traj, 1, &res, nullptr, &yearly))) return rc;
+  eg_sites sites;
+  if ((rc = eg_replay_batch(c, &rcfg, &traj, 1, &res, &sites, &yearly))) return rc;
 
   char ts[32];
   const std::time_t t = std::time(nullptr);
@@ -631,6 +644,106 @@ int eg_export_best_run_csv(eg_ctx* c, const eg_weights* w, const eg_run_cfg* cfg
                      lon, lat, pop, rust_display(usage).c_str());
       }
     }
+    std::fclose(f);
+  }
+  {  // yearly_details/generators.csv, csv_export.rs:532-984
+    // `Generator.eol` holds a lifespan in years, so the exporter's first pass (`year > eol`, :701) skips every plant of the
+    // map and all rows come from its second pass (:813-979): one row per generator listed as active in that year's
+    // metrics, with type, commissioning year and end of life parsed back out of the id and the remaining columns filled
+    // from per-type defaults; plants added during the run get the id-hash coordinates of :867-869, pre-existing plants
+    // their real ones. Row order inside a year is HashMap order there; here: pre-existing plants, then build order.
+    std::FILE* f = std::fopen((dir + "/yearly_details/generators.csv").c_str(), "w");
+    if (!f) return eg_fail(EG_ERR_IO, "cannot write generators.csv in " + dir);
+    std::fprintf(f, "Year,Generator ID,Type,Longitude,Latitude,Power Output (MW),Efficiency (%%),Operation (%%),CO2 Output (tonnes),Is Active,"
+                    "Commissioning Year,End of Life Year,Size,Capital Cost (\xE2\x82\xAC),Operating Cost (\xE2\x82\xAC),Total Annual Cost (\xE2\x82\xAC),"
+                    "Reliability Factor,Planning Time (years),Construction Time (years),Construction Speed\n");
+    static const double kDefPower[EG_NT] = {50.0, 200.0, 0.01, 0.5, 50.0, 1000.0, 500.0, 400.0, 100.0, 50.0, 250.0, 200.0, 50.0, 30.0, 20.0};
+    static const double kDefCo2PerKwh[EG_NT] = {0, 0, 0, 0, 0, 0, 3.0, 0.4, 0.5, 0.1, 0, 0, 0, 0, 0};
+    static const double kDefCostPerMw[EG_NT] = {1500000.0, 3500000.0, 1000000.0, 800000.0, 600000.0, 6000000.0, 2000000.0, 1000000.0,
+                                                500000.0, 3000000.0, 2500000.0, 2000000.0, 400000.0, 5000000.0, 4000000.0};
+    static const double kDefReliability[EG_NT] = {0.35, 0.35, 0.25, 0.25, 0.25, 0.95, 0.90, 0.85, 0.90, 0.80, 0.75, 0.95, 0.98, 0.45, 0.40};
+    struct Plant { std::string id; int type, first_year, commissioning; double x, y; };
+    std::vector<Plant> plants;
+    const EgHostMap& m = c->hmap;
+    for (size_t g = 0; g < m.ex.size(); g++)  // "Existing_{type}_{n}" (generators_loader.rs:190): the third id field is the row number
+      plants.push_back({std::string("Existing_") + kCsvGenNames[m.etype[g]] + "_" + std::to_string(g), m.etype[g],
+                        g < c->htab.ex_online_year.size() && c->htab.ex_online_year[g] ? c->htab.ex_online_year[g] : 1 << 30, (int)g, m.ex[g], m.ey[g]});
+    for (int y = 0; y < EG_NY; y++)
+      for (int i = 0; i < traj.n_deficit[y] + traj.n_additional[y]; i++) {
+        const int a = traj.actions[y][i];
+        if (a >= 45 || sites.site[y][i] == EG_SITE_NONE) continue;
+        const int year = EG_BASE_YEAR + y;
+        Plant p{std::string("Gen_") + kCsvGenNames[a / 3] + "_" + std::to_string(year) + "_" + std::to_string(plants.size()), a / 3, year, year, 0, 0};
+        uint32_t h = 0;
+        for (unsigned char ch : p.id) h += ch;
+        p.x = 5000.0 + (double)(h % 100) / 100.0 * (50000.0 - 10000.0);
+        p.y = 5000.0 + (double)((h / 100) % 100) / 100.0 * (50000.0 - 10000.0);
+        plants.push_back(p);
+      }
+    for (int y = 0; y < EG_NY; y++) {
+      const int year = EG_BASE_YEAR + y;
+      for (const Plant& p : plants) {
+        if (p.first_year > year) continue;
+        const int t = p.type;
+        const double xv = std::min(std::max(p.x, 0.0), 50000.0), yv = std::min(std::max(p.y, 0.0), 50000.0);
+        const double lon = -10.6 + ((-5.9 - -10.6) * (xv / 50000.0)), lat = 51.4 + ((55.4 - 51.4) * (yv / 50000.0));
+        const double power = kDefPower[t];
+        const double co2 = kDefCo2PerKwh[t] == 0 ? 0.0 : power * kDefCo2PerKwh[t] * 8760.0 / 1000.0;
+        const double size = t == 0 ? power / 3.0 : t == 1 ? power / 8.0 : t == 2 ? power * 8.0 : t == 3 ? power * 6.0 : t == 4 ? power * 2.0 : power / 50.0;
+        const double capital = power * kDefCostPerMw[t], operating = capital * 0.03;
+        double planning, construction;
+        eg_host_tech_durations(t, p.commissioning, &planning, &construction);
+        // efficiency 0.99 and operation 100 (get_operation_percentage, a 0..100 value that the exporter scales by 100 again)
+        std::fprintf(f, "%d,%s,%s,%.6f,%.6f,%.2f,%.2f,%.2f,%.2f,true,%d,%d,%.2f,%.2f,%.2f,%.2f,%.2f,%.2f,%.2f,Normal\n", year, p.id.c_str(), kCsvGenNames[t],
+                     lon, lat, power, 0.99 * 100.0, 100.0 * 100.0, co2, p.commissioning, p.commissioning + 25, size * 100.0, capital, operating,
+                     capital + operating, kDefReliability[t], planning, construction);
+      }
+    }
+    std::fclose(f);
+  }
+  {  // yearly_details/carbon_offsets.csv, csv_export.rs:987-1093
+    // The exporter rebuilds the offsets on a copy of the base map, whose construction delays are on and whose clock stands
+    // at 2024 (multi_simulation.rs:862-888, map_handler.rs:785-811): every offset is still `Planned` when the rows are
+    // written, so calc_carbon_offset is 0 in every year and the size column, derived from it (:1353-1366), is 0 as well.
+    // Coordinates are thread_rng draws there (actions.rs:142-144); here a Philox stream keyed by the offset's position.
+    std::FILE* f = std::fopen((dir + "/yearly_details/carbon_offsets.csv").c_str(), "w");
+    if (!f) return eg_fail(EG_ERR_IO, "cannot write carbon_offsets.csv in " + dir);
+    std::fprintf(f, "Year,Offset ID,Type,X,Y,Size,Capture Efficiency (%%),Power Consumption (MW),CO2 Offset (tonnes),Negative CO2 Emissions (tonnes),"
+                    "Cost (\xE2\x82\xAC),Operating Cost (\xE2\x82\xAC),Total Annual Cost (\xE2\x82\xAC),Cost Per Tonne (\xE2\x82\xAC)\n");
+    static const double kOffOperating[EG_N_OFFSET_TYPES] = {10000.0, 15000.0, 100000.0, 5000.0};
+    static const double kOffOpTrend[EG_N_OFFSET_TYPES] = {1.0, 1.01, 0.97, 1.02};
+    struct Offset { std::string id; int type, year, mult; double x, y; };
+    std::vector<Offset> offs;
+    for (int y = 0; y < EG_NY; y++)
+      for (int i = traj.n_deficit[y]; i < traj.n_deficit[y] + traj.n_additional[y]; i++) {
+        const int a = traj.actions[y][i];
+        if (a < 45 || a >= 57) continue;
+        const int o = (a - 45) / 3, year = EG_BASE_YEAR + y;
+        Offset r{std::string("Offset_") + kCsvOffsetNames[o] + "_" + std::to_string(year) + "_" + std::to_string(offs.size()), o, year, (a - 45) % 3, 0, 0};
+        r.x = csv_uniform((uint32_t)offs.size(), 0) * 50000.0;
+        r.y = csv_uniform((uint32_t)offs.size(), 1) * 50000.0;
+        offs.push_back(r);
+      }
+    auto powi = [](double a, int b) { double r = 1.0; for (;;) { if (b & 1) r *= a; b /= 2; if (b == 0) break; a *= a; } return r; };
+    for (int y = 0; y < EG_NY; y++) {
+      const int year = EG_BASE_YEAR + y;
+      for (const Offset& r : offs) {
+        if (year < r.year) continue;
+        const double lon = -10.6 + ((-5.9 - -10.6) * (r.x / 50000.0)), lat = 51.4 + ((55.4 - 51.4) * (r.y / 50000.0));
+        const double cost = (T.off_base_cost[r.type] * powi(1.0 + 0.0185, y)) * T.mult[r.mult];                       // carbon_offset.rs:188-195
+        const double operating = kOffOperating[r.type] * T.year[y].inflation * std::pow(kOffOpTrend[r.type], (double)y);  // :197-209
+        std::fprintf(f, "%d,%s,%s,%.6f,%.6f,0,%.2f,%s,0.00,-0.00,%.2f,%.2f,%.2f,0.00\n", year, r.id.c_str(), kCsvOffsetNames[r.type], lon, lat,
+                     0.85 * 100.0, r.type == 2 ? "50" : "0", cost, operating, cost + operating);
+      }
+    }
+    std::fclose(f);
+  }
+  {  // operation_logs/generator_operation_logs.csv, csv_export.rs:1096-1310: the year loop there runs over
+     // commissioning_year..=min(eol, 2050) with eol a lifespan (25..60 years), an empty range, so only the header is written
+    if (!mkdir_p(dir + "/operation_logs")) return eg_fail(EG_ERR_IO, "cannot create " + dir + "/operation_logs");
+    std::FILE* f = std::fopen((dir + "/operation_logs/generator_operation_logs.csv").c_str(), "w");
+    if (!f) return eg_fail(EG_ERR_IO, "cannot write generator_operation_logs.csv in " + dir);
+    std::fprintf(f, "Year,Month,Day,Hour,Generator ID,Type,Power Output (MW),Operation %%,Actual Output (MW),Weather Factor,CO2 Emissions (tonnes)\n");
     std::fclose(f);
   }
   if (written_dir) std::snprintf(written_dir, 512, "%s", dir.c_str());

@@ -136,6 +136,8 @@ std::string trim(const std::string& s) {
 
 }  // namespace
 
+void eg_host_tech_durations(int type, int year, double* planning, double* construction) { tech_durations(type, year, planning, construction); }
+
 int eg_host_map_load(EgHostMap* m, const char* settlements_json, const char* generators_csv, const char* coastline_json) {
   *m = EgHostMap();
   std::string text;
@@ -318,6 +320,7 @@ void eg_host_build_tables(const EgHostMap& m, EgHostTables* out) {
     size[g] = normalized_size(m.ecap[g], m.etype[g]);
   }
   std::vector<int> status(E, 0), start(E, 0);  // 0 Planned, 1 Granted, 2 UnderConstruction, 3 Operational
+  out->ex_online_year.assign(E, 0);
   for (int y = 0; y < EG_NY; y++) {
     const int year = EG_BASE_YEAR + y;
     EgYearRow& row = T.year[y];
@@ -325,6 +328,7 @@ void eg_host_build_tables(const EgHostMap& m, EgHostTables* out) {
       if (status[g] == 0) { if ((double)(year - 2024) >= planning[g]) status[g] = 1; }
       else if (status[g] == 1) { status[g] = 2; start[g] = year; }
       else if (status[g] == 2) { if ((double)(year - start[g]) >= construction[g]) status[g] = 3; }
+      if (status[g] == 3 && !out->ex_online_year[g]) out->ex_online_year[g] = year;
     }
     double usage = 0.0;
     uint32_t pop_total = 0;

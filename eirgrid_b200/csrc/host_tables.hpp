@@ -25,9 +25,12 @@ struct EgHostTables {
   int r2_stride = 0;
   int kmax = 0;
   int near_wide = 0;                 // coordinates above 127 or a factor table too large for shared memory
+  std::vector<int> ex_online_year;   // first year in which each pre-existing plant is Operational (quirk Q1); 0 = never
 };
 
 int eg_host_map_load(EgHostMap* m, const char* settlements_json, const char* generators_csv, const char* coastline_json);
 int eg_host_map_set(EgHostMap* m, const eg_map_desc* d);
 int eg_host_map_validate(const EgHostMap& m);
 void eg_host_build_tables(const EgHostMap& m, EgHostTables* out);
+// planning_duration / construction_duration of config/tech_type.rs:70-200 for a generator type registered in `year`
+void eg_host_tech_durations(int type, int year, double* planning, double* construction);

@@ -303,8 +303,13 @@ int eg_update_combine_apply(eg_weights* w, const int64_t* stats_sum, const void*
  *   <output_dir>/<%Y%m%d_%H%M%S>/simulation_summary.csv     final metrics, actions taken with estimated costs, yearly summary
  *   <output_dir>/<%Y%m%d_%H%M%S>/improvement_history.csv    the weights' improvement history
  *   <output_dir>/<%Y%m%d_%H%M%S>/yearly_details/settlements.csv
- * in the reference's column order and number formats. generators.csv, carbon_offsets.csv and the operation logs of the
- * reference's exporter are NOT written (per-plant lifetime/operating-cost bookkeeping is off the hot path, Appendix B).
+ *   <output_dir>/<%Y%m%d_%H%M%S>/yearly_details/generators.csv       csv_export.rs:532-984: one row per active plant and year
+ *   <output_dir>/<%Y%m%d_%H%M%S>/yearly_details/carbon_offsets.csv   csv_export.rs:987-1093
+ *   <output_dir>/<%Y%m%d_%H%M%S>/operation_logs/generator_operation_logs.csv   csv_export.rs:1096-1310 (header only, as there)
+ * in the reference's column order and number formats, including what its exporter actually does with them: plant rows are
+ * rebuilt from the ids with per-type default figures and id-hash coordinates, offsets are still `Planned` on the export
+ * map so their offset columns are 0 (DESIGN.md §9 N2 lists these). Row order inside a year (HashMap order in the reference)
+ * is plant order; offset coordinates (thread_rng there) come from a fixed Philox stream.
  * `written_dir` (nullable, >= 512 bytes) receives the directory. Returns EG_ERR_STATE if `w` has no best strategy. */
 int eg_export_best_run_csv(eg_ctx* ctx, const eg_weights* w, const eg_run_cfg* cfg, const char* output_dir, char* written_dir);
 
