@@ -184,3 +184,25 @@ def test_rollout_stagnation_branch(gpu_ctx, oracle_world):
         assert traj.tobytes() == etraj.tobytes()
         assert sites.tobytes() == esites.tobytes()
         assert_results_equal(res, eres)
+
+
+def test_batch_shape_edge_cases(gpu_ctx, oracle_world):
+    """Empty, single-episode and ragged batch sizes (not a multiple of the 4 warps of a block or of the grid), and a batch
+    split at arbitrary points: an episode's outputs depend on (seed, episode id) only, never on the batch around it."""
+    gw = _lib.Weights()
+    n = 777
+    res, traj, sites, yearly = gpu_ctx.rollout(gw, n, seed=55, first_episode=1000, want_sites=True, want_yearly=True)
+    eres, etraj, esites, _ = oracle_world.rollout(O.Weights(), n, seed=55, first_episode=1000)
+    assert traj.tobytes() == etraj.tobytes() and sites.tobytes() == esites.tobytes()
+    assert_results_equal(res, eres)
+    r0, t0, _, _ = gpu_ctx.rollout(gw, 0, seed=55)
+    assert len(r0) == 0 and len(t0) == 0
+    for first, cnt in ((0, 1), (1, 3), (4, 33), (37, 131), (168, 609)):
+        r, t, s, yr = gpu_ctx.rollout(gw, cnt, seed=55, first_episode=1000 + first, want_sites=True, want_yearly=True)
+        assert t.tobytes() == traj[first:first + cnt].tobytes() and s.tobytes() == sites[first:first + cnt].tobytes()
+        assert r.tobytes() == res[first:first + cnt].tobytes() and yr.tobytes() == yearly[first:first + cnt].tobytes()
+    rr, ss, yy = gpu_ctx.replay(traj[5:6])
+    assert ss.tobytes() == sites[5:6].tobytes() and yy.tobytes() == yearly[5:6].tobytes()
+    assert_results_equal(rr, res[5:6])
+    r_empty, s_empty, _ = gpu_ctx.replay(traj[:0])
+    assert len(r_empty) == 0
