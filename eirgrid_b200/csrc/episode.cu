@@ -911,20 +911,31 @@ cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
   while (warps > 1 && warps * slice + shared_tab > 100 * 1024) warps >>= 1;
   const size_t smem_bytes = (size_t)warps * slice + shared_tab;
   if (smem_bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
-  cudaError_t err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  // function attributes and the occupancy query are per (device, shared-memory size): done once, then cached
+  struct Shape { size_t smem = 0; int resident = 0; };
+  static thread_local Shape cache[64];
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
   if (err != cudaSuccess) return err;
-  // shared-memory carveout: room for as many blocks as the register budget allows, the rest stays L1
-  const int resident_want = (int)std::min<size_t>(EG_EPISODE_MIN_BLOCKS * (EG_EPISODE_WARPS / warps), (227 * 1024) / (smem_bytes + 1024));
-  const int carveout = std::min(100, (int)((resident_want * (smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
-  cudaFuncSetAttribute(eg_episode_kernel<REPLAY, WIDE>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
-  // grid = every block the device can hold at once (a multiple of the SM count), never more warps than episodes
-  int dev = 0, sms = 0, per_sm = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eg_episode_kernel<REPLAY, WIDE>, 32 * warps, smem_bytes);
-  if (err != cudaSuccess) return err;
-  if (per_sm < 1) return cudaErrorInvalidConfiguration;
-  uint32_t blocks = std::min<uint32_t>((uint32_t)(sms * per_sm), (p.n + warps - 1) / warps);
+  Shape local;
+  Shape& shape = (dev >= 0 && dev < 64) ? cache[dev] : local;
+  if (shape.smem != smem_bytes || shape.resident == 0) {
+    err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (err != cudaSuccess) return err;
+    // shared-memory carveout: room for as many blocks as the register budget allows, the rest stays L1
+    const int resident_want = (int)std::min<size_t>(EG_EPISODE_MIN_BLOCKS * (EG_EPISODE_WARPS / warps), (227 * 1024) / (smem_bytes + 1024));
+    const int carveout = std::min(100, (int)((resident_want * (smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
+    cudaFuncSetAttribute(eg_episode_kernel<REPLAY, WIDE>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+    // grid = every block the device can hold at once (a multiple of the SM count), never more warps than episodes
+    int sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eg_episode_kernel<REPLAY, WIDE>, 32 * warps, smem_bytes);
+    if (err != cudaSuccess) return err;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    shape.smem = smem_bytes;
+    shape.resident = sms * per_sm;
+  }
+  uint32_t blocks = std::min<uint32_t>((uint32_t)shape.resident, (p.n + warps - 1) / warps);
   if (blocks == 0) return cudaErrorInvalidConfiguration;
   err = cudaMemsetAsync(p.next_episode, 0, sizeof(uint32_t), stream);
   if (err != cudaSuccess) return err;
