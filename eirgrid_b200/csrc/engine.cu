@@ -19,7 +19,7 @@
 #include "suitability.cuh"
 #include "weights.hpp"
 
-static_assert(sizeof(EgPolicyDevice) == 38792, "bench.py and eirgrid_b200/_abi.py quote this size");
+static_assert(sizeof(EgPolicyDevice) == 38800, "bench.py and eirgrid_b200/_abi.py quote this size");
 static thread_local std::string g_last_error;
 int eg_fail(int code, const std::string& message) {
   g_last_error = message;

@@ -579,9 +579,7 @@ struct Warp {
       return smart_fallback_pick(y, index(smart_fallback_total(y)));
     }
     const uint32_t iwi = p.policy->iwi;
-    const double eps = p.policy->exploration_rate;
-    const double cur_eps = iwi > 100 ? eps * ddiv(1.0, 1.0 + 0.01 * (double)iwi) : eps;
-    const bool explore = f64() < cur_eps;
+    const bool explore = f64() < p.policy->action_exploration;  // exploration_rate / (1 + 0.01 iwi) once iwi > 100, per snapshot
     if (explore) return (int)index(EG_N_ACTIONS);
     const double* lw = LW(y);
     double total;

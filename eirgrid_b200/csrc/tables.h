@@ -88,6 +88,7 @@ struct EgPolicyDevice {   // weights snapshot + the per-batch constants of updat
   double rows[EG_NY][EG_POLICY_ROW];
   double learning_rate;
   double exploration_rate;
+  double action_exploration;      // sample_action's rate: exploration_rate / (1 + 0.01 iwi) once iwi > 100 (sampling.rs:150-156)
   double relative_improvement;    // learning.rs:40-49 (0 whenever a best strategy with positive score exists)
   // stagnation branch of sample_action (sampling.rs:190-220), evaluated per snapshot with the host libm
   double stagnation_power;        // 1 + 2 * min(iwi / 1000, 3)

@@ -358,6 +358,7 @@ void eg_weights_fill_policy(const eg_weights& W, EgPolicyDevice* out) {
   }
   out->learning_rate = W.learning_rate;
   out->exploration_rate = W.exploration_rate;
+  out->action_exploration = W.iwi > 100 ? W.exploration_rate * (1.0 / (1.0 + 0.01 * (double)W.iwi)) : W.exploration_rate;
   // update_weights (learning.rs:36-49): final_impact_score and best_score are both score(best_metrics)
   double rel = 0.0;
   if (W.has_best) {
