@@ -32,3 +32,24 @@ h = hashlib.sha1(d_res.cpu().numpy().tobytes() + d_traj.cpu().numpy().tobytes())
 times.sort()
 print("%-20s n=%d  min %.3f ms  median %.3f ms  -> %.2f M episodes/s  sha %s" % (
     os.environ.get("EIRGRID_LIB_NAME", "default"), n, times[0], times[len(times) // 2], n / times[len(times) // 2] / 1e3, h))
+
+# the same on the table the end-to-end steps train (3 batch-rule steps: stagnation counter far above 500)
+from eirgrid_b200 import trainer as T  # noqa: E402
+ctx.close()
+tr = T.BatchTrainer(n, seed=20250101, device=0, asset_dir=os.path.join(ROOT, "tests", "golden", "ireland_map"))
+for _ in range(3):
+    tr.step()
+tr.upload_weights()
+times = []
+for r in range(reps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(tr.stream)
+    tr.launch_rollout(first_episode=10_000_000)
+    e1.record(tr.stream)
+    tr.stream.synchronize()
+    times.append(e0.elapsed_time(e1))
+res, traj = tr.fetch_results()
+h = hashlib.sha1(res.tobytes() + traj.tobytes()).hexdigest()[:12]
+times.sort()
+print("%-20s trained table     min %.3f ms  median %.3f ms  -> %.2f M episodes/s  sha %s" % (
+    os.environ.get("EIRGRID_LIB_NAME", "default"), times[0], times[len(times) // 2], n / times[len(times) // 2] / 1e3, h))
