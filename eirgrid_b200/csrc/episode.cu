@@ -95,7 +95,12 @@ struct State {  // ActionResult, ai/metrics/simulation_metrics.rs:14-19
 
 // evaluate_action_impact(.., None), scoring.rs:60-84
 __device__ __forceinline__ double action_impact(const State& cur, const State& nw) {
-  if (cur.net > 0.0) return ddiv(cur.net - nw.net, fmax(fabs(cur.net), 1.0));
+  if (cur.net > 0.0) {
+    // a plant without CO2 leaves the emissions unchanged: +0 / x = +0, without the division (whose hardware sequence
+    // takes its ~100-instruction slow path for a zero numerator)
+    const double reduction = cur.net - nw.net;
+    return reduction == 0.0 ? reduction : ddiv(reduction, fmax(fabs(cur.net), 1.0));
+  }
   double cost_change = nw.cost - cur.cost;
   double cost_improvement = ddiv(-cost_change, fmax(fabs(cur.cost), 1.0));
   double opinion_improvement = ddiv(nw.opinion - cur.opinion, fmax(fabs(cur.opinion), 1.0));
@@ -510,9 +515,16 @@ struct Warp {
     const double rel = p.policy->relative_improvement;
     const double immediate = rel > 0.0 ? 0.7 : 0.3;
     const double combined = immediate * improvement + (1.0 - immediate) * rel;
+    double* lw = LW(y);
+    if (combined == 0.0) {
+      // adjustment = 1 / (1 + 0) = 1 and nobody is boosted: the row keeps its values (any weight inside the clamp range,
+      // as every weight the rules produce is), and stays clean, so the snapshot's totals and sorted row remain valid.
+      // The common case: a plant without CO2 built while emissions are above zero has impact 0 (scoring.rs:60-66).
+      const double w0 = lw[action];
+      if (w0 >= kMinWeight && w0 <= kMaxWeight) return;
+    }
     const double adj = combined > 0.0 ? 1.0 + (lr * combined) : ddiv(1.0, 1.0 + (lr * fabs(combined)));
     const double boost = 1.0 + (lr * 0.1);
-    double* lw = LW(y);
     for (int k = lane; k < EG_N_ACTIONS; k += 32) {
       if (k == action) lw[k] = fmin(fmax(lw[k] * adj, kMinWeight), kMaxWeight);
       else if (combined < 0.0 && k < 45) lw[k] = fmin(lw[k] * boost, kMaxWeight);
@@ -838,7 +850,8 @@ struct Warp {
     double score;
     {
       const double normalized_cost = fmax(ddiv(r_cost, kMaxAcceptableCost), 1.0);
-      const double cost_term = fmin(ddiv(log(normalized_cost), p.ln100), 1.0);
+      // ln(1) = 0 whenever the cost is within budget: no logarithm and no zero-numerator division then
+      const double cost_term = normalized_cost == 1.0 ? 0.0 : fmin(ddiv(log(normalized_cost), p.ln100), 1.0);
       if (p.cost_only) score = 2.0 - cost_term;
       else if (r_net > 0.0) score = 1.0 - fmin(ddiv(r_net, kMaxAcceptableEmissions), 1.0);
       else {
