@@ -40,6 +40,7 @@ struct eg_ctx {
   uint64_t launches = 0;
   bool map_ready = false;
   bool policy_ready = false;
+  bool policy_count_weights = false;
   EgHostMap hmap;
   EgHostTables htab;
   // device memory
@@ -213,6 +214,7 @@ EgEpisodeParams make_params(const eg_ctx* c, const eg_run_cfg* cfg, uint64_t see
   p.energy_sales = cfg->enable_energy_sales;
   p.same_stream = cfg->same_stream_all_episodes;
   p.replay_best = cfg->replay_best;
+  p.count_weights = c->policy_count_weights ? 1u : 0u;
   p.ln100 = std::log(50000000000.0 * 100.0 / 50000000000.0);
   p.next_episode = c->d_next_episode;
   p.nf_entries = c->htab.r2_limit[2 * EG_N_RCLASS];
@@ -337,6 +339,7 @@ int eg_weights_upload(eg_ctx* c, const eg_weights* w) {
   EG_CUDA(cudaMemcpyAsync(c->d_policy, &pol, sizeof(pol), cudaMemcpyHostToDevice, c->stream));
   EG_CUDA(cudaStreamSynchronize(c->stream));
   c->policy_ready = true;
+  c->policy_count_weights = pol.has_count_weights != 0;
   return EG_OK;
 }
 

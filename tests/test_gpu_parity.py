@@ -195,6 +195,9 @@ def test_batch_shape_edge_cases(gpu_ctx, oracle_world):
     eres, etraj, esites, _ = oracle_world.rollout(O.Weights(), n, seed=55, first_episode=1000)
     assert traj.tobytes() == etraj.tobytes() and sites.tobytes() == esites.tobytes()
     assert_results_equal(res, eres)
+    # the launch without optional outputs runs the lean instantiation of the kernel: same episodes
+    rl, tl, _, _ = gpu_ctx.rollout(gw, n, seed=55, first_episode=1000)
+    assert tl.tobytes() == traj.tobytes() and rl.tobytes() == res.tobytes()
     r0, t0, _, _ = gpu_ctx.rollout(gw, 0, seed=55)
     assert len(r0) == 0 and len(t0) == 0
     for first, cnt in ((0, 1), (1, 3), (4, 33), (37, 131), (168, 609)):
