@@ -41,6 +41,7 @@ struct eg_ctx {
   bool map_ready = false;
   bool policy_ready = false;
   bool policy_count_weights = false;
+  bool policy_stagnation = false;
   EgHostMap hmap;
   EgHostTables htab;
   // device memory
@@ -215,6 +216,7 @@ EgEpisodeParams make_params(const eg_ctx* c, const eg_run_cfg* cfg, uint64_t see
   p.same_stream = cfg->same_stream_all_episodes;
   p.replay_best = cfg->replay_best;
   p.count_weights = c->policy_count_weights ? 1u : 0u;
+  p.stagnation = c->policy_stagnation ? 1u : 0u;
   p.ln100 = std::log(50000000000.0 * 100.0 / 50000000000.0);
   p.next_episode = c->d_next_episode;
   p.nf_entries = c->htab.r2_limit[2 * EG_N_RCLASS];
@@ -340,6 +342,7 @@ int eg_weights_upload(eg_ctx* c, const eg_weights* w) {
   EG_CUDA(cudaStreamSynchronize(c->stream));
   c->policy_ready = true;
   c->policy_count_weights = pol.has_count_weights != 0;
+  c->policy_stagnation = pol.iwi > 500;
   return EG_OK;
 }
 

@@ -193,11 +193,14 @@ __device__ __forceinline__ int deficit_key_action(int k) {
   return 3 * (int)((0xED325A4109BC78ull >> (4 * k)) & 0xF);
 }
 
-// LEAN: the training launch — no optional outputs (eg_sites, eg_yearly), no replay-best mode, count weights present;
-// EG_OPT(x) is x in the general instantiation and false in the lean one
+// MODE 0: every option decided at run time. MODE 1, 2: the training launch — no optional outputs (eg_sites, eg_yearly),
+// no replay-best mode, count weights present — with the plain sampler (iterations_without_improvement <= 500) or the
+// stagnation sampler (> 500) compiled in alone. EG_OPT(x) is x in the general instantiation and false in the lean ones.
 #define EG_OPT(x) (!LEAN && (x))
-template <bool REPLAY, bool WIDE, bool LEAN>
+template <bool REPLAY, bool WIDE, int MODE>
 struct Warp {
+  static constexpr bool LEAN = MODE != 0;
+  __device__ __forceinline__ bool stagnation() const { return MODE == 0 ? p.policy->iwi > 500 : MODE == 2; }
   const EgEpisodeParams& p;
   const EgSmallTables* __restrict__ T;
   const int lane;
@@ -490,7 +493,7 @@ struct Warp {
     if (y + 1 < EG_NY) prefetch_rows(y + 1);
 #endif
     rows_dirty = false; dw_dirty = false; sorted_valid = false; total_valid = false;
-    if (p.policy->iwi > 500) {  // the snapshot's sorted, scaled row of this year (host libm) for the stagnation sampler
+    if (stagnation()) {  // the snapshot's sorted, scaled row of this year (host libm) for the stagnation sampler
       double* scl = (double*)(smem + sb + kOffScratch);
       for (int k = lane; k < EG_N_ACTIONS; k += 32) scl[k] = __ldg(&p.policy->scaled_sorted[y][k]);
       ((uint16_t*)(smem + sb + kOffSortIdx))[lane] = __ldg((const uint16_t*)p.policy->sorted_idx[y] + lane);
@@ -593,7 +596,6 @@ struct Warp {
       if (p.policy->has_best && *replay_pos < p.policy->n_best[y]) return p.policy->best[y][(*replay_pos)++];
       return smart_fallback_pick(y, index(smart_fallback_total(y)));
     }
-    const uint32_t iwi = p.policy->iwi;
     const bool explore = f64() < p.policy->action_exploration;  // exploration_rate / (1 + 0.01 iwi) once iwi > 100, per snapshot
     if (explore) return (int)index(EG_N_ACTIONS);
     const double* lw = LW(y);
@@ -612,7 +614,7 @@ struct Warp {
       total = __ldg(&p.policy->w_total[y]);
     }
     if (total <= 0.0) return kGasPeaker100;
-    if (iwi > 500) {
+    if (stagnation()) {
       // stagnation branch (sampling.rs:190-220): weights^power in stable descending order. The sorted row lives in the
       // scratch area: copied from the host-built snapshot row at the start of the year (load_rows), rebuilt on the
       // device after this episode edited the year's weights (sort_local).
@@ -892,7 +894,7 @@ struct Warp {
   }
 };
 
-template <bool REPLAY, bool WIDE, bool LEAN>
+template <bool REPLAY, bool WIDE, int MODE>
 __global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) eg_episode_kernel(const __grid_constant__ EgEpisodeParams p, int slice_bytes, int table_bytes) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (!WIDE) {  // block-shared copy of the distance/radius factors at the start of the shared memory
@@ -903,7 +905,7 @@ __global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) 
     }
     __syncthreads();
   }
-  Warp<REPLAY, WIDE, LEAN> w(p, opaque((uint32_t)(table_bytes + warp * slice_bytes)), lane);
+  Warp<REPLAY, WIDE, MODE> w(p, opaque((uint32_t)(table_bytes + warp * slice_bytes)), lane);
   // persistent warps: every warp fetches the next unclaimed episode of the batch until none is left, so a short
   // episode never leaves its warp idle while the block's longest one finishes
   for (;;) {
@@ -915,7 +917,7 @@ __global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) 
   }
 }
 
-template <bool REPLAY, bool WIDE, bool LEAN>
+template <bool REPLAY, bool WIDE, int MODE>
 cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
   const bool wide = WIDE;
   const int slice = kSliceBytes;
@@ -934,16 +936,16 @@ cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
   Shape local;
   Shape& shape = (dev >= 0 && dev < 64) ? cache[dev] : local;
   if (shape.smem != smem_bytes || shape.resident == 0) {
-    err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, WIDE, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, WIDE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
     // shared-memory carveout: room for as many blocks as the register budget allows, the rest stays L1
     const int resident_want = (int)std::min<size_t>(EG_EPISODE_MIN_BLOCKS * (EG_EPISODE_WARPS / warps), (227 * 1024) / (smem_bytes + 1024));
     const int carveout = std::min(100, (int)((resident_want * (smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
-    cudaFuncSetAttribute(eg_episode_kernel<REPLAY, WIDE, LEAN>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+    cudaFuncSetAttribute(eg_episode_kernel<REPLAY, WIDE, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
     // grid = every block the device can hold at once (a multiple of the SM count), never more warps than episodes
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eg_episode_kernel<REPLAY, WIDE, LEAN>, 32 * warps, smem_bytes);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eg_episode_kernel<REPLAY, WIDE, MODE>, 32 * warps, smem_bytes);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     shape.smem = smem_bytes;
@@ -953,7 +955,7 @@ cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
   if (blocks == 0) return cudaErrorInvalidConfiguration;
   err = cudaMemsetAsync(p.next_episode, 0, sizeof(uint32_t), stream);
   if (err != cudaSuccess) return err;
-  eg_episode_kernel<REPLAY, WIDE, LEAN><<<blocks, 32 * warps, smem_bytes, stream>>>(p, slice, shared_tab);
+  eg_episode_kernel<REPLAY, WIDE, MODE><<<blocks, 32 * warps, smem_bytes, stream>>>(p, slice, shared_tab);
   return cudaGetLastError();
 }
 
@@ -963,9 +965,11 @@ cudaError_t launch(const EgEpisodeParams& p, cudaStream_t stream) {
   // the training launch (no per-year or per-site outputs, sampling from the weights, count weights present) runs a lean
   // instantiation without the code of those options: the kernel is bound by instruction fetch, and 8 KB of code that
   // never executes still spreads the hot instructions over more cache lines (-10 % time on trained tables)
-  if (!REPLAY && !p.yearly && !p.sites && !p.replay_best && p.count_weights)
-    return p.map.near_wide ? launch_as<false, true, true>(p, stream) : launch_as<false, false, true>(p, stream);
-  return p.map.near_wide ? launch_as<REPLAY, true, false>(p, stream) : launch_as<REPLAY, false, false>(p, stream);
+  if (!REPLAY && !p.yearly && !p.sites && !p.replay_best && p.count_weights) {
+    if (p.stagnation) return p.map.near_wide ? launch_as<false, true, 2>(p, stream) : launch_as<false, false, 2>(p, stream);
+    return p.map.near_wide ? launch_as<false, true, 1>(p, stream) : launch_as<false, false, 1>(p, stream);
+  }
+  return p.map.near_wide ? launch_as<REPLAY, true, 0>(p, stream) : launch_as<REPLAY, false, 0>(p, stream);
 }
 
 }  // namespace

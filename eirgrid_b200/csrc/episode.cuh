@@ -20,6 +20,7 @@ struct EgEpisodeParams {
   uint32_t energy_sales;
   uint32_t same_stream;
   uint32_t replay_best;
+  uint32_t stagnation;           // host copy of EgPolicyDevice::iwi > 500 (which sampler the lean instantiation carries)
   uint32_t count_weights;        // the uploaded policy has action-count weights (host copy of EgPolicyDevice::has_count_weights)
   double ln100;                  // ln(MAX_ACCEPTABLE_COST*100/MAX_ACCEPTABLE_COST), host libm (scoring.rs:13,32)
 };
