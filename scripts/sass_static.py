@@ -1,12 +1,13 @@
 #!/usr/bin/env python3
 """Static SASS size of the rollout kernel per device function / source line of episode.cu (needs -lineinfo).
 
-    python scripts/sass_static.py [lib.so] [--lines N]
+    python scripts/sass_static.py [lib.so] [--lines N] [--mode 0|1|2]
 """
 import collections, os, re, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else os.path.join(ROOT, "eirgrid_b200", "libeirgrid_b200.so")
 nlines = int(sys.argv[sys.argv.index("--lines") + 1]) if "--lines" in sys.argv else 25
+MODE = sys.argv[sys.argv.index("--mode") + 1] if "--mode" in sys.argv else "1"  # 0 general, 1 lean/plain sampler, 2 lean/stagnation sampler
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.startswith("episode")][0]
@@ -27,7 +28,7 @@ cnt, byfn, on, line = collections.Counter(), collections.Counter(), False, None
 for l in dis.split("\n"):
     s = l.strip()
     if s.startswith(".text."):
-        on = "eg_episode_kernelILb0ELb0EE" in s
+        on = ("eg_episode_kernelILb0ELb0ELi%sEE" % MODE) in s
     m = re.match(r'//## File "([^"]+)", line (\d+)', s)
     if m:
         line = (os.path.basename(m.group(1)), int(m.group(2)))
