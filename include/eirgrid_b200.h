@@ -240,7 +240,9 @@ int eg_rollout_batch(eg_ctx* ctx, const eg_weights* w, const eg_run_cfg* cfg, ui
                      uint64_t first_episode, uint32_t n, eg_result* out, eg_traj* traj_out,
                      eg_sites* sites_out, eg_yearly* yearly_out);
 /* Same with DEVICE output buffers, asynchronous on the ctx stream (inputs resident: the weights
- * snapshot is uploaded by eg_weights_upload). */
+ * snapshot is uploaded by eg_weights_upload). A call with d_sites == d_yearly == NULL, replay_best == 0 and a snapshot
+ * that has count weights (every ActionWeights::new / reference checkpoint has) runs the lean instantiation of the
+ * kernel, 10-30 % faster than the general one; results are identical either way. */
 int eg_weights_upload(eg_ctx* ctx, const eg_weights* w);
 int eg_rollout_batch_device(eg_ctx* ctx, const eg_run_cfg* cfg, uint64_t seed, uint64_t first_episode,
                             uint32_t n, eg_result* d_out, eg_traj* d_traj, eg_sites* d_sites, eg_yearly* d_yearly);
