@@ -190,16 +190,34 @@ struct Recorded {
 
 struct UpdateRng {  // Philox4x32-10 stream for the randomisation branch (learning.rs:267-280,358-370)
   uint32_t k0, k1, c0, draw;
-  double f64() {
-    uint32_t a0 = c0, a1 = 0u, a2 = draw++, a3 = 0x55504454u, x0 = k0, x1 = k1;  // counter = (iteration, 0, draw, "UPDT")
+  // Draw d is the low 64 bits of Philox(counter = (iteration, 0, d, "UPDT"), key). The branch consumes ~2,000 draws per
+  // episode, one after the other; a single evaluation is a 10-round dependent chain, so draws are produced eight at a
+  // time with the rounds interleaved (same values, ~4x the throughput).
+  static constexpr int kBatch = 8;
+  double buf[kBatch];
+  uint32_t buf_first = 0, buf_count = 0;
+  void refill() {
+    uint32_t a0[kBatch], a1[kBatch], a2[kBatch], a3[kBatch];
+    for (int j = 0; j < kBatch; j++) { a0[j] = c0; a1[j] = 0u; a2[j] = draw + (uint32_t)j; a3[j] = 0x55504454u; }
+    uint32_t x0 = k0, x1 = k1;
     for (int r = 0; r < 10; r++) {
-      uint64_t p0 = (uint64_t)0xD2511F53u * a0, p1 = (uint64_t)0xCD9E8D57u * a2;
-      uint32_t n0 = (uint32_t)(p1 >> 32) ^ a1 ^ x0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ a3 ^ x1, n3 = (uint32_t)p0;
-      a0 = n0; a1 = n1; a2 = n2; a3 = n3;
+      for (int j = 0; j < kBatch; j++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * a0[j], p1 = (uint64_t)0xCD9E8D57u * a2[j];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ a1[j] ^ x0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ a3[j] ^ x1, n3 = (uint32_t)p0;
+        a0[j] = n0; a1[j] = n1; a2[j] = n2; a3[j] = n3;
+      }
       x0 += 0x9E3779B9u; x1 += 0xBB67AE85u;
     }
-    uint64_t u = (uint64_t)a0 | ((uint64_t)a1 << 32);
-    return (double)(u >> 11) * (1.0 / 9007199254740992.0);
+    for (int j = 0; j < kBatch; j++) {
+      const uint64_t u = (uint64_t)a0[j] | ((uint64_t)a1[j] << 32);
+      buf[j] = (double)(u >> 11) * (1.0 / 9007199254740992.0);
+    }
+    buf_first = draw;
+    buf_count = kBatch;
+  }
+  double f64() {
+    if (buf_count == 0 || draw - buf_first >= (uint32_t)kBatch) refill();
+    return buf[draw++ - buf_first];
   }
 };
 
