@@ -150,6 +150,10 @@ int eg_host_map_load(EgHostMap* m, const char* settlements_json, const char* gen
     for (const egjson::Value& s : list->arr) {
       const egjson::Value *lat = s.get("lat"), *lon = s.get("lon"), *pop = s.get("population");
       if (!lat || !lon || !pop) return eg_fail(EG_ERR_IO, "settlements.json: entry without lat/lon/population");
+      // SettlementData { lat: f64, lon: f64, population: u32 } (settlements_loader.rs:8-16): serde fails on other types
+      if (lat->kind != egjson::Value::Number || lon->kind != egjson::Value::Number || pop->kind != egjson::Value::Number ||
+          !(pop->num >= 0.0 && pop->num <= 4294967295.0) || pop->num != std::floor(pop->num))
+        return eg_fail(EG_ERR_IO, "settlements.json: lat/lon must be numbers and population a u32");
       double x, y;
       if (!lat_lon_to_grid(lat->num, lon->num, &x, &y)) continue;  // reference warns and skips (settlements_loader.rs:38-40)
       m->sx.push_back(x);

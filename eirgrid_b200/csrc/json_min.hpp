@@ -31,7 +31,7 @@ struct Value {
 
 class Parser {
  public:
-  explicit Parser(const std::string& text) : s_(text), i_(0) {}
+  explicit Parser(const std::string& text) : s_(text), i_(0), depth_(0) {}
   Value parse() {
     Value v = value();
     ws();
@@ -42,6 +42,12 @@ class Parser {
  private:
   const std::string& s_;
   size_t i_;
+  int depth_;  // nesting of the value being parsed; serde_json's recursion limit is 128
+  struct Nest {
+    Parser& p;
+    explicit Nest(Parser& q) : p(q) { if (++p.depth_ > 128) p.fail("recursion limit exceeded"); }
+    ~Nest() { p.depth_--; }
+  };
   [[noreturn]] void fail(const char* what) const {
     throw std::runtime_error(std::string("JSON parse error at byte ") + std::to_string(i_) + ": " + what);
   }
@@ -54,6 +60,7 @@ class Parser {
     char c = s_[i_];
     Value v;
     if (c == '{') {
+      Nest nest(*this);
       v.kind = Value::Object;
       i_++;
       ws();
@@ -72,6 +79,7 @@ class Parser {
         fail("expected ',' or '}'");
       }
     } else if (c == '[') {
+      Nest nest(*this);
       v.kind = Value::Array;
       i_++;
       ws();
@@ -93,12 +101,27 @@ class Parser {
     } else if (c == 'n' && s_.compare(i_, 4, "null") == 0) {
       i_ += 4;
     } else {
-      const char* start = s_.c_str() + i_;
-      char* end = nullptr;
-      v.num = std::strtod(start, &end);  // correctly rounded
-      if (end == start) fail("expected value");
+      // JSON number grammar only (strtod alone would also take "NaN", "inf", hex floats and a leading '+')
+      size_t j = i_;
+      if (j < s_.size() && s_[j] == '-') j++;
+      const size_t int_start = j;
+      while (j < s_.size() && s_[j] >= '0' && s_[j] <= '9') j++;
+      if (j == int_start) fail("expected value");
+      if (j < s_.size() && s_[j] == '.') {
+        const size_t frac_start = ++j;
+        while (j < s_.size() && s_[j] >= '0' && s_[j] <= '9') j++;
+        if (j == frac_start) fail("bad number");
+      }
+      if (j < s_.size() && (s_[j] == 'e' || s_[j] == 'E')) {
+        j++;
+        if (j < s_.size() && (s_[j] == '+' || s_[j] == '-')) j++;
+        const size_t exp_start = j;
+        while (j < s_.size() && s_[j] >= '0' && s_[j] <= '9') j++;
+        if (j == exp_start) fail("bad number");
+      }
+      v.num = std::strtod(s_.substr(i_, j - i_).c_str(), nullptr);  // correctly rounded
       v.kind = Value::Number;
-      i_ += (size_t)(end - start);
+      i_ = j;
     }
     return v;
   }

@@ -74,7 +74,7 @@ int read_action(const egjson::Value& v) {
       t = -1;
       for (int i = 0; i < EG_NT; i++)
         if (g->str == kGenNames[i]) t = i;
-      if (t < 0) return -1;
+      if (t < 0) return -3;  // unknown generator type: an error in the main table, skipped elsewhere
     }
     int m = mult_index();
     return m < 0 ? -1 : 3 * t + m;
@@ -134,15 +134,25 @@ void write_action_lists(std::string& o, const char* name, const std::vector<uint
   o += "  }";
 }
 
+// year keys are u32 in the reference's maps (HashMap<u32, _>): anything else fails the whole load there
+bool parse_year_key(const std::string& k, long long* year) {
+  if (k.empty() || k.size() > 10) return false;
+  for (char ch : k)
+    if (ch < '0' || ch > '9') return false;
+  *year = std::atoll(k.c_str());
+  return *year <= 4294967295ll;
+}
+
 bool read_weight_map(const egjson::Value* v, double* rows, int n_keys, bool deficit, bool* any) {
   if (!v || v->kind != egjson::Value::Object) return true;
   for (const auto& kv : v->obj) {
-    int year = std::atoi(kv.first.c_str());
+    long long year = 0;
+    if (!parse_year_key(kv.first, &year)) return false;
     if (year < EG_BASE_YEAR || year > EG_END_YEAR || kv.second.kind != egjson::Value::Array) continue;
     for (const egjson::Value& entry : kv.second.arr) {
       if (entry.kind != egjson::Value::Array || entry.arr.size() != 2) continue;
       int code = read_action(entry.arr[0]);
-      if (code == -2 && !deficit) return false;
+      if ((code == -2 || code == -3) && !deficit) return false;  // weights/serialization.rs:158-159,201-205
       if (code < 0) continue;
       int k = deficit ? deficit_key_of_action(code) : code;
       if (k < 0 || k >= n_keys) continue;
@@ -153,16 +163,18 @@ bool read_weight_map(const egjson::Value* v, double* rows, int n_keys, bool defi
   return true;
 }
 
-void read_action_lists(const egjson::Value* v, std::vector<uint8_t>* lists) {
-  if (!v || v->kind != egjson::Value::Object) return;
+bool read_action_lists(const egjson::Value* v, std::vector<uint8_t>* lists) {
+  if (!v || v->kind != egjson::Value::Object) return true;
   for (const auto& kv : v->obj) {
-    int year = std::atoi(kv.first.c_str());
+    long long year = 0;
+    if (!parse_year_key(kv.first, &year)) return false;
     if (year < EG_BASE_YEAR || year > EG_END_YEAR || kv.second.kind != egjson::Value::Array) continue;
     for (const egjson::Value& a : kv.second.arr) {
       int code = read_action(a);
       if (code >= 0) lists[year - EG_BASE_YEAR].push_back((uint8_t)code);
     }
   }
+  return true;
 }
 
 // the episode's recorded lists as the shared weights see them after transfer_recorded_actions_from
@@ -546,14 +558,18 @@ int eg_weights_load_json(const char* path, eg_weights** out) {  // load_from_fil
   } catch (const std::exception& ex) {
     return eg_fail(EG_ERR_IO, std::string(path) + ": " + ex.what());
   }
-  if (root.kind != egjson::Value::Object || !root.get("weights")) return eg_fail(EG_ERR_IO, std::string(path) + ": not a weights file");
+  if (root.kind != egjson::Value::Object || !root.get("weights") || root.get("weights")->kind != egjson::Value::Object)
+    return eg_fail(EG_ERR_IO, std::string(path) + ": not a weights file");
   eg_weights* W = new eg_weights();
   if (!read_weight_map(root.get("weights"), &W->w[0][0], EG_N_ACTIONS, false, nullptr)) {
     delete W;
-    return eg_fail(EG_ERR_IO, std::string(path) + ": unknown action type");
+    return eg_fail(EG_ERR_IO, std::string(path) + ": unknown action or generator type, or a year key that is not a u32");
   }
   // deficit weights default to the initial table when the file has none (weights/serialization.rs:266-283)
-  read_weight_map(root.get("deficit_weights"), &W->dw[0][0], EG_N_DEFICIT_KEYS, true, nullptr);
+  if (!read_weight_map(root.get("deficit_weights"), &W->dw[0][0], EG_N_DEFICIT_KEYS, true, nullptr)) {
+    delete W;
+    return eg_fail(EG_ERR_IO, std::string(path) + ": deficit_weights: a year key that is not a u32");
+  }
   if (const egjson::Value* v = root.get("learning_rate")) W->learning_rate = v->num;
   if (const egjson::Value* v = root.get("exploration_rate")) W->exploration_rate = v->num;
   if (const egjson::Value* v = root.get("iteration_count")) W->iteration_count = (uint32_t)v->num;
@@ -580,8 +596,11 @@ int eg_weights_load_json(const char* path, eg_weights** out) {  // load_from_fil
           if (code >= 0) W->best_weights[(size_t)(year - EG_BASE_YEAR) * EG_N_ACTIONS + code] = entry.arr[1].num;
         }
       }
-    read_action_lists(root.get("best_actions"), W->best_actions);
-    read_action_lists(root.get("best_deficit_actions"), W->best_deficit_actions);
+    if (!read_action_lists(root.get("best_actions"), W->best_actions) ||
+        !read_action_lists(root.get("best_deficit_actions"), W->best_deficit_actions)) {
+      delete W;
+      return eg_fail(EG_ERR_IO, std::string(path) + ": best actions: a year key that is not a u32");
+    }
   }
   const egjson::Value* hist = root.get("improvement_history");
   if (hist && hist->kind == egjson::Value::Array)

@@ -128,6 +128,33 @@ def test_load_errors_are_reported(tmp_path):
     assert t.deficit_weights[0][0] == 0.15  # defaults when the file has none (weights/serialization.rs:266-283)
 
 
+def test_malformed_weight_files_fail_like_serde(tmp_path):
+    """What serde_json + load_from_file (weights/serialization.rs:141-205) reject must be an error here too, never a crash:
+    truncated or non-JSON text, wrong types, non-JSON number tokens, nesting beyond serde's recursion limit, year keys
+    that are not u32, unknown action or generator types in the main table."""
+    good = tmp_path / "good.json"
+    _lib.Weights().save_to_file(str(good))
+    txt = good.read_text()
+    assert _lib.Weights.load_from_file(str(good)).table().weights[0][0] == 0.08
+    cases = {
+        "empty": "", "truncated": txt[: len(txt) // 2], "not_json": "hello", "wrong_type": '{"weights": 5}', "array": "[]",
+        "no_weights": "{}", "nan": txt.replace("0.08", "NaN", 1), "plus": txt.replace("0.08", "+0.08", 1),
+        "hex": txt.replace("0.08", "0x1p-3", 1), "negative_year": txt.replace('"2025"', '"-5"', 1),
+        "bad_action": txt.replace('"AddGenerator"', '"Explode"', 1), "bad_generator": txt.replace('"OnshoreWind"', '"Fusion"', 1),
+        "deep_array": "[" * 100000, "deep_object": '{"a":' * 100000,
+    }
+    for name, text in cases.items():
+        p = tmp_path / (name + ".json")
+        p.write_text(text)
+        with pytest.raises(_lib.EirgridError) as e:
+            _lib.Weights.load_from_file(str(p))
+        assert e.value.code == -2, name
+    # a year outside 2025..2050 is a valid u32 key: loaded and ignored, as the reference's map would hold it unused
+    far = tmp_path / "far_year.json"
+    far.write_text(txt.replace('"2025"', '"99999"', 1))
+    assert _lib.Weights.load_from_file(str(far)).table().weights[1][0] == 0.08
+
+
 def test_weight_history_file_is_what_the_animation_tool_reads(tmp_path, oracle_world):
     """save_weight_history (multi_simulation.rs:179-207): a JSON array of {iteration, timestamp, weights: to_json(), best_score};
     tools/visualization/weight_history_animation.py reads entry['weights']['weights'][year][action] and the learning rates."""
