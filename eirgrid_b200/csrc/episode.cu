@@ -689,7 +689,7 @@ struct Warp {
       double remaining = deficit_mode ? -cur.balance : 0.0;  // Map::handle_power_deficit returns it unchanged (Q2)
       uint32_t attempts = 0, n_def = 0, n_add = 0, n_to_add = 0, replay_def = 0, replay_act = 0;
       bool counted = false;
-      const uint32_t in_def = REPLAY ? in->n_deficit[y] : 0;
+      const uint32_t in_def = REPLAY ? min((uint32_t)in->n_deficit[y], (uint32_t)EG_MAX_ACTIONS_PER_YEAR) : 0;  // a malformed count never reads past the row
 
       for (;;) {
         int action;

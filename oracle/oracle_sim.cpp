@@ -269,7 +269,8 @@ void handle_power_deficit(EpMap& map, double deficit, int year, Weights& W, Rng&
     attempts += 1;
     uint8_t action;
     if (replay_in) {
-      action = replay_pos < replay_in->n_deficit[y] ? replay_in->actions[y][replay_pos] : (uint8_t)(3 * BatteryStorage);
+      // counts above the row capacity (malformed input) are read as the capacity
+      action = replay_pos < std::min<int>(replay_in->n_deficit[y], EG_MAX_ACTIONS_PER_YEAR) ? replay_in->actions[y][replay_pos] : (uint8_t)(3 * BatteryStorage);
       replay_pos++;
     } else if (attempts < 5) {
       action = sample_deficit_action(W, year, rng);
@@ -356,7 +357,7 @@ void run_episode(const World& world, Weights& W, const eg_run_cfg& cfg, uint64_t
     for (uint32_t i = 0; i < num_additional; i++) {
       uint8_t action;
       if (io.replay_in) {
-        int pos = io.replay_in->n_deficit[y] + (int)i;
+        int pos = std::min<int>(io.replay_in->n_deficit[y], EG_MAX_ACTIONS_PER_YEAR) + (int)i;
         action = pos < EG_MAX_ACTIONS_PER_YEAR ? io.replay_in->actions[y][pos] : (uint8_t)EG_ACT_DO_NOTHING;
       } else {
         action = sample_action(W, year, rng);
