@@ -27,6 +27,8 @@
 //    maintaining the map cost more than it saved — 20 % on the shipped map, 45 % on the 10x map — and it was removed.)
 //  * Philox draws are produced 32 at a time (lane l computes draw base+l) and handed out by shuffle.
 //  * Compiled with --fmad=false: + - * / sqrt are the reference's IEEE operations, no contraction.
+//  * The kernel is bound by instruction fetch as much as by issue: it is instantiated per (REPLAY, WIDE, MODE) so that the
+//    training launch runs an image without the optional outputs, the replay-best branches and the sampler it does not use.
 #include "episode.cuh"
 #include <algorithm>
 
