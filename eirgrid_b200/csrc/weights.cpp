@@ -187,12 +187,15 @@ struct Recorded {
       int nd = std::min<int>(t.n_deficit[y], EG_MAX_ACTIONS_PER_YEAR);
       int na = std::min<int>(t.n_additional[y], EG_MAX_ACTIONS_PER_YEAR - nd);
       // replay iterations record every sampled action twice (sampling.rs:97-99,262-264 + simulation.rs:197,406-409; quirk Q10)
+      // (codes outside the key set never come from the device; a malformed record must not index the tables with them)
       for (int i = 0; i < nd; i++) {
+        if (t.actions[y][i] >= EG_N_ACTIONS) continue;
         run[y].push_back(t.actions[y][i]);
         deficit[y].push_back(t.actions[y][i]);
         if (replay && i < 4) deficit[y].push_back(t.actions[y][i]);
       }
       for (int i = nd; i < nd + na; i++) {
+        if (t.actions[y][i] >= EG_N_ACTIONS) continue;
         run[y].push_back(t.actions[y][i]);
         if (replay) run[y].push_back(t.actions[y][i]);
       }
@@ -845,6 +848,8 @@ int eg_update_combine_apply(eg_weights* w, const int64_t* stats_sum, const void*
     if (!win || score > win_score || (score == win_score && id < win_id)) { win = p; win_score = score; win_id = id; }
   }
   if (!win) return eg_update_apply_stats(w, stats_sum, n_total, nullptr, nullptr, -1, stats_out);
+  if (n_total > 0 && (win_id < (int64_t)first_episode || (uint64_t)(win_id - (int64_t)first_episode) >= n_total))
+    return eg_fail(EG_ERR_INVALID, "eg_update_combine_apply: the winner record's episode id lies outside the batch");
   eg_result res;
   eg_traj traj;
   std::memcpy(&res, win + 16, sizeof(res));
