@@ -56,13 +56,22 @@ void write_action(std::string& o, int code, const std::string& ind) {
   o += ind + "}";
 }
 
+// a JSON number as the u32 the reference's struct declares (serde fails the load on anything else); a missing or null
+// value keeps the default
+bool number_as_u32(const egjson::Value* v, uint32_t* out) {
+  if (!v || v->is_null()) return true;
+  if (v->kind != egjson::Value::Number || !(v->num >= 0.0 && v->num <= 4294967295.0) || v->num != std::floor(v->num)) return false;
+  *out = (uint32_t)v->num;
+  return true;
+}
+
 // returns the action code or -1 for keys outside the closed key set (e.g. a 200 % multiplier)
 int read_action(const egjson::Value& v) {
   const egjson::Value* type = v.get("action_type");
   if (!type || type->kind != egjson::Value::String) return -1;
   auto mult_index = [&]() {
     const egjson::Value* m = v.get("cost_multiplier");
-    int pct = (m && m->kind == egjson::Value::Number) ? (int)m->num : 100;  // unwrap_or(DEFAULT_COST_MULTIPLIER)
+    int pct = (m && m->kind == egjson::Value::Number && m->num >= 0.0 && m->num <= 65535.0) ? (int)m->num : 100;  // unwrap_or(DEFAULT_COST_MULTIPLIER); u16
     for (int i = 0; i < EG_N_MULTS; i++)
       if (kMultPercent[i] == pct) return i;
     return -1;
@@ -575,8 +584,10 @@ int eg_weights_load_json(const char* path, eg_weights** out) {  // load_from_fil
   }
   if (const egjson::Value* v = root.get("learning_rate")) W->learning_rate = v->num;
   if (const egjson::Value* v = root.get("exploration_rate")) W->exploration_rate = v->num;
-  if (const egjson::Value* v = root.get("iteration_count")) W->iteration_count = (uint32_t)v->num;
-  if (const egjson::Value* v = root.get("iterations_without_improvement")) W->iwi = (uint32_t)v->num;
+  if (!number_as_u32(root.get("iteration_count"), &W->iteration_count) || !number_as_u32(root.get("iterations_without_improvement"), &W->iwi)) {
+    delete W;
+    return eg_fail(EG_ERR_IO, std::string(path) + ": iteration_count / iterations_without_improvement must be u32");
+  }
   if (const egjson::Value* v = root.get("optimization_mode"))
     if (v->kind == egjson::Value::String) W->optimization_mode = v->str;
   const egjson::Value* bm = root.get("best_metrics");
@@ -609,7 +620,7 @@ int eg_weights_load_json(const char* path, eg_weights** out) {  // load_from_fil
   if (hist && hist->kind == egjson::Value::Array)
     for (const egjson::Value& h : hist->arr) {
       EgImprovement r{};
-      if (const egjson::Value* v = h.get("iteration")) r.iteration = (uint32_t)v->num;
+      number_as_u32(h.get("iteration"), &r.iteration);
       if (const egjson::Value* v = h.get("score")) r.score = v->num;
       if (const egjson::Value* v = h.get("net_emissions")) r.net_emissions = v->num;
       if (const egjson::Value* v = h.get("total_cost")) r.total_cost = v->num;

@@ -143,6 +143,10 @@ def test_malformed_weight_files_fail_like_serde(tmp_path):
         "bad_action": txt.replace('"AddGenerator"', '"Explode"', 1), "bad_generator": txt.replace('"OnshoreWind"', '"Fusion"', 1),
         "deep_array": "[" * 100000, "deep_object": '{"a":' * 100000,
     }
+    doc = json.loads(txt)
+    for name, key, value in (("count_1e40", "iteration_count", 1e40), ("count_negative", "iterations_without_improvement", -5),
+                             ("count_fraction", "iteration_count", 2.5), ("count_string", "iteration_count", "7")):
+        cases[name] = json.dumps(dict(doc, **{key: value}))
     for name, text in cases.items():
         p = tmp_path / (name + ".json")
         p.write_text(text)
