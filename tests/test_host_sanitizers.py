@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "eirgrid_b200", "csrc")
 FUZZ = os.path.join(ROOT, "tests", "fuzz")
 ASSETS = os.path.join(ROOT, "tests", "golden", "ireland_map")
-FLAGS = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-std=c++17", "-I" + CSRC,
+FLAGS = ["-O1", "-g", "-fsanitize=address,undefined,float-cast-overflow,float-divide-by-zero", "-fno-sanitize-recover=undefined", "-std=c++17", "-I" + CSRC,
          "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include"]
 
 
