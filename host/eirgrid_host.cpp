@@ -98,18 +98,30 @@ Args parse(int argc, char** argv) {
     if (i + 1 >= argc) die(std::string("missing value for ") + argv[i]);
     return argv[++i];
   };
+  // unsigned decimal integers only (clap's usize/u64 parser): no sign, no garbage, no overflow
+  auto number = [&](int& i, uint64_t max) -> uint64_t {
+    const std::string flag = argv[i], v = need(i);
+    uint64_t x = 0;
+    bool ok = !v.empty() && v.size() <= 20;
+    for (char ch : v) {
+      if (ch < '0' || ch > '9' || x > (UINT64_MAX - (uint64_t)(ch - '0')) / 10) { ok = false; break; }
+      x = x * 10 + (uint64_t)(ch - '0');
+    }
+    if (!ok || x > max) die("invalid value '" + v + "' for '" + flag + "'");
+    return x;
+  };
   for (int i = 1; i < argc; i++) {
     const std::string f = argv[i];
-    if (f == "-n" || f == "--iterations") a.iterations = std::stoull(need(i));
+    if (f == "-n" || f == "--iterations") a.iterations = number(i, UINT64_MAX);
     else if (f == "-p" || f == "--parallel") a.parallel = true;
     else if (f == "--no-continue") a.no_continue = true;
     else if (f == "-c" || f == "--checkpoint-dir") a.checkpoint_dir = need(i);
-    else if (f == "-i" || f == "--checkpoint-interval") a.checkpoint_interval = std::max<uint64_t>(1, std::stoull(need(i)));
-    else if (f == "-r" || f == "--progress-interval") a.progress_interval = std::stoull(need(i));
+    else if (f == "-i" || f == "--checkpoint-interval") a.checkpoint_interval = std::max<uint64_t>(1, number(i, UINT64_MAX));
+    else if (f == "-r" || f == "--progress-interval") a.progress_interval = number(i, UINT64_MAX);
     else if (f == "-C" || f == "--cache-dir") a.cache_dir = need(i);
     else if (f == "--force-full-simulation") a.force_full_simulation = true;
     else if (f == "--enable-timing") a.enable_timing = true;
-    else if (f == "--seed") { a.has_seed = true; a.seed = std::stoull(need(i)); }
+    else if (f == "--seed") { a.has_seed = true; a.seed = number(i, UINT64_MAX); }
     else if (f == "-v" || f == "--verbose-state-logging") a.verbose_state_logging = true;
     else if (f == "--cost-only") a.cost_only = true;
     else if (f == "--enable-energy-sales") a.enable_energy_sales = true;
@@ -119,14 +131,15 @@ Args parse(int argc, char** argv) {
     else if (f == "--enable-construction-delays") a.enable_construction_delays = true;
     else if (f == "--track-weight-history") a.track_weight_history = true;
     else if (f == "--assets") a.assets = need(i);
-    else if (f == "--batch-size") a.batch_size = (uint32_t)std::stoul(need(i));
+    else if (f == "--batch-size") a.batch_size = (uint32_t)number(i, UINT32_MAX);
     else if (f == "--update-mode") a.update_mode = need(i);
-    else if (f == "--master-seed") { a.has_master_seed = true; a.master_seed = std::stoull(need(i)); }
+    else if (f == "--master-seed") { a.has_master_seed = true; a.master_seed = number(i, UINT64_MAX); }
     else if (f == "--devices") {
       a.devices.clear();
       std::string v = need(i), cur;
       for (char ch : v + ",") {
         if (ch == ',') { if (!cur.empty()) a.devices.push_back(std::stoi(cur)); cur.clear(); }
+        else if (ch < '0' || ch > '9' || cur.size() >= 4) die("invalid value '" + v + "' for '--devices'");
         else cur += ch;
       }
       if (a.devices.empty()) die("--devices needs at least one index");
