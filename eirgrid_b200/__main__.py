@@ -10,31 +10,45 @@ import os
 import sys
 
 
+def _unsigned(text):
+    # clap's usize/u64: decimal digits only
+    if not text.isdigit():
+        raise argparse.ArgumentTypeError("invalid value '%s': expected an unsigned integer" % text)
+    return int(text)
+
+
+def _positive(text):
+    v = _unsigned(text)
+    if v == 0:
+        raise argparse.ArgumentTypeError("must be positive")
+    return v
+
+
 def parse_args(argv=None):
     ap = argparse.ArgumentParser(prog="eirgrid_b200", description="EirGrid Power System Simulator (2025-2050), B200 episode engine")
-    ap.add_argument("-n", "--iterations", type=int, default=1000)
+    ap.add_argument("-n", "--iterations", type=_unsigned, default=1000)
     ap.add_argument("-p", "--parallel", action="store_true", default=True)
     ap.add_argument("--no-continue", action="store_true", default=False)
     ap.add_argument("-c", "--checkpoint-dir", default="checkpoints")
-    ap.add_argument("-i", "--checkpoint-interval", type=int, default=5)
-    ap.add_argument("-r", "--progress-interval", type=int, default=10)
+    ap.add_argument("-i", "--checkpoint-interval", type=_positive, default=5)
+    ap.add_argument("-r", "--progress-interval", type=_unsigned, default=10)
     ap.add_argument("-C", "--cache-dir", default="cache")
     ap.add_argument("--force-full-simulation", action="store_true", default=False)
     ap.add_argument("--enable-timing", action="store_true", default=False)
-    ap.add_argument("--seed", type=int, default=None, help="Random seed for deterministic simulation")
+    ap.add_argument("--seed", type=_unsigned, default=None, help="Random seed for deterministic simulation")
     ap.add_argument("-v", "--verbose-state-logging", action="store_true", default=False)
     ap.add_argument("--cost-only", action="store_true", default=False, help="Optimize for cost only, ignoring emissions and public opinion")
     ap.add_argument("--enable-energy-sales", action="store_true", default=True, help="Enable revenue from energy sales to offset costs")
-    ap.add_argument("--enable-csv-export", action="store_true", default=True, help="(accepted; CSV export is out of scope)")
+    ap.add_argument("--enable-csv-export", action="store_true", default=True, help="Enable CSV export of detailed simulation results")
     ap.add_argument("--debug-logging", action="store_true", default=False)
     ap.add_argument("--debug-weights", action="store_true", default=False)
     ap.add_argument("--enable-construction-delays", action="store_true", default=False)
     ap.add_argument("--track-weight-history", action="store_true", default=False)
     # additions of this implementation
     ap.add_argument("--assets", default=os.path.join("aiSimulator", "assets"), help="directory with settlements.json, ireland_generators.csv, coastline_points.json")
-    ap.add_argument("--batch-size", type=int, default=65536, help="episodes in flight per GPU")
+    ap.add_argument("--batch-size", type=_positive, default=65536, help="episodes in flight per GPU")
     ap.add_argument("--update-mode", choices=["batch", "sequential"], default="batch")
-    ap.add_argument("--master-seed", type=int, default=None, help="seed of the per-episode RNG streams when --seed is not given")
+    ap.add_argument("--master-seed", type=_unsigned, default=None, help="seed of the per-episode RNG streams when --seed is not given")
     return ap.parse_args(argv)
 
 
