@@ -25,7 +25,7 @@ def _build(tmp_path, harness, source):
     exe = str(tmp_path / harness.replace(".cpp", ""))
     r = subprocess.run(["g++"] + FLAGS + [os.path.join(FUZZ, harness), os.path.join(CSRC, source), "-o", exe],
                        capture_output=True, text=True)
-    if r.returncode != 0 and "sanitize" in r.stderr and "cannot find" in r.stderr:
+    if r.returncode != 0 and ("cannot find -lasan" in r.stderr or "cannot find -lubsan" in r.stderr or "libasan" in r.stderr):
         pytest.skip("sanitizer runtime not installed")
     assert r.returncode == 0, r.stderr[-2000:]
     return exe
