@@ -166,19 +166,24 @@ def run_multi_simulation(asset_dir, num_iterations, parallel=True, continue_from
         # never past the requested iteration count, nor past the start of the replay phase: the last batch is smaller
         phase_end = num_iterations if (is_full_run or final_full >= num_iterations) else num_iterations - final_full
         trainer.n = max(1, min(per_gpu, (phase_end - completed + world - 1) // world))
+        advance = trainer.n * world
         if update_mode == "batch" and not replay_best:
             st = trainer.step()
         else:
             # replay batches and the sequential mode go through the host update (it rebuilds the doubled records of
             # replay iterations, quirk Q10)
-            trainer.upload_weights()
-            trainer.launch_rollout()
-            res, traj = trainer.fetch_results()
+            # The per-episode rule is sequential, so with several ranks every rank rolls out the SAME episode ids and applies the
+            # same update to its own copy of the weights: identical kernels on identical inputs give identical tables on every
+            # rank without an exchange (the extra GPUs add nothing in this phase, they only stay consistent).
             if world > 1:
-                raise NotImplementedError("replay-best batches are single-GPU")
+                trainer.n = max(1, min(per_gpu, phase_end - completed))
+                advance = trainer.n
+            trainer.upload_weights()
+            trainer.launch_rollout(first_episode=trainer.next_episode)
+            res, traj = trainer.fetch_results()
             st = weights.update(res, traj, replay_best=replay_best, rng_seed=rng_seed)
             trainer.next_episode += trainer.n
-        completed += trainer.n * world
+        completed += advance
         n_flagged += int(st.n_flagged)
         if st.n_flagged and rank == 0:
             log("warning: %d episodes of this batch carry eg_result.flags (replay-phase years with more than 40 recorded actions, "
