@@ -162,3 +162,20 @@ def test_update_sequence_properties(oracle_world):
     assert res["score"][k] == res["score"].max()
     w_arr = t.arrays()[0]
     assert w_arr.min() >= 0.0001 and w_arr.max() <= 0.999
+
+
+def test_oracle_outputs_are_frozen():
+    """The oracle is the definition the CUDA path is held to wherever the reference pins nothing. Its outputs
+    for a fixed set of inputs are frozen in tests/golden/oracle_frozen_r01.npz (made by make_oracle_frozen.py): a change of
+    the oracle, of the compiler flags or of libm underneath it must show up here, not move the target silently."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_oracle_frozen", os.path.join(GOLDEN, "make_oracle_frozen.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    now = mod.frozen_outputs()
+    frozen = np.load(os.path.join(GOLDEN, "oracle_frozen_r01.npz"))
+    assert sorted(frozen.files) == sorted(now.keys())
+    for k in frozen.files:
+        a, b = frozen[k], now[k]
+        assert a.dtype == b.dtype and a.shape == b.shape, k
+        assert a.tobytes() == b.tobytes(), k
