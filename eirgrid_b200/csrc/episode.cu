@@ -640,6 +640,34 @@ struct Warp {
       return (smem + sb + kOffSortIdx)[0];
     }
     double rv = f64() * total;
+#ifndef EG_SCAN_SEQUENTIAL
+    {
+      // Decide the scan from a warp-parallel prefix sum when no partial sum comes near
+      // the draw. The sequential chain rv_k = fl(rv_{k-1} - w_k) and the tree sums S_k both differ from the exact
+      // rv - sum(w_0..w_k) by less than 61 * 2^-52 * total (~1e-14 * total); if every |rv - S_k| exceeds 1e-9 * total, the
+      // signs of all rv_k equal the signs of rv - S_k, so the first key with rv_k <= 0 is the first with rv - S_k <= 0.
+      // Otherwise (probability ~1e-7 per draw), and when no key crosses, the sequential scan below decides.
+      const int k0 = 2 * lane, k1 = 2 * lane + 1;  // lane l holds keys 2l and 2l+1
+      const double a = k0 < EG_N_ACTIONS ? lw[k0] : 0.0;
+      const double b = k1 < EG_N_ACTIONS ? lw[k1] : 0.0;
+      double s = a + b;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double t = __shfl_up_sync(kFull, s, d);
+        if (lane >= d) s += t;
+      }
+      const double d1 = rv - s, d0 = rv - (s - b);
+      const double margin = total * 1e-9;
+      const bool near = (k0 < EG_N_ACTIONS && fabs(d0) <= margin) || (k1 < EG_N_ACTIONS && fabs(d1) <= margin);
+      const unsigned m0 = __ballot_sync(kFull, k0 < EG_N_ACTIONS && d0 <= 0.0);
+      const unsigned m1 = __ballot_sync(kFull, k1 < EG_N_ACTIONS && d1 <= 0.0);
+      if (!__any_sync(kFull, near) && (m0 | m1) != 0u) {
+        const int f0 = m0 ? 2 * (__ffs((int)m0) - 1) : 1000;
+        const int f1 = m1 ? 2 * (__ffs((int)m1) - 1) + 1 : 1000;
+        return min(f0, f1);
+      }
+    }
+#endif
     #pragma unroll 4
     for (int k = 0; k < EG_N_ACTIONS; k++) {
       rv -= lw[k];
