@@ -31,7 +31,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 ASSETS = os.path.join(ROOT, "tests", "golden", "ireland_map")
 METRIC = "full 2025-2050 episodes simulated and scored per second"
 UNIT = "episodes/s"
-RESULT_BYTES, TRAJ_BYTES, POLICY_BYTES = 64, 1092, 38800
+RESULT_BYTES, TRAJ_BYTES, POLICY_BYTES = 64, 1088, 38784
 
 
 def load_peaks():

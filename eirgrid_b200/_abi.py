@@ -14,13 +14,14 @@ N_GEN_TYPES = 15
 N_ACTIONS = 61
 N_DEFICIT_KEYS = 15
 N_COUNT_KEYS = 21
-MAX_ACTIONS_PER_YEAR = 40
+TRAJ_CAPACITY = 984   # action slots per episode record (EG_TRAJ_CAPACITY); year rows are stored back to back
+BEST_CAPACITY = 2 * TRAJ_CAPACITY
 SITE_NONE = 0xFFFF
 ACT_DO_NOTHING = 60
 
 FLAG_GEN_OVERFLOW = 1
 FLAG_OFFSET_OVERFLOW = 2
-FLAG_YEAR_OVERFLOW = 4
+FLAG_RECORD_OVERFLOW = 4
 FLAG_NO_SITE = 8
 
 GEN_TYPES = ["OnshoreWind", "OffshoreWind", "DomesticSolar", "CommercialSolar", "UtilitySolar", "Nuclear",
@@ -37,12 +38,45 @@ RESULT_DTYPE = np.dtype([
 assert RESULT_DTYPE.itemsize == 64
 
 TRAJ_DTYPE = np.dtype([
-    ("n_deficit", "u1", (N_YEARS,)), ("n_additional", "u1", (N_YEARS,)),
-    ("actions", "u1", (N_YEARS, MAX_ACTIONS_PER_YEAR))])
-assert TRAJ_DTYPE.itemsize == 1092
+    ("n_deficit", "<u2", (N_YEARS,)), ("n_additional", "<u2", (N_YEARS,)),
+    ("actions", "u1", (TRAJ_CAPACITY,))])
+assert TRAJ_DTYPE.itemsize == 1088
 
-SITES_DTYPE = np.dtype([("site", "<u2", (N_YEARS, MAX_ACTIONS_PER_YEAR))])
-assert SITES_DTYPE.itemsize == 2080
+SITES_DTYPE = np.dtype([("site", "<u2", (TRAJ_CAPACITY,))])
+assert SITES_DTYPE.itemsize == 1968
+
+
+def traj_row_starts(traj):
+    """First slot of each year's row: int array [..., 27] (last entry = slots used) for one record or an array of records."""
+    n = traj["n_deficit"].astype(np.int64) + traj["n_additional"].astype(np.int64)
+    return np.concatenate([np.zeros(n.shape[:-1] + (1,), np.int64), np.cumsum(n, axis=-1)], axis=-1)
+
+
+def traj_rows(rec, values=None):
+    """The 26 year rows of ONE record as a list of (deficit part, additional part) arrays; `values` = the per-slot
+    array to slice (default: the record's actions; pass sites["site"] for the placement sites)."""
+    a = rec["actions"] if values is None else values
+    start = traj_row_starts(rec)
+    out = []
+    for y in range(N_YEARS):
+        nd = int(rec["n_deficit"][y])
+        out.append((a[start[y]:start[y] + nd], a[start[y] + nd:start[y + 1]]))
+    return out
+
+
+def pack_traj(rows):
+    """Inverse of traj_rows: rows = 26 x (deficit actions, additional actions) -> one TRAJ_DTYPE record."""
+    rec = np.zeros((), TRAJ_DTYPE)
+    pos = 0
+    for y, (d, a) in enumerate(rows):
+        d, a = np.asarray(d, np.uint8), np.asarray(a, np.uint8)
+        if pos + len(d) + len(a) > TRAJ_CAPACITY:
+            raise ValueError("record exceeds TRAJ_CAPACITY")
+        rec["n_deficit"][y], rec["n_additional"][y] = len(d), len(a)
+        rec["actions"][pos:pos + len(d)] = d
+        rec["actions"][pos + len(d):pos + len(d) + len(a)] = a
+        pos += len(d) + len(a)
+    return rec
 
 YEAR_FIELDS = ["total_power_usage", "total_power_generation", "power_balance", "average_public_opinion",
                "yearly_capital_cost", "total_capital_cost", "inflation_factor", "total_co2_emissions",

@@ -64,7 +64,7 @@ def lib():
     L.eg_weights_merge.argtypes = [vp, vp]
     L.eg_weights_get_table.argtypes = [vp, C.POINTER(_abi.WeightsTable)]
     L.eg_weights_set_table.argtypes = [vp, C.POINTER(_abi.WeightsTable)]
-    L.eg_weights_get_best.argtypes = [vp, vp, vp, vp, vp]
+    L.eg_weights_get_best.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, C.c_size_t]
     L.eg_deficit_key_action.argtypes = [u32]
     L.eg_deficit_key_action.restype = C.c_uint8
     L.eg_rollout_batch.argtypes = [vp, vp, C.POINTER(_abi.RunCfg), u64, u64, u32, vp, vp, vp, vp]
@@ -148,13 +148,13 @@ class Weights:
         check(self.L.eg_weights_set_table(self.h, C.byref(t)))
 
     def best(self):
-        """(has_best, n_best[26], best[26,80], n_best_deficit[26], best_deficit[26,40])"""
-        nb = np.zeros(26, np.uint8)
-        b = np.zeros((26, 2 * _abi.MAX_ACTIONS_PER_YEAR), np.uint8)
-        nd = np.zeros(26, np.uint8)
-        d = np.zeros((26, _abi.MAX_ACTIONS_PER_YEAR), np.uint8)
-        has = check(self.L.eg_weights_get_best(self.h, _abi.ptr(nb), _abi.ptr(b), _abi.ptr(nd), _abi.ptr(d)))
-        return bool(has), nb, b, nd, d
+        """(has_best, best_actions, best_deficit_actions): two lists of 26 uint8 arrays (any length, like the reference's Vecs)"""
+        nb, nd = np.zeros(26, np.uint32), np.zeros(26, np.uint32)
+        has = check(self.L.eg_weights_get_best(self.h, _abi.ptr(nb), None, 0, _abi.ptr(nd), None, 0))
+        b, d = np.zeros(max(int(nb.sum()), 1), np.uint8), np.zeros(max(int(nd.sum()), 1), np.uint8)
+        check(self.L.eg_weights_get_best(self.h, _abi.ptr(nb), _abi.ptr(b), b.size, _abi.ptr(nd), _abi.ptr(d), d.size))
+        ob, od = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64), np.concatenate([[0], np.cumsum(nd)]).astype(np.int64)
+        return (bool(has), [b[ob[y]:ob[y + 1]].copy() for y in range(26)], [d[od[y]:od[y + 1]].copy() for y in range(26)])
 
     def has_best_actions(self):  # ActionWeights::has_best_actions
         return bool(self.table().has_best)

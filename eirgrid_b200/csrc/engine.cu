@@ -19,7 +19,7 @@
 #include "suitability.cuh"
 #include "weights.hpp"
 
-static_assert(sizeof(EgPolicyDevice) == 38800, "bench.py and eirgrid_b200/_abi.py quote this size");
+static_assert(sizeof(EgPolicyDevice) == 38784, "bench.py and eirgrid_b200/_abi.py quote this size");
 static thread_local std::string g_last_error;
 int eg_fail(int code, const std::string& message) {
   g_last_error = message;
@@ -60,6 +60,9 @@ struct eg_ctx {
   double *d_sx = nullptr, *d_sy = nullptr, *d_ex = nullptr, *d_ey = nullptr, *d_cx = nullptr, *d_cy = nullptr;
   uint32_t* d_pop = nullptr;
   EgPolicyDevice* d_policy = nullptr;
+  EgPolicyDevice* h_policy[2] = {nullptr, nullptr};   // pinned staging of the snapshot, used in turn
+  cudaEvent_t policy_copied[2] = {nullptr, nullptr};  // the H2D copy issued from h_policy[b] has completed
+  int policy_turn = 0;
   uint32_t* d_next_episode = nullptr;  // work counter of the persistent episode kernels
   // eg_train_batch_*: statistics table, shard best, winner record (device) and their pinned host mirrors
   int64_t* d_stats = nullptr;
@@ -259,6 +262,10 @@ void eg_destroy(eg_ctx* c) {
   free_map(c);
   if (c->h_stats) cudaFreeHost(c->h_stats);
   if (c->h_record) cudaFreeHost(c->h_record);
+  for (int b = 0; b < 2; b++) {
+    if (c->h_policy[b]) cudaFreeHost(c->h_policy[b]);
+    if (c->policy_copied[b]) cudaEventDestroy(c->policy_copied[b]);
+  }
   void* ptrs[] = {c->d_policy, c->d_next_episode, c->d_stats, c->d_best_score, c->d_best_index, c->d_record, c->s_out, c->s_traj, c->s_traj_in, c->s_sites, c->s_yearly};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -334,12 +341,23 @@ int eg_map_site_static(eg_ctx* c, double* coast_factor, double* site_opinion) {
 int eg_weights_upload(eg_ctx* c, const eg_weights* w) {
   if (!c || !w) return eg_fail(EG_ERR_INVALID, "eg_weights_upload: NULL argument");
   EG_CUDA(cudaSetDevice(c->device));
-  if (!c->d_policy) EG_CUDA(cudaMalloc((void**)&c->d_policy, sizeof(EgPolicyDevice)));
-  EgPolicyDevice pol;
-  eg_weights_fill_policy(*w, &pol);
-  // pageable source: the copy is staged before the call returns, so `pol` may go out of scope
+  if (!c->d_policy) {
+    EG_CUDA(cudaMalloc((void**)&c->d_policy, sizeof(EgPolicyDevice)));
+    for (int b = 0; b < 2; b++) {
+      EG_CUDA(cudaMallocHost((void**)&c->h_policy[b], sizeof(EgPolicyDevice)));
+      EG_CUDA(cudaEventCreateWithFlags(&c->policy_copied[b], cudaEventDisableTiming));
+    }
+  }
+  // two pinned staging buffers used in turn: the copy is queued on the stream and the call returns without waiting for it;
+  // a buffer is refilled only after the copy issued from it two uploads ago has completed (normally long ago)
+  const int b = c->policy_turn;
+  c->policy_turn ^= 1;
+  EG_CUDA(cudaEventSynchronize(c->policy_copied[b]));
+  EgPolicyDevice& pol = *c->h_policy[b];
+  if (!eg_weights_fill_policy(*w, &pol))
+    return eg_fail(EG_ERR_OVERFLOW, "eg_weights_upload: the best-strategy lists exceed the device snapshot's capacity (EG_BEST_CAPACITY / EG_TRAJ_CAPACITY actions)");
   EG_CUDA(cudaMemcpyAsync(c->d_policy, &pol, sizeof(pol), cudaMemcpyHostToDevice, c->stream));
-  EG_CUDA(cudaStreamSynchronize(c->stream));
+  EG_CUDA(cudaEventRecord(c->policy_copied[b], c->stream));
   c->policy_ready = true;
   c->policy_count_weights = pol.has_count_weights != 0;
   c->policy_stagnation = pol.iwi > 500;
@@ -555,12 +573,15 @@ int eg_export_best_run_csv(eg_ctx* c, const eg_weights* w, const eg_run_cfg* cfg
   // the best run as a record: best_actions[y] = deficit actions followed by the additional actions (Appendix C of SURVEY.md)
   eg_traj traj;
   std::memset(&traj, 0, sizeof(traj));
+  int row[EG_NY + 1];  // first slot of each year's row in the record
+  row[0] = 0;
   for (int y = 0; y < EG_NY; y++) {
-    const size_t nd = std::min<size_t>(w->best_deficit_actions[y].size(), EG_MAX_ACTIONS_PER_YEAR);
-    const size_t n = std::min<size_t>(w->best_actions[y].size(), EG_MAX_ACTIONS_PER_YEAR);
-    traj.n_deficit[y] = (uint8_t)std::min(nd, n);
-    traj.n_additional[y] = (uint8_t)(n - traj.n_deficit[y]);
-    for (size_t i = 0; i < n; i++) traj.actions[y][i] = w->best_actions[y][i];
+    const size_t n = std::min<size_t>(w->best_actions[y].size(), (size_t)(EG_TRAJ_CAPACITY - row[y]));
+    const size_t nd = std::min<size_t>(w->best_deficit_actions[y].size(), n);
+    traj.n_deficit[y] = (uint16_t)nd;
+    traj.n_additional[y] = (uint16_t)(n - nd);
+    for (size_t i = 0; i < n; i++) traj.actions[row[y] + i] = w->best_actions[y][i];
+    row[y + 1] = row[y] + (int)n;
   }
   eg_result res;
   eg_yearly yearly;
@@ -590,7 +611,7 @@ int eg_export_best_run_csv(eg_ctx* c, const eg_weights* w, const eg_run_cfg* cfg
     for (int y = 0; y < EG_NY; y++) {
       // SimulationResult.actions holds the additional actions only (simulation.rs:193, iteration.rs:90)
       for (int i = traj.n_deficit[y]; i < traj.n_deficit[y] + traj.n_additional[y]; i++) {
-        const int a = traj.actions[y][i];
+        const int a = traj.actions[row[y] + i];
         const int year = EG_BASE_YEAR + y;
         if (a < 45) {
           const int tp = a / 3, m = a % 3;
@@ -676,8 +697,8 @@ int eg_export_best_run_csv(eg_ctx* c, const eg_weights* w, const eg_run_cfg* cfg
                         g < c->htab.ex_online_year.size() && c->htab.ex_online_year[g] ? c->htab.ex_online_year[g] : 1 << 30, (int)g, m.ex[g], m.ey[g]});
     for (int y = 0; y < EG_NY; y++)
       for (int i = 0; i < traj.n_deficit[y] + traj.n_additional[y]; i++) {
-        const int a = traj.actions[y][i];
-        if (a >= 45 || sites.site[y][i] == EG_SITE_NONE) continue;
+        const int a = traj.actions[row[y] + i];
+        if (a >= 45 || sites.site[row[y] + i] == EG_SITE_NONE) continue;
         const int year = EG_BASE_YEAR + y;
         Plant p{std::string("Gen_") + kCsvGenNames[a / 3] + "_" + std::to_string(year) + "_" + std::to_string(plants.size()), a / 3, year, year, 0, 0};
         uint32_t h = 0;
@@ -722,7 +743,7 @@ int eg_export_best_run_csv(eg_ctx* c, const eg_weights* w, const eg_run_cfg* cfg
     std::vector<Offset> offs;
     for (int y = 0; y < EG_NY; y++)
       for (int i = traj.n_deficit[y]; i < traj.n_deficit[y] + traj.n_additional[y]; i++) {
-        const int a = traj.actions[y][i];
+        const int a = traj.actions[row[y] + i];
         if (a < 45 || a >= 57) continue;
         const int o = (a - 45) / 3, year = EG_BASE_YEAR + y;
         Offset r{std::string("Offset_") + kCsvOffsetNames[o] + "_" + std::to_string(year) + "_" + std::to_string(offs.size()), o, year, (a - 45) % 3, 0, 0};

@@ -31,6 +31,7 @@
 //    training launch runs an image without the optional outputs, the replay-best branches and the sampler it does not use.
 #include "episode.cuh"
 #include <algorithm>
+#include <cstddef>
 
 extern __shared__ __align__(16) unsigned char smem[];  // dynamic shared memory of the episode kernels: one slice per warp
 
@@ -64,11 +65,12 @@ constexpr int kOffVars = kOffScratch + kScratchBytes;           // double[16]  r
 constexpr int kOffGxy = kOffVars + 8 * 16;                      // uint16[EG_MAX_NEW_GENERATORS] plant cells (gi << 8) | gj
 constexpr int kOffGat = kOffGxy + 2 * EG_MAX_NEW_GENERATORS;    // uint16[EG_MAX_NEW_GENERATORS] type(4) mult(2) build(5)
 constexpr int kOffOffs = kOffGat + 2 * EG_MAX_NEW_GENERATORS;   // uint16[EG_MAX_OFFSETS]
-constexpr int kOffYearSites = kOffOffs + 2 * EG_MAX_OFFSETS;    // uint16[40]
-constexpr int kOffYearActions = kOffYearSites + 2 * EG_MAX_ACTIONS_PER_YEAR;  // uint8[40]
-constexpr int kOffCounts = kOffYearActions + EG_MAX_ACTIONS_PER_YEAR;         // uint8[26] deficit + uint8[26] additional
-constexpr int kSliceBytes = (kOffCounts + 2 * EG_NY + 15) & ~15;  // 5.7 KB per warp
-static_assert(kOffScratch % 16 == 0 && kOffVars % 8 == 0 && kOffGxy % 8 == 0 && kOffOffs % 4 == 0 && kOffYearSites % 4 == 0 && kOffYearActions % 4 == 0, "alignment");
+constexpr int kOffCounts = kOffOffs + 2 * EG_MAX_OFFSETS;       // uint16[26] deficit + uint16[26] additional recorded per year
+constexpr int kSliceBytes = (kOffCounts + 4 * EG_NY + 15) & ~15;  // 5.6 KB per warp
+static_assert(kOffScratch % 16 == 0 && kOffVars % 8 == 0 && kOffGxy % 8 == 0 && kOffOffs % 4 == 0 && kOffCounts % 4 == 0, "alignment");
+// the action record (eg_traj / eg_sites) is written straight to global memory, one slot per recorded action (lane 0), the
+// unused tail once at the end of the episode with 8-byte stores
+static_assert(offsetof(eg_traj, actions) % 8 == 0 && sizeof(eg_traj) % 8 == 0 && EG_TRAJ_CAPACITY % 8 == 0 && sizeof(eg_sites) % 8 == 0, "tail fill uses 8-byte stores");
 
 // slots of the per-warp scalar area: values every lane agrees on that are touched a few times per year
 enum { kVTotalCost = 0, kVTotalCredit, kVTotalSales, kVGcostPrev, kVOcostPrev, kVLwTotal, kVInitNet, kVInitOpinion, kVInitBalance, kVInitCost, kVScaledTotal };
@@ -214,6 +216,8 @@ struct Warp {
                               // the same sums re-priced at year-1 live in the scalar area (kVGcostPrev, kVOcostPrev)
   double off_amount;          // calc_total_carbon_offset(year)
   uint32_t n_gens, n_offs, flags;
+  uint32_t ep;                // index of the episode in the batch (output slot)
+  uint32_t rec_used;          // slots of the action record written so far (all years)
 #ifdef EG_WALK_STATS
   uint32_t dbg_steps, dbg_evals, dbg_cands, dbg_pairs;
 #endif
@@ -235,9 +239,7 @@ struct Warp {
   __device__ __forceinline__ double* LCW(int y) const { return LW(y) + EG_N_ACTIONS + EG_N_DEFICIT_KEYS; }
   __device__ __forceinline__ double2* SCR() const { return (double2*)(smem + sb + kOffScratch); }
   __device__ __forceinline__ uint16_t* OFFS() const { return (uint16_t*)(smem + sb + kOffOffs); }
-  __device__ __forceinline__ uint16_t* YSITES() const { return (uint16_t*)(smem + sb + kOffYearSites); }
-  __device__ __forceinline__ uint8_t* YACT() const { return smem + sb + kOffYearActions; }
-  __device__ __forceinline__ uint8_t* COUNTS() const { return smem + sb + kOffCounts; }
+  __device__ __forceinline__ uint16_t* COUNTS() const { return (uint16_t*)(smem + sb + kOffCounts); }
 
 
   // ---- random draws ---------------------------------------------------------------------------------------
@@ -439,8 +441,9 @@ struct Warp {
     return best_site;
   }
 
-  __device__ __forceinline__ void add_generator(int site, int t, int m, int y) {
-    if (n_gens >= EG_MAX_NEW_GENERATORS) { flags |= EG_FLAG_GEN_OVERFLOW; return; }
+  // false: the episode's plant list is full (flagged); nothing was added
+  __device__ __forceinline__ bool add_generator(int site, int t, int m, int y) {
+    if (n_gens >= EG_MAX_NEW_GENERATORS) { flags |= EG_FLAG_GEN_OVERFLOW; return false; }
     const int n = p.map.grid_n;
     const int gi = site / n, gj = site - gi * n;
     EG_CHECK(gi >= 0 && gi < n && gj >= 0 && gj < n && n_gens < EG_MAX_NEW_GENERATORS && t < EG_NT && m < EG_N_MULTS && y < EG_NY);
@@ -459,6 +462,7 @@ struct Warp {
       gcost += pt.y;
       if (y > 0 && lane == 0) VARS()[kVGcostPrev] += gen_cost(t, m, y, y - 1);
     }
+    return true;
   }
   __device__ __forceinline__ void add_offset(int ot, int m, int y) {
     if (n_offs >= EG_MAX_OFFSETS) { flags |= EG_FLAG_OFFSET_OVERFLOW; return; }
@@ -547,7 +551,7 @@ struct Warp {
   // ---- sampling (canonical key order replaces HashMap iteration order) ---------------------------------------
   __device__ __forceinline__ int sample_deficit_action(int y, uint32_t* replay_pos) {  // sampling.rs:240-378
     if (EG_OPT(p.replay_best)) {
-      if (p.policy->has_best && *replay_pos < p.policy->n_best_deficit[y]) return p.policy->best_deficit[y][(*replay_pos)++];
+      if (p.policy->has_best && *replay_pos < p.policy->n_best_deficit[y]) return p.policy->best_deficit[p.policy->best_deficit_off[y] + (*replay_pos)++];
       return smart_deficit_fallback_pick(index(93));
     }
     const bool explore = f64() < p.policy->exploration_rate;
@@ -595,7 +599,7 @@ struct Warp {
 
   __device__ __forceinline__ int sample_action(int y, uint32_t* replay_pos) {  // sampling.rs:76-238
     if (EG_OPT(p.replay_best)) {
-      if (p.policy->has_best && *replay_pos < p.policy->n_best[y]) return p.policy->best[y][(*replay_pos)++];
+      if (p.policy->has_best && *replay_pos < p.policy->n_best[y]) return p.policy->best[p.policy->best_off[y] + (*replay_pos)++];
       return smart_fallback_pick(y, index(smart_fallback_total(y)));
     }
     const bool explore = f64() < p.policy->action_exploration;  // exploration_rate / (1 + 0.01 iwi) once iwi > 100, per snapshot
@@ -676,15 +680,20 @@ struct Warp {
     return kGasPeaker100;
   }
 
-  __device__ __forceinline__ void record(int slot, int action, int site) {
-    if (slot >= EG_MAX_ACTIONS_PER_YEAR) { flags |= EG_FLAG_YEAR_OVERFLOW; return; }
+  // record_action / record_deficit_action (simulation.rs:406-409,197): the next slot of the episode's record
+  __device__ __forceinline__ void record(int action, int site) {
+    if (rec_used >= EG_TRAJ_CAPACITY) { flags |= EG_FLAG_RECORD_OVERFLOW; return; }
     if (lane == 0) {
-      YACT()[slot] = (uint8_t)action;
-      YSITES()[slot] = site >= 0 ? (uint16_t)site : (uint16_t)EG_SITE_NONE;
+      if (p.traj) p.traj[ep].actions[rec_used] = (uint8_t)action;
+      if (EG_OPT(p.sites)) p.sites[ep].site[rec_used] = site >= 0 ? (uint16_t)site : (uint16_t)EG_SITE_NONE;
     }
+    rec_used++;
   }
 
-  __device__ __forceinline__ void run(uint32_t ep) {
+  __device__ __forceinline__ void run(uint32_t ep_) {
+    ep = ep_;
+    rec_used = 0;
+    uint32_t in_row = 0;  // REPLAY: first slot of the current year's row in the input record
     rng_id = p.same_stream ? 0ull : p.first_episode + ep;
     draw = 0; rbase = 0x80000000u; rbuf = 0ull;
     n_gens = 0; n_offs = 0; flags = 0;
@@ -719,7 +728,10 @@ struct Warp {
       double remaining = deficit_mode ? -cur.balance : 0.0;  // Map::handle_power_deficit returns it unchanged (Q2)
       uint32_t attempts = 0, n_def = 0, n_add = 0, n_to_add = 0, replay_def = 0, replay_act = 0;
       bool counted = false;
-      const uint32_t in_def = REPLAY ? min((uint32_t)in->n_deficit[y], (uint32_t)EG_MAX_ACTIONS_PER_YEAR) : 0;  // a malformed count never reads past the row
+      // a malformed count never reads past the record: the row is cut at the capacity
+      const uint32_t in_def = REPLAY ? min((uint32_t)in->n_deficit[y], (uint32_t)EG_TRAJ_CAPACITY - in_row) : 0;
+      const uint32_t in_add = REPLAY ? min((uint32_t)in->n_additional[y], (uint32_t)EG_TRAJ_CAPACITY - in_row - in_def) : 0;
+      const uint32_t rec_year = rec_used;  // first slot of this year's row in the record
 
       for (;;) {
         int action;
@@ -727,7 +739,7 @@ struct Warp {
         if (deficit_mode) {
           if (remaining > 0.0) {                             // simulation.rs:358
             attempts++;
-            if (REPLAY) { action = replay_def < in_def ? in->actions[y][replay_def] : kBattery100; replay_def++; }
+            if (REPLAY) { action = replay_def < in_def ? in->actions[in_row + replay_def] : kBattery100; replay_def++; }
             else action = attempts < 5 ? sample_deficit_action(y, &replay_def) : kBattery100;
             // "Only add a generator if the sampled action is an AddGenerator" (simulation.rs:396-397): anything else is
             // neither applied nor recorded and the loop tries again (recorded trajectories can contain such entries)
@@ -741,22 +753,23 @@ struct Warp {
               const double overall_success = action_impact(initial, cur);
               if (cur.balance >= 0.0 && overall_success > 0.0 && n_def > 0) {
                 const double success_factor = 0.1 * overall_success;
-                for (uint32_t i = 0; i < n_def && i < EG_MAX_ACTIONS_PER_YEAR; i++) update_deficit_weights(y, YACT()[i], success_factor);
+                // this year's deficit actions are the AddGenerator(type, 100 %) keys of the last n_def plants of the list
+                if (n_gens >= n_def)
+                  for (uint32_t i = 0; i < n_def; i++) update_deficit_weights(y, 3 * (int)(GAT()[n_gens - n_def + i] & 0xF), success_factor);
               }
             }
             deficit_mode = false;
             continue;
           }
         } else if (!counted) {                               // simulation.rs:144-187
-          if (REPLAY) n_to_add = in->n_additional[y];
+          if (REPLAY) n_to_add = in_add;
           else if (EG_OPT(p.replay_best)) n_to_add = p.policy->has_best ? p.policy->n_best[y] : 0;
           else n_to_add = sample_additional_actions(y, n_def);
           counted = true;
           continue;
         } else if (n_add < n_to_add) {                       // simulation.rs:189-198
           if (REPLAY) {
-            const uint32_t pos = in_def + n_add;
-            action = pos < EG_MAX_ACTIONS_PER_YEAR ? in->actions[y][pos] : EG_ACT_DO_NOTHING;
+            action = in->actions[in_row + in_def + n_add];
           } else {
             action = sample_action(y, &replay_act);
           }
@@ -769,15 +782,16 @@ struct Warp {
         if (action < 45) {                                   // apply_action, actions.rs:42-76
           const int t = action / 3, m = action - 3 * t;
           site = place(t, y);
-          if (site >= 0) add_generator(site, t, m, y);
-          else flags |= EG_FLAG_NO_SITE;
+          if (site < 0) flags |= EG_FLAG_NO_SITE;
+          else if (!add_generator(site, t, m, y) && is_def) site = -1;  // plant list full: the deficit loop is left like below
         } else if (action < 57) {                            // actions.rs:129-179
           const int a = action - 45;
           const int ot = a / 3;
           add_offset(ot, a - 3 * ot, y);
         }                                                    // 57..60: no generator id matches / DoNothing (Q4)
-        if (is_def && site < 0) { remaining = 0.0; continue; }  // no site with score > 0: flagged, loop left
-        record(n_def + n_add, action, site);
+        // no site with score > 0, or no room for another plant: flagged, the deficit loop is left (it could never end otherwise)
+        if (is_def && site < 0) { remaining = 0.0; continue; }
+        record(action, site);
         if (is_def) {
           n_def++;
           // state_before of this iteration (simulation.rs:380-395) is the state after the previous change: `cur`
@@ -804,28 +818,12 @@ struct Warp {
       }
       __syncwarp();
 
-      const uint32_t nd_rec = min(n_def, (uint32_t)EG_MAX_ACTIONS_PER_YEAR);
-      const uint32_t na_rec = min(n_add, (uint32_t)EG_MAX_ACTIONS_PER_YEAR - nd_rec);
-      if (lane == 0) { COUNTS()[y] = (uint8_t)nd_rec; COUNTS()[EG_NY + y] = (uint8_t)na_rec; }
+      if (lane == 0) {  // recorded entries of the year: the deficit actions come first, the record may have been cut
+        const uint32_t nd_rec = min(n_def, rec_used - rec_year);
+        COUNTS()[y] = (uint16_t)nd_rec; COUNTS()[EG_NY + y] = (uint16_t)(rec_used - rec_year - nd_rec);
+      }
       n_def_total += n_def; n_add_total += n_add;
-      const uint32_t used = nd_rec + na_rec;
-      if (p.traj) {  // 40 B row, one 32-bit word per lane
-        if (lane < EG_MAX_ACTIONS_PER_YEAR / 4) {
-          const uint32_t raw = ((const uint32_t*)YACT())[lane];
-          const uint32_t first = lane * 4;
-          const uint32_t keep = used <= first ? 0u : (used - first >= 4u ? 0xFFFFFFFFu : (1u << (8 * (used - first))) - 1u);
-          ((uint32_t*)p.traj[ep].actions[y])[lane] = raw & keep;
-        }
-      }
-      if (EG_OPT(p.sites)) {
-        if (lane < EG_MAX_ACTIONS_PER_YEAR / 2) {
-          const uint32_t raw = ((const uint32_t*)YSITES())[lane];
-          const uint32_t first = lane * 2;
-          const uint32_t word = used <= first ? 0xFFFFFFFFu : (used - first >= 2u ? raw : (raw | 0xFFFF0000u));
-          ((uint32_t*)p.sites[ep].site[y])[lane] = word;
-        }
-      }
-      __syncwarp();
+      if (REPLAY) in_row += in_def + in_add;
 
       // calculate_yearly_metrics, analysis/metrics_calculation.rs:32-175 (only the rows somebody asked for; the
       // episode result needs the 2050 row alone, iteration.rs:57-84)
@@ -915,10 +913,21 @@ struct Warp {
       }
       ((unsigned long long*)(p.out + ep))[lane] = word;
     }
+    // per-year counts (n_deficit[26] then n_additional[26] are contiguous), then the unused tail of the record: zero
+    // actions, EG_SITE_NONE sites (single slots up to the next 8-byte boundary, then words)
+    __syncwarp();
+    const uint32_t tail8 = (rec_used + 7u) & ~7u;
     if (p.traj) {
-      __syncwarp();
-      uint8_t* dst = p.traj[ep].n_deficit;  // n_deficit[26] then n_additional[26] are contiguous
-      for (int i = lane; i < 2 * EG_NY; i += 32) dst[i] = COUNTS()[i];
+      uint8_t* a = p.traj[ep].actions;
+      if (lane < EG_NY) ((uint32_t*)p.traj[ep].n_deficit)[lane] = ((const uint32_t*)COUNTS())[lane];
+      if (rec_used + lane < tail8) a[rec_used + lane] = 0;
+      for (uint32_t i = tail8 / 8 + lane; i < EG_TRAJ_CAPACITY / 8; i += 32) ((unsigned long long*)a)[i] = 0ull;
+    }
+    if (EG_OPT(p.sites)) {
+      uint16_t* st = p.sites[ep].site;
+      const uint32_t tail4 = (rec_used + 3u) & ~3u;
+      for (uint32_t i = rec_used + lane; i < tail4; i += 32) st[i] = (uint16_t)EG_SITE_NONE;
+      for (uint32_t i = tail4 / 4 + lane; i < EG_TRAJ_CAPACITY / 4; i += 32) ((unsigned long long*)st)[i] = ~0ull;
     }
     __syncwarp();
   }

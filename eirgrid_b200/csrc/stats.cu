@@ -47,17 +47,20 @@ __global__ void eg_stats_reset_kernel(double* best_score, unsigned long long* be
 __global__ void __launch_bounds__(256) eg_stats_kernel(const EgStatsParams p) {
   __shared__ unsigned long long acc[EG_STATS_WORDS];
   __shared__ unsigned long long best_mask[EG_NY];                      // actions that occur in best(y) = best_actions ++ best_deficit
-  __shared__ uint8_t best_cat[EG_NY][EG_MAX_ACTIONS_PER_YEAR * 3];     // that concatenation, by position
-  __shared__ uint8_t best_len[EG_NY];
+  __shared__ uint8_t best_cat[EG_BEST_CAPACITY + EG_TRAJ_CAPACITY];    // that concatenation by position, year after year
+  __shared__ uint16_t best_len[EG_NY], best_start[EG_NY];
   for (int i = threadIdx.x; i < EG_STATS_WORDS; i += blockDim.x) acc[i] = 0ull;
   if (threadIdx.x < EG_NY) {
     const int y = threadIdx.x;
     const int nb = p.policy->n_best[y], nbd = p.policy->n_best_deficit[y];
+    const int ob = p.policy->best_off[y], obd = p.policy->best_deficit_off[y];
+    uint8_t* cat = best_cat + ob + obd;  // both offsets are prefix sums over the years before y
     unsigned long long m = 0ull;
-    for (int b = 0; b < nb; b++) { const int a = p.policy->best[y][b]; best_cat[y][b] = (uint8_t)a; m |= 1ull << a; }
-    for (int b = 0; b < nbd; b++) { const int a = p.policy->best_deficit[y][b]; best_cat[y][nb + b] = (uint8_t)a; m |= 1ull << a; }
+    for (int b = 0; b < nb; b++) { const int a = p.policy->best[ob + b]; cat[b] = (uint8_t)a; m |= 1ull << a; }
+    for (int b = 0; b < nbd; b++) { const int a = p.policy->best_deficit[obd + b]; cat[nb + b] = (uint8_t)a; m |= 1ull << a; }
     best_mask[y] = m;
-    best_len[y] = (uint8_t)(nb + nbd);
+    best_len[y] = (uint16_t)(nb + nbd);
+    best_start[y] = (uint16_t)(ob + obd);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -97,10 +100,18 @@ __global__ void __launch_bounds__(256) eg_stats_kernel(const EgStatsParams p) {
     // a time, each lane finding its item's year by binary search over the prefix sums.
     const eg_traj* t = p.trajs + ep;
     int nd = 0, nrun = 0;
-    if (lane < EG_NY) {
-      nd = min((int)t->n_deficit[lane], EG_MAX_ACTIONS_PER_YEAR);
-      nrun = nd + min((int)t->n_additional[lane], EG_MAX_ACTIONS_PER_YEAR - nd);
+    if (lane < EG_NY) { nd = t->n_deficit[lane]; nrun = nd + t->n_additional[lane]; }
+    // first slot of each year's row in the record (rows are stored back to back); counts that run past the capacity
+    // (never written by the episode kernels) are cut
+    int row_end = nrun;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xFFFFFFFFu, row_end, o);
+      if (lane >= o) row_end += v;
     }
+    int row = row_end - nrun;
+    if (row > EG_TRAJ_CAPACITY) row = EG_TRAJ_CAPACITY;
+    if (row + nrun > EG_TRAJ_CAPACITY) { nrun = EG_TRAJ_CAPACITY - row; nd = min(nd, nrun); }
     const int cnt = nrun + nd;
     int incl = cnt;
 #pragma unroll
@@ -118,10 +129,10 @@ __global__ void __launch_bounds__(256) eg_stats_kernel(const EgStatsParams p) {
         if (v <= q) y += step;
       }
       const int y_incl = __shfl_sync(0xFFFFFFFFu, incl, y), y_cnt = __shfl_sync(0xFFFFFFFFu, cnt, y);
-      const int y_nrun = __shfl_sync(0xFFFFFFFFu, nrun, y);
+      const int y_nrun = __shfl_sync(0xFFFFFFFFu, nrun, y), y_row = __shfl_sync(0xFFFFFFFFu, row, y);
       if (q >= total) continue;
       const int i = q - (y_incl - y_cnt);
-      const int a = t->actions[y][i < y_nrun ? i : i - y_nrun];
+      const int a = t->actions[y_row + (i < y_nrun ? i : i - y_nrun)];
       if (a >= EG_N_ACTIONS) continue;  // not an action code (records are produced by the episode kernels; defensive)
       unsigned long long* ys = acc + EG_STATS_HEADER + y * EG_STATS_YEAR_STRIDE;
       if (i < y_nrun) atomicAdd(&ys[2 * EG_N_ACTIONS + a], 1ull);
@@ -133,7 +144,7 @@ __global__ void __launch_bounds__(256) eg_stats_kernel(const EgStatsParams p) {
       if (!((best_mask[y] >> a) & 1ull)) {
         atomicAdd(&ys[a], (unsigned long long)log_pen);
       } else if (i < (int)best_len[y]) {
-        if (best_cat[y][i] != a) atomicAdd(&ys[EG_N_ACTIONS + a], (unsigned long long)log_mild);
+        if (best_cat[best_start[y] + i] != a) atomicAdd(&ys[EG_N_ACTIONS + a], (unsigned long long)log_mild);
       }
     }
   }
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__(256) eg_stats_argbest_kernel(const EgStatsPara
 
 __global__ void __launch_bounds__(320) eg_stats_pack_best_kernel(const eg_result* results, const eg_traj* trajs, uint32_t n, const double* best_score,
                                                                  const unsigned long long* best_index, unsigned long long first_global, uint32_t* record) {
-  // 16 + 64 + 1092 bytes = 293 words, one per thread
+  // 16 + 64 + 1088 bytes = 292 words, one per thread
   const unsigned long long raw = *best_index;
   const uint32_t idx = raw < n ? (uint32_t)raw : (n ? n - 1 : 0);
   const int w = threadIdx.x;

@@ -102,9 +102,12 @@ struct EgPolicyDevice {   // weights snapshot + the per-batch constants of updat
   uint32_t noop_boost;            // learning.rs:82: best is net-zero but costs > 8 * MAX_ACCEPTABLE_COST
   uint32_t has_best;
   // best strategy for replay iterations (force_best_actions, sampling.rs:78-145,242-313)
-  uint8_t n_best[EG_NY];
-  uint8_t n_best_deficit[EG_NY];
-  uint8_t best[EG_NY][EG_MAX_ACTIONS_PER_YEAR * 2];
-  uint8_t best_deficit[EG_NY][EG_MAX_ACTIONS_PER_YEAR];
+  // (lists of any length on the host; here back to back, year after year, like the rows of eg_traj)
+  uint16_t n_best[EG_NY];            // len(best_actions[y])
+  uint16_t n_best_deficit[EG_NY];    // len(best_deficit_actions[y])
+  uint16_t best_off[EG_NY];          // start of year y's list in best[]
+  uint16_t best_deficit_off[EG_NY];  // start of year y's list in best_deficit[]
+  uint8_t best[EG_BEST_CAPACITY];
+  uint8_t best_deficit[EG_TRAJ_CAPACITY];
   uint8_t sorted_idx[EG_NY][64];  // action code at each rank of scaled_sorted
 };

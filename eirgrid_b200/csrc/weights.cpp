@@ -190,24 +190,27 @@ bool read_action_lists(const egjson::Value* v, std::vector<uint8_t>* lists) {
 struct Recorded {
   std::vector<uint8_t> run[EG_NY], deficit[EG_NY];
   void from_traj(const eg_traj& t, bool replay) {
+    int row = 0;  // the year rows follow each other in the record; counts that run past its capacity are cut
     for (int y = 0; y < EG_NY; y++) {
       run[y].clear();
       deficit[y].clear();
-      int nd = std::min<int>(t.n_deficit[y], EG_MAX_ACTIONS_PER_YEAR);
-      int na = std::min<int>(t.n_additional[y], EG_MAX_ACTIONS_PER_YEAR - nd);
+      const int nd = std::min<int>(t.n_deficit[y], EG_TRAJ_CAPACITY - row);
+      const int na = std::min<int>(t.n_additional[y], EG_TRAJ_CAPACITY - row - nd);
+      const uint8_t* a = t.actions + row;
       // replay iterations record every sampled action twice (sampling.rs:97-99,262-264 + simulation.rs:197,406-409; quirk Q10)
       // (codes outside the key set never come from the device; a malformed record must not index the tables with them)
       for (int i = 0; i < nd; i++) {
-        if (t.actions[y][i] >= EG_N_ACTIONS) continue;
-        run[y].push_back(t.actions[y][i]);
-        deficit[y].push_back(t.actions[y][i]);
-        if (replay && i < 4) deficit[y].push_back(t.actions[y][i]);
+        if (a[i] >= EG_N_ACTIONS) continue;
+        run[y].push_back(a[i]);
+        deficit[y].push_back(a[i]);
+        if (replay && i < 4) deficit[y].push_back(a[i]);
       }
       for (int i = nd; i < nd + na; i++) {
-        if (t.actions[y][i] >= EG_N_ACTIONS) continue;
-        run[y].push_back(t.actions[y][i]);
-        if (replay) run[y].push_back(t.actions[y][i]);
+        if (a[i] >= EG_N_ACTIONS) continue;
+        run[y].push_back(a[i]);
+        if (replay) run[y].push_back(a[i]);
       }
+      row += nd + na;
     }
   }
 };
@@ -391,7 +394,7 @@ eg_weights::eg_weights() {  // ActionWeights::new, weights/core.rs:25-250
   }
 }
 
-void eg_weights_fill_policy(const eg_weights& W, EgPolicyDevice* out) {
+bool eg_weights_fill_policy(const eg_weights& W, EgPolicyDevice* out) {
   std::memset(out, 0, sizeof(*out));
   for (int y = 0; y < EG_NY; y++) {
     std::memcpy(&out->rows[y][0], W.w[y], sizeof(W.w[y]));
@@ -434,12 +437,19 @@ void eg_weights_fill_policy(const eg_weights& W, EgPolicyDevice* out) {
   out->has_count_weights = W.has_count_weights ? 1 : 0;
   out->noop_boost = (W.has_best && W.best_metrics[0] <= 0.0 && W.best_metrics[2] > kMaxCost * 8.0) ? 1 : 0;
   out->has_best = W.has_best ? 1 : 0;
+  size_t ob = 0, obd = 0;
+  bool fits = true;
   for (int y = 0; y < EG_NY; y++) {
-    out->n_best[y] = (uint8_t)std::min<size_t>(W.best_actions[y].size(), EG_MAX_ACTIONS_PER_YEAR * 2);
-    for (int i = 0; i < out->n_best[y]; i++) out->best[y][i] = W.best_actions[y][i];
-    out->n_best_deficit[y] = (uint8_t)std::min<size_t>(W.best_deficit_actions[y].size(), EG_MAX_ACTIONS_PER_YEAR);
-    for (int i = 0; i < out->n_best_deficit[y]; i++) out->best_deficit[y][i] = W.best_deficit_actions[y][i];
+    const size_t nb = std::min<size_t>(W.best_actions[y].size(), EG_BEST_CAPACITY - ob);
+    const size_t nbd = std::min<size_t>(W.best_deficit_actions[y].size(), EG_TRAJ_CAPACITY - obd);
+    fits = fits && nb == W.best_actions[y].size() && nbd == W.best_deficit_actions[y].size();
+    out->n_best[y] = (uint16_t)nb; out->best_off[y] = (uint16_t)ob;
+    out->n_best_deficit[y] = (uint16_t)nbd; out->best_deficit_off[y] = (uint16_t)obd;
+    for (size_t i = 0; i < nb; i++) out->best[ob + i] = W.best_actions[y][i];
+    for (size_t i = 0; i < nbd; i++) out->best_deficit[obd + i] = W.best_deficit_actions[y][i];
+    ob += nb; obd += nbd;
   }
+  return fits;
 }
 
 EgContrastConsts eg_contrast_consts(const eg_weights& W) {
@@ -497,14 +507,21 @@ int eg_weights_set_table(eg_weights* w, const eg_weights_table* t) {
   w->iwi = t->iterations_without_improvement;
   return EG_OK;
 }
-int eg_weights_get_best(const eg_weights* w, uint8_t n_best[EG_N_YEARS], uint8_t best[EG_N_YEARS][EG_MAX_ACTIONS_PER_YEAR * 2],
-                        uint8_t n_best_deficit[EG_N_YEARS], uint8_t best_deficit[EG_N_YEARS][EG_MAX_ACTIONS_PER_YEAR]) {
-  if (!w) return eg_fail(EG_ERR_INVALID, "eg_weights_get_best: NULL argument");
+int eg_weights_get_best(const eg_weights* w, uint32_t n_best[EG_N_YEARS], uint8_t* best, size_t best_capacity,
+                        uint32_t n_best_deficit[EG_N_YEARS], uint8_t* best_deficit, size_t best_deficit_capacity) {
+  if (!w || !n_best || !n_best_deficit) return eg_fail(EG_ERR_INVALID, "eg_weights_get_best: NULL argument");
+  size_t ob = 0, obd = 0;
   for (int y = 0; y < EG_NY; y++) {
-    n_best[y] = (uint8_t)std::min<size_t>(w->best_actions[y].size(), EG_MAX_ACTIONS_PER_YEAR * 2);
-    for (int i = 0; i < n_best[y]; i++) best[y][i] = w->best_actions[y][i];
-    n_best_deficit[y] = (uint8_t)std::min<size_t>(w->best_deficit_actions[y].size(), EG_MAX_ACTIONS_PER_YEAR);
-    for (int i = 0; i < n_best_deficit[y]; i++) best_deficit[y][i] = w->best_deficit_actions[y][i];
+    n_best[y] = (uint32_t)w->best_actions[y].size();
+    n_best_deficit[y] = (uint32_t)w->best_deficit_actions[y].size();
+    for (uint8_t a : w->best_actions[y]) {
+      if (best && ob < best_capacity) best[ob] = a;
+      ob++;
+    }
+    for (uint8_t a : w->best_deficit_actions[y]) {
+      if (best_deficit && obd < best_deficit_capacity) best_deficit[obd] = a;
+      obd++;
+    }
   }
   return w->has_best ? 1 : 0;
 }

@@ -35,8 +35,9 @@ struct eg_weights {
 double eg_score_default(const double m[4]);
 double eg_score(const double m[4], bool cost_only);
 
-// fills the device-side snapshot (weights + per-batch constants of update_weights + best lists)
-void eg_weights_fill_policy(const eg_weights& w, EgPolicyDevice* out);
+// fills the device-side snapshot (weights + per-batch constants of update_weights + best lists); false when the best
+// lists are longer than the snapshot's capacity (EG_BEST_CAPACITY / EG_TRAJ_CAPACITY slots) and were cut
+bool eg_weights_fill_policy(const eg_weights& w, EgPolicyDevice* out);
 
 // per-batch constants of the batch-synchronous contrast rule, shared by the stats kernel and the host apply
 struct EgContrastConsts {

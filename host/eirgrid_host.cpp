@@ -326,9 +326,8 @@ int main(int argc, char** argv) {
     const bool is_full_run = a.force_full_simulation || !cache_loaded || completed + final_full >= a.iterations;
     bool has_best = false;
     best_score_of(weights, &has_best);
-    uint8_t nb[EG_N_YEARS], nbd[EG_N_YEARS];
-    static uint8_t b[EG_N_YEARS][EG_MAX_ACTIONS_PER_YEAR * 2], bd[EG_N_YEARS][EG_MAX_ACTIONS_PER_YEAR];
-    const bool has_best_actions = eg_weights_get_best(weights, nb, b, nbd, bd) == 1;
+    uint32_t nb[EG_N_YEARS], nbd[EG_N_YEARS];
+    const bool has_best_actions = eg_weights_get_best(weights, nb, nullptr, 0, nbd, nullptr, 0) == 1;
     eg_run_cfg cfg{};
     cfg.cost_only = a.cost_only;
     cfg.enable_energy_sales = a.enable_energy_sales;

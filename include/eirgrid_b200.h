@@ -35,7 +35,12 @@ extern "C" {
 #define EG_N_ACTIONS 61                /* regular action keys per year, weights/core.rs:35-120 */
 #define EG_N_DEFICIT_KEYS 15           /* weights/core.rs:130-152 */
 #define EG_N_COUNT_KEYS 21             /* action counts 0..=20, weights/core.rs:163 */
-#define EG_MAX_ACTIONS_PER_YEAR 40     /* slots per year in eg_traj (deficit + additional) */
+#define EG_TRAJ_CAPACITY 984           /* action slots per EPISODE in eg_traj; year rows are stored back to back (CSR), so a
+                                          single year may hold all of them. The reference's Vec<GridAction> lists are unbounded
+                                          (simulation.rs:406-409, strategy.rs:188-196); an episode that outgrows the capacity is
+                                          flagged EG_FLAG_RECORD_OVERFLOW. Training episodes stay below 26 x ~21 actions; the
+                                          plant capacity (EG_MAX_NEW_GENERATORS) is reached first in compounding replay runs. */
+#define EG_BEST_CAPACITY (2 * EG_TRAJ_CAPACITY)  /* best_actions of a replay iteration hold every additional action twice (quirk Q10) */
 #define EG_SITE_NONE 0xFFFFu
 
 /* Action codes (uint8) — canonical key order == insertion order in ActionWeights::new:
@@ -61,7 +66,7 @@ typedef enum {
 /* eg_result.flags */
 #define EG_FLAG_GEN_OVERFLOW 1u     /* more than EG_MAX_NEW_GENERATORS new plants */
 #define EG_FLAG_OFFSET_OVERFLOW 2u  /* more than EG_MAX_OFFSETS offsets */
-#define EG_FLAG_YEAR_OVERFLOW 4u    /* more than EG_MAX_ACTIONS_PER_YEAR actions in one year */
+#define EG_FLAG_RECORD_OVERFLOW 4u  /* more than EG_TRAJ_CAPACITY actions in the episode: the simulation applied them all, the record is cut */
 #define EG_FLAG_NO_SITE 8u          /* placement search found no site with score > 0 (reference falls back; we flag) */
 #define EG_MAX_NEW_GENERATORS 560
 #define EG_MAX_OFFSETS 520
@@ -85,18 +90,19 @@ typedef struct {
   uint32_t reserved;
 } eg_result;
 
-/* Recorded actions of one episode: current_deficit_actions[y] followed by the additional actions
- * of year y (== current_run_actions[y], simulation.rs:406-409,197). 1092 B. */
+/* Recorded actions of one episode. Year y's row is current_deficit_actions[y] followed by the additional actions of
+ * year y (== current_run_actions[y], simulation.rs:406-409,197); the rows of 2025..2050 follow each other without gaps:
+ * row y starts at slot sum_{y' < y} (n_deficit[y'] + n_additional[y']). Unused slots are zero. 1088 B. */
 typedef struct {
-  uint8_t n_deficit[EG_N_YEARS];
-  uint8_t n_additional[EG_N_YEARS];
-  uint8_t actions[EG_N_YEARS][EG_MAX_ACTIONS_PER_YEAR];
+  uint16_t n_deficit[EG_N_YEARS];
+  uint16_t n_additional[EG_N_YEARS];
+  uint8_t actions[EG_TRAJ_CAPACITY];
 } eg_traj;
 
 /* Candidate-site index (i*grid_n + j of find_suitable_location's scan, metal_location_search.rs:120-124)
- * chosen for the action in the same slot of eg_traj; EG_SITE_NONE for actions that place nothing. */
+ * chosen for the action in the same slot of eg_traj; EG_SITE_NONE for actions that place nothing and for unused slots. */
 typedef struct {
-  uint16_t site[EG_N_YEARS][EG_MAX_ACTIONS_PER_YEAR];
+  uint16_t site[EG_TRAJ_CAPACITY];
 } eg_sites;
 
 /* Numeric fields of YearlyMetrics (analysis/metrics.rs:6-31). 144 B. */
@@ -222,12 +228,13 @@ int eg_weights_merge(eg_weights* dst, const eg_weights* other);
 int eg_weights_history_append(const eg_weights* w, uint64_t iteration, const char* history_path);
 int eg_weights_get_table(const eg_weights* w, eg_weights_table* out);
 int eg_weights_set_table(eg_weights* w, const eg_weights_table* in);
-/* best strategy lists (best_actions / best_deficit_actions, Option<HashMap<u32, Vec<GridAction>>>):
- * best_actions[y] in `actions`, best_deficit_actions[y] in `deficit` — counts in n_additional / n_deficit
- * fields are reused as list lengths (actions row = best_actions, which already contains the deficit
- * actions first, Appendix C of SURVEY.md). Returns 1 if a best strategy exists, 0 if not. */
-int eg_weights_get_best(const eg_weights* w, uint8_t n_best[EG_N_YEARS], uint8_t best[EG_N_YEARS][EG_MAX_ACTIONS_PER_YEAR * 2],
-                        uint8_t n_best_deficit[EG_N_YEARS], uint8_t best_deficit[EG_N_YEARS][EG_MAX_ACTIONS_PER_YEAR]);
+/* best strategy lists (best_actions / best_deficit_actions, Option<HashMap<u32, Vec<GridAction>>>), any length:
+ * n_best[y] = len(best_actions[y]) (which already contains the year's deficit actions first, Appendix C of SURVEY.md),
+ * n_best_deficit[y] = len(best_deficit_actions[y]); the lists themselves are written back to back, year after year, into
+ * `best` / `best_deficit` as far as their capacities reach (either may be NULL to query the lengths only).
+ * Returns 1 if a best strategy exists, 0 if not. */
+int eg_weights_get_best(const eg_weights* w, uint32_t n_best[EG_N_YEARS], uint8_t* best, size_t best_capacity,
+                        uint32_t n_best_deficit[EG_N_YEARS], uint8_t* best_deficit, size_t best_deficit_capacity);
 uint8_t eg_deficit_key_action(uint32_t deficit_key);
 
 /* ---- the hot path ------------------------------------------------------------------------------- */

@@ -215,6 +215,8 @@ void run_episode(const World& world, Weights& local, const eg_run_cfg& cfg, uint
 
 // the write-lock section multi_simulation.rs:494-508 for one finished episode
 bool update_shared(Weights& shared, const eg_result& r, const eg_traj& t, bool replay, Rng* rng);
+// the same with the episode's own unbounded lists (transfer_recorded_actions_from, strategy.rs:313-342) instead of a record
+bool update_shared_from(Weights& shared, const eg_result& r, const Weights& local, Rng* rng);
 
 // location analysis (map_handler.rs:1319-1433)
 double calculate_generator_suitability(const World& w, const std::vector<Generator>& gens, const Coord& c, int type);

@@ -143,14 +143,16 @@ void orc_weights_set_table(void* wp, const eg_weights_table* t) {
   w->has_count_weights = t->has_count_weights != 0;
   w->iteration_count = t->iteration_count; w->iwi = t->iterations_without_improvement;
 }
-int orc_weights_get_best(void* wp, uint8_t n_best[26], uint8_t best[26][EG_MAX_ACTIONS_PER_YEAR * 2],
-                         uint8_t n_best_deficit[26], uint8_t best_deficit[26][EG_MAX_ACTIONS_PER_YEAR]) {
+// list lengths per year and the lists back to back (either buffer may be NULL / too small: written as far as it reaches)
+int orc_weights_get_best(void* wp, uint32_t n_best[26], uint8_t* best, size_t best_cap, uint32_t n_best_deficit[26],
+                         uint8_t* best_deficit, size_t best_deficit_cap) {
   Weights* w = (Weights*)wp;
+  size_t ob = 0, obd = 0;
   for (int y = 0; y < 26; y++) {
-    n_best[y] = (uint8_t)std::min<size_t>(w->best_actions[y].size(), EG_MAX_ACTIONS_PER_YEAR * 2);
-    for (int i = 0; i < n_best[y]; i++) best[y][i] = w->best_actions[y][i];
-    n_best_deficit[y] = (uint8_t)std::min<size_t>(w->best_deficit_actions[y].size(), EG_MAX_ACTIONS_PER_YEAR);
-    for (int i = 0; i < n_best_deficit[y]; i++) best_deficit[y][i] = w->best_deficit_actions[y][i];
+    n_best[y] = (uint32_t)w->best_actions[y].size();
+    n_best_deficit[y] = (uint32_t)w->best_deficit_actions[y].size();
+    for (uint8_t a : w->best_actions[y]) { if (best && ob < best_cap) best[ob] = a; ob++; }
+    for (uint8_t a : w->best_deficit_actions[y]) { if (best_deficit && obd < best_deficit_cap) best_deficit[obd] = a; obd++; }
   }
   return w->has_best ? 1 : 0;
 }
@@ -228,6 +230,41 @@ int orc_update(void* weights, const eg_result* results, const eg_traj* trajs, ui
     Metrics m{results[i].net_emissions, results[i].public_opinion, results[i].total_cost, results[i].power_reliability};
     double sc = score_metrics(m, false);
     if (s.batch_best_episode < 0 || sc > s.batch_best_score) { s.batch_best_score = sc; s.batch_best_episode = i; }
+  }
+  s.iterations_without_improvement = W->iwi;
+  s.best_score = W->has_best ? score_metrics(W->best_metrics, false) : 0.0;
+  if (stats) *stats = s;
+  return 0;
+}
+
+// One batch of the reference loop with the reference's own bookkeeping: n episodes run against ONE snapshot of the shared
+// weights (threads), then the write-lock section for each of them in episode order, fed from the episode's own unbounded
+// action lists (transfer_recorded_actions_from) — no eg_traj in between. Results and records are written out as well
+// (a record longer than EG_TRAJ_CAPACITY is flagged there, the update still sees the full lists).
+int orc_train_batch(void* wp, void* weights, const eg_run_cfg* cfg, uint64_t seed, uint64_t first_episode, uint32_t n,
+                    int mode, int threads, uint64_t rng_seed, eg_result* out, eg_traj* traj, eg_update_stats* stats) {
+  World* world = (World*)wp;
+  if (mode == FAST && !world->fast_ready) return -1;
+  Weights* W = (Weights*)weights;
+  const Weights snap = *W;
+  std::vector<Weights> locals(n, snap);  // multi_simulation.rs:457-460
+  std::vector<eg_result> res(n);
+  parallel_for_impl(n, threads, [&](uint32_t i) {
+    EpisodeIO io;
+    io.result = &res[i];
+    io.traj = traj ? traj + i : nullptr;
+    run_episode(*world, locals[i], *cfg, seed, first_episode + i, io, (Mode)mode, false);
+  });
+  eg_update_stats s;
+  std::memset(&s, 0, sizeof(s));
+  s.batch_best_episode = -1;
+  s.n_episodes = n;
+  for (uint32_t i = 0; i < n; i++) {
+    Rng rng(rng_seed, W->iteration_count, 0x55504454u);
+    if (update_shared_from(*W, res[i], locals[i], &rng)) s.n_improvements++;
+    if (res[i].flags) s.n_flagged++;
+    if (s.batch_best_episode < 0 || res[i].score > s.batch_best_score) { s.batch_best_score = res[i].score; s.batch_best_episode = i; }
+    if (out) out[i] = res[i];
   }
   s.iterations_without_improvement = W->iwi;
   s.best_score = W->has_best ? score_metrics(W->best_metrics, false) : 0.0;

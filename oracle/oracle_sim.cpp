@@ -244,19 +244,33 @@ struct Recorder {
     if (traj) std::memset(traj, 0, sizeof(*traj));
     if (sites) std::memset(sites, 0xFF, sizeof(*sites));
   }
-  int slots[NY] = {0};
+  // The C-ABI record eg_traj stores the year rows back to back in EG_TRAJ_CAPACITY slots (years are visited in order, and
+  // within a year the deficit actions come first, so appending keeps the layout). The reference's own lists are the
+  // unbounded Weights::current_run_actions / current_deficit_actions, which run_episode fills as well.
+  int used = 0;
   void push(int y, bool deficit, uint8_t action, int site) {
     if (deficit) n_def_total++; else n_add_total++;
-    int s = slots[y];
-    if (s >= EG_MAX_ACTIONS_PER_YEAR) { flags |= EG_FLAG_YEAR_OVERFLOW; return; }
-    slots[y] = s + 1;
+    if (used >= EG_TRAJ_CAPACITY) { flags |= EG_FLAG_RECORD_OVERFLOW; return; }
+    const int s = used++;
     if (traj) {
-      traj->actions[y][s] = action;
+      traj->actions[s] = action;
       if (deficit) traj->n_deficit[y]++; else traj->n_additional[y]++;
     }
-    if (sites) sites->site[y][s] = site >= 0 ? (uint16_t)site : (uint16_t)EG_SITE_NONE;
+    if (sites) sites->site[s] = site >= 0 ? (uint16_t)site : (uint16_t)EG_SITE_NONE;
   }
 };
+
+// first slot of year y's row in a record, and the row's (deficit, additional) lengths cut at the capacity
+struct RowView { int row, nd, na; };
+RowView row_of(const eg_traj& t, int y) {
+  int row = 0;
+  for (int k = 0; k < y; k++) {
+    const int nd = std::min<int>(t.n_deficit[k], EG_TRAJ_CAPACITY - row);
+    row += nd + std::min<int>(t.n_additional[k], EG_TRAJ_CAPACITY - row - nd);
+  }
+  const int nd = std::min<int>(t.n_deficit[y], EG_TRAJ_CAPACITY - row);
+  return {row, nd, std::min<int>(t.n_additional[y], EG_TRAJ_CAPACITY - row - nd)};
+}
 
 // core/simulation.rs:319-522
 void handle_power_deficit(EpMap& map, double deficit, int year, Weights& W, Rng& rng, const eg_traj* replay_in, Recorder& rec) {
@@ -269,8 +283,9 @@ void handle_power_deficit(EpMap& map, double deficit, int year, Weights& W, Rng&
     attempts += 1;
     uint8_t action;
     if (replay_in) {
-      // counts above the row capacity (malformed input) are read as the capacity
-      action = replay_pos < std::min<int>(replay_in->n_deficit[y], EG_MAX_ACTIONS_PER_YEAR) ? replay_in->actions[y][replay_pos] : (uint8_t)(3 * BatteryStorage);
+      // counts that run past the record's capacity (malformed input) are cut there
+      const RowView rv = row_of(*replay_in, y);
+      action = replay_pos < rv.nd ? replay_in->actions[rv.row + replay_pos] : (uint8_t)(3 * BatteryStorage);
       replay_pos++;
     } else if (attempts < 5) {
       action = sample_deficit_action(W, year, rng);
@@ -351,14 +366,14 @@ void run_episode(const World& world, Weights& W, const eg_run_cfg& cfg, uint64_t
     ActionResult current_state = map.state(year);
     if (current_state.balance < 0.0) handle_power_deficit(map, -current_state.balance, year, W, rng, io.replay_in, rec);
     uint32_t num_additional;
-    if (io.replay_in) num_additional = io.replay_in->n_additional[y];
+    if (io.replay_in) num_additional = (uint32_t)row_of(*io.replay_in, y).na;
     else if (W.force_best_actions) num_additional = W.has_best ? (uint32_t)W.best_actions[y].size() : 0;  // :146-162
     else num_additional = sample_additional_actions(W, year, rng);
     for (uint32_t i = 0; i < num_additional; i++) {
       uint8_t action;
       if (io.replay_in) {
-        int pos = std::min<int>(io.replay_in->n_deficit[y], EG_MAX_ACTIONS_PER_YEAR) + (int)i;
-        action = pos < EG_MAX_ACTIONS_PER_YEAR ? io.replay_in->actions[y][pos] : (uint8_t)EG_ACT_DO_NOTHING;
+        const RowView rv = row_of(*io.replay_in, y);
+        action = io.replay_in->actions[rv.row + rv.nd + (int)i];
       } else {
         action = sample_action(W, year, rng);
       }

@@ -412,24 +412,45 @@ void apply_deficit_contrast_learning(Weights& W, Rng* rng) {
 // `replay` reproduces the double recording of replay iterations (quirk Q10): sampled actions are pushed by
 // sample_*_action's replay branch AND by the caller; the forced battery (attempt >= 5) only by the caller.
 void transfer_recorded_actions(Weights& W, const eg_traj& t, bool replay) {
+  int row = 0;
   for (int y = 0; y < NY; y++) {
     W.current_run_actions[y].clear();
     W.current_deficit_actions[y].clear();
-    int nd = std::min<int>(t.n_deficit[y], EG_MAX_ACTIONS_PER_YEAR);
-    int na = std::min<int>(t.n_additional[y], EG_MAX_ACTIONS_PER_YEAR - nd);
+    int nd = std::min<int>(t.n_deficit[y], EG_TRAJ_CAPACITY - row);
+    int na = std::min<int>(t.n_additional[y], EG_TRAJ_CAPACITY - row - nd);
+    const uint8_t* a = t.actions + row;
     for (int i = 0; i < nd; i++) {
-      W.current_run_actions[y].push_back(t.actions[y][i]);
-      W.current_deficit_actions[y].push_back(t.actions[y][i]);
-      if (replay && i < 4) W.current_deficit_actions[y].push_back(t.actions[y][i]);
+      W.current_run_actions[y].push_back(a[i]);
+      W.current_deficit_actions[y].push_back(a[i]);
+      if (replay && i < 4) W.current_deficit_actions[y].push_back(a[i]);
     }
     for (int i = nd; i < nd + na; i++) {
-      W.current_run_actions[y].push_back(t.actions[y][i]);
-      if (replay) W.current_run_actions[y].push_back(t.actions[y][i]);
+      W.current_run_actions[y].push_back(a[i]);
+      if (replay) W.current_run_actions[y].push_back(a[i]);
     }
+    row += nd + na;
   }
 }
 
-bool update_shared(Weights& shared, const eg_result& r, const eg_traj& t, bool replay, Rng* rng) {  // multi_simulation.rs:494-508
+// strategy.rs:313-342 as the reference does it: the episode's own (unbounded) lists are copied over
+void transfer_recorded_actions_from(Weights& W, const Weights& local) {
+  for (int y = 0; y < NY; y++) {
+    W.current_run_actions[y] = local.current_run_actions[y];
+    W.current_deficit_actions[y] = local.current_deficit_actions[y];
+  }
+}
+
+bool update_shared_from(Weights& shared, const eg_result& r, const Weights& local, Rng* rng) {  // multi_simulation.rs:494-508
+  transfer_recorded_actions_from(shared, local);
+  Metrics m{r.net_emissions, r.public_opinion, r.total_cost, r.power_reliability};
+  uint32_t before = (uint32_t)shared.improvement_history.size();
+  apply_contrast_learning(shared, m, rng);
+  update_best_strategy(shared, m);
+  apply_deficit_contrast_learning(shared, rng);
+  return shared.improvement_history.size() != before;
+}
+
+bool update_shared(Weights& shared, const eg_result& r, const eg_traj& t, bool replay, Rng* rng) {  // the same from a C-ABI record
   transfer_recorded_actions(shared, t, replay);
   Metrics m{r.net_emissions, r.public_opinion, r.total_cost, r.power_reliability};
   uint32_t before = (uint32_t)shared.improvement_history.size();

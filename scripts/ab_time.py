@@ -18,7 +18,7 @@ ctx.map_load_dir(os.path.join(ROOT, "tests", "golden", "ireland_map"))
 w = _lib.Weights()
 ctx.weights_upload(w)
 d_res = torch.empty(n * 64, dtype=torch.uint8, device=dev)
-d_traj = torch.empty(n * 1092, dtype=torch.uint8, device=dev)
+d_traj = torch.empty(n * 1088, dtype=torch.uint8, device=dev)
 torch.cuda.synchronize()
 times = []
 for r in range(reps):

@@ -11,6 +11,7 @@ ctx = tr.ctx
 for g in range(4):
     cfg = _abi.RunCfg(replay_best=1)
     res, traj, _, _ = ctx.rollout(w, 4096, seed=99, first_episode=10**7 + g * 4096, cfg=cfg)
-    has, nb, b, nd, d = w.best()
+    has, b, d = w.best()
+    nb, nd = np.array([len(x) for x in b]), np.array([len(x) for x in d])
     st = w.update(res, traj, replay_best=True, rng_seed=99)
     print("replay gen", g, "flags hist", np.bincount(res["flags"], minlength=16)[:9].tolist(), "best list max", int(nb.max()), "deficit list max", int(nd.max()), "improved", st.n_improvements, "flagged", st.n_flagged)

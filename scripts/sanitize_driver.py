@@ -16,7 +16,7 @@ t = w.table(); t.iterations_without_improvement = 900; w.set_table(t)
 res, traj, _, _ = ctx.rollout(w, 96, seed=4)
 rres, rsites, _ = ctx.replay(traj)
 assert np.array_equal(rres["total_cost"], res["total_cost"])
-stats = np.zeros(_abi.STATS_WORDS, np.int64); rec = np.zeros(16 + 64 + 1092, np.uint8)
+stats = np.zeros(_abi.STATS_WORDS, np.int64); rec = np.zeros(16 + 64 + 1088, np.uint8)
 cfg = _abi.RunCfg()
 _lib.check(_lib.lib().eg_train_batch_begin(ctx.h, w.h, __import__("ctypes").byref(cfg), 5, 0, 96))
 _lib.check(_lib.lib().eg_train_batch_end(ctx.h, _abi.ptr(stats), _abi.ptr(rec)))

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Freeze the oracle's outputs (round 1): tests/golden/oracle_frozen_r01.npz.
+"""Freeze the oracle's outputs: tests/golden/oracle_frozen_r02.npz (round 2: eg_traj / eg_sites store the year rows back to
+back; oracle_frozen_r01.npz is the same content in round 1's fixed 40-slots-per-year layout and is still checked).
 
 Everything except the population table, the 2025 generation and the location analysis is "parity unpinned" against the
 reference: the oracle's reading of the Rust code is the definition the CUDA path is held to. This fixture
@@ -34,6 +35,7 @@ def frozen_outputs():
     t = w.table()
     out["updated_table_sha1"] = np.frombuffer(hashlib.sha1(bytes(t)).digest(), np.uint8)
     out["updated_weights_2025"] = np.array(t.weights[0][:], np.float64)
+    out["updated_weights"], out["updated_deficit_weights"], _ = t.arrays()
     out["updated_iwi"] = np.array([t.iterations_without_improvement, t.iteration_count], np.int64)
     for iwi in (150, 600, 1300):
         t = w.table()
@@ -50,5 +52,5 @@ def frozen_outputs():
 
 if __name__ == "__main__":
     o = frozen_outputs()
-    np.savez_compressed(os.path.join(HERE, "oracle_frozen_r01.npz"), **o)
+    np.savez_compressed(os.path.join(HERE, "oracle_frozen_r02.npz"), **o)
     print("wrote", len(o), "arrays;", "mean score %.6f" % o["initial_results"]["score"].mean())

@@ -76,7 +76,9 @@ def lib():
         L.orc_score.restype = C.c_double
         L.orc_weights_get_table.argtypes = [C.c_void_p, C.POINTER(_abi.WeightsTable)]
         L.orc_weights_set_table.argtypes = [C.c_void_p, C.POINTER(_abi.WeightsTable)]
-        L.orc_weights_get_best.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_weights_get_best.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.orc_train_batch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_abi.RunCfg), C.c_uint64, C.c_uint64, C.c_uint32,
+                                      C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(_abi.UpdateStats)]
         L.orc_rollout.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_abi.RunCfg), C.c_uint64, C.c_uint64, C.c_uint32,
                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_replay.argtypes = [C.c_void_p, C.POINTER(_abi.RunCfg), C.c_void_p, C.c_uint32, C.c_int, C.c_int,
@@ -236,12 +238,26 @@ class Weights:
         self.L.orc_weights_set_table(self.h, C.byref(t))
 
     def best(self):
-        nb = np.zeros(26, np.uint8)
-        b = np.zeros((26, 80), np.uint8)
-        nd = np.zeros(26, np.uint8)
-        d = np.zeros((26, 40), np.uint8)
-        has = self.L.orc_weights_get_best(self.h, _abi.ptr(nb), _abi.ptr(b), _abi.ptr(nd), _abi.ptr(d))
-        return bool(has), nb, b, nd, d
+        """(has_best, best_actions, best_deficit_actions): two lists of 26 uint8 arrays of any length"""
+        nb, nd = np.zeros(26, np.uint32), np.zeros(26, np.uint32)
+        has = self.L.orc_weights_get_best(self.h, _abi.ptr(nb), None, 0, _abi.ptr(nd), None, 0)
+        b, d = np.zeros(max(int(nb.sum()), 1), np.uint8), np.zeros(max(int(nd.sum()), 1), np.uint8)
+        self.L.orc_weights_get_best(self.h, _abi.ptr(nb), _abi.ptr(b), b.size, _abi.ptr(nd), _abi.ptr(d), d.size)
+        ob, od = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64), np.concatenate([[0], np.cumsum(nd)]).astype(np.int64)
+        return (bool(has), [b[ob[y]:ob[y + 1]].copy() for y in range(26)], [d[od[y]:od[y + 1]].copy() for y in range(26)])
+
+    def train_batch(self, world, n, seed=1, first_episode=0, cfg=None, mode=FAST, threads=0, rng_seed=0):
+        """One batch of the reference loop with the episodes' own unbounded action lists (no eg_traj between rollout
+        and update). Returns (results, records, stats); the records are for comparison only."""
+        cfg = cfg or _abi.RunCfg()
+        threads = threads or (os.cpu_count() or 1)
+        res = np.zeros(n, _abi.RESULT_DTYPE)
+        traj = np.zeros(n, _abi.TRAJ_DTYPE)
+        st = _abi.UpdateStats()
+        rc = self.L.orc_train_batch(world.h, self.h, C.byref(cfg), seed, first_episode, n, mode, threads, rng_seed,
+                                    _abi.ptr(res), _abi.ptr(traj), C.byref(st))
+        assert rc == 0
+        return res, traj, st
 
     def update(self, results, trajs, replay=False, rng_seed=0):
         st = _abi.UpdateStats()

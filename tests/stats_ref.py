@@ -59,11 +59,11 @@ def batch_stats(results, trajs, consts, best, best_deficit):
                     log_pen = int(np.rint(math.log(1.0 / (1.0 + consts["alr"] * 1.5 * combined)) * FIXED))
                     log_mild = int(np.rint(math.log(1.0 / (1.0 + consts["alr"] * combined * 0.5)) * FIXED))
                 stats[1] += 1
+        rows = _abi.traj_rows(t)
         for y in range(26):
             base = HEADER + y * YEAR_STRIDE
-            nd = min(int(t["n_deficit"][y]), 40)
-            na = min(int(t["n_additional"][y]), 40 - nd)
-            run = [int(a) for a in t["actions"][y][:nd + na]]
+            nd = len(rows[y][0])
+            run = [int(a) for a in rows[y][0]] + [int(a) for a in rows[y][1]]
             cur = run + run[:nd]
             cb = list(best[y]) + list(best_deficit[y])
             for i, a in enumerate(cur):

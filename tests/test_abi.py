@@ -30,8 +30,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_sizes_match_header():
-    assert _abi.RESULT_DTYPE.itemsize == 64 and _abi.TRAJ_DTYPE.itemsize == 1092
-    assert _abi.SITES_DTYPE.itemsize == 2080 and _abi.YEAR_DTYPE.itemsize == 144
+    assert _abi.RESULT_DTYPE.itemsize == 64 and _abi.TRAJ_DTYPE.itemsize == 1088
+    assert _abi.SITES_DTYPE.itemsize == 1968 and _abi.YEAR_DTYPE.itemsize == 144
     assert C.sizeof(_abi.WeightsTable) == 8 * (26 * (61 + 15 + 21) + 6) + 16
     assert C.sizeof(_abi.RunCfg) == 32 and C.sizeof(_abi.UpdateStats) == 48
 
@@ -59,7 +59,7 @@ def test_sequential_update_matches_oracle(oracle_world):
         assert (so.n_improvements, so.iterations_without_improvement, so.best_score) == \
                (sg.n_improvements, sg.iterations_without_improvement, sg.best_score)
         bo, bg = ow.best(), gw.best()
-        assert bo[0] == bg[0] and all(np.array_equal(a, b) for a, b in zip(bo[1:], bg[1:]))
+        assert bo[0] == bg[0] and all(np.array_equal(a, b) for a, b in zip(bo[1] + bo[2], bg[1] + bg[2]))
     # stagnation regimes: forced contrast (> 800) and randomisation (> 1200)
     for iwi in (850, 1300):
         t = ow.table()
@@ -100,7 +100,8 @@ def test_weights_json_schema_and_roundtrip(tmp_path, oracle_world):
     assert t2.has_count_weights == 0  # action_count_weights are not serialised (weights/serialization.rs:474)
     assert (t2.has_best, t2.iteration_count, t2.iterations_without_improvement) == (1, t1.iteration_count, t1.iterations_without_improvement)
     assert list(t2.best_metrics) == list(t1.best_metrics)
-    assert all(np.array_equal(a, b) for a, b in zip(gw.best()[1:], g2.best()[1:]))
+    b1, b2 = gw.best(), g2.best()
+    assert all(np.array_equal(a, b) for a, b in zip(b1[1] + b1[2], b2[1] + b2[2]))
     # merge == update_weights_from: weights overwritten, iteration_count = max
     fresh = _lib.Weights()
     fresh.update_weights_from(g2)

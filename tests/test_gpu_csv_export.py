@@ -26,8 +26,8 @@ def test_best_run_csv_matches_replay_and_reference_layout(gpu_ctx, oracle_world,
     iy = text.index("Yearly Summary Metrics")
     assert text[iy + 1].startswith("Year,Population,PowerUsage,PowerGeneration,PowerBalance,PublicOpinion,YearlyCapitalCost")
     # the best episode of the batch, replayed by the oracle: same yearly rows and final metrics
-    has, nb, b, nd, d = w.best()
     k = int(np.lexsort((np.arange(len(res)), -res["score"]))[0])
+    rec = _abi.traj_rows(traj[k])  # 26 x (deficit actions, additional actions)
     eres, _, _, eyearly = oracle_world.replay(traj[k:k + 1])
     assert float(text[4].split(",")[1]) == eres["net_emissions"][0]
     assert text[6].split(",")[1] == "%.2f" % eres["total_cost"][0]
@@ -44,7 +44,7 @@ def test_best_run_csv_matches_replay_and_reference_layout(gpu_ctx, oracle_world,
     want = sum(int(traj[k]["n_additional"][y]) for y in range(26))
     assert len(acts) == want
     first_year_with = next(y for y in range(26) if traj[k]["n_additional"][y])
-    a0 = int(traj[k]["actions"][first_year_with][traj[k]["n_deficit"][first_year_with]])
+    a0 = int(rec[first_year_with][1][0])
     assert int(acts[0][0]) == 2025 + first_year_with
     assert acts[0][1] == ("AddGenerator" if a0 < 45 else "AddCarbonOffset" if a0 < 57 else acts[0][1])
     if a0 < 45:
@@ -68,7 +68,7 @@ def test_best_run_csv_matches_replay_and_reference_layout(gpu_ctx, oracle_world,
     ids_2025 = [r[1] for r in per_year[0]]
     assert all(i.startswith("Gen_") and i.split("_")[2] == "2025" for i in ids_2025)
     assert [int(i.split("_")[3]) for i in ids_2025] == list(range(59, 59 + len(ids_2025)))
-    kinds = [int(a) // 3 for a in traj[k]["actions"][0][: traj[k]["n_deficit"][0] + traj[k]["n_additional"][0]] if a < 45]
+    kinds = [int(a) // 3 for a in list(rec[0][0]) + list(rec[0][1]) if a < 45]
     assert [r[2] for r in per_year[0]] == [_abi.GEN_TYPES[t] for t in kinds]
     r = per_year[0][0]
     h = sum(ord(ch) for ch in r[1])                                   # id-hash coordinates, csv_export.rs:867-869
@@ -84,8 +84,7 @@ def test_best_run_csv_matches_replay_and_reference_layout(gpu_ctx, oracle_world,
     # yearly_details/carbon_offsets.csv: offsets stay Planned on the export map, so the offset columns are zero (csv_export.rs:987-1093)
     off = open(os.path.join(out, "yearly_details", "carbon_offsets.csv"), encoding="utf-8").read().strip().split("\n")
     assert off[0].startswith("Year,Offset ID,Type,X,Y,Size,Capture Efficiency (%),Power Consumption (MW),CO2 Offset (tonnes),Negative CO2 Emissions (tonnes),Cost (€)")
-    codes = [(2025 + y, int(a)) for y in range(26)
-             for a in traj[k]["actions"][y][traj[k]["n_deficit"][y]: traj[k]["n_deficit"][y] + traj[k]["n_additional"][y]] if 45 <= a < 57]
+    codes = [(2025 + y, int(a)) for y in range(26) for a in rec[y][1] if 45 <= a < 57]
     orow = [r.split(",") for r in off[1:]]
     assert len(orow) == sum(2051 - yr for yr, _ in codes)
     if codes:

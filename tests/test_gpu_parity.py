@@ -84,12 +84,9 @@ def test_replay_matches_oracle_and_rollout(gpu_ctx, oracle_world):
 def test_replay_edge_cases(gpu_ctx, oracle_world):
     """Empty record (deficit handler falls back to batteries), a full year of DoNothing, ragged years."""
     t = np.zeros(4, _abi.TRAJ_DTYPE)
-    t["n_additional"][1, :] = 20
-    t["actions"][1, :, :20] = _abi.ACT_DO_NOTHING
-    t["n_additional"][2, ::3] = 5
-    t["actions"][2, ::3, :5] = [15, 45, 57, 40, 3]
-    t["n_deficit"][3, 0] = 2  # too few deficit actions: battery fallback completes the year
-    t["actions"][3, 0, :2] = [24, 21]
+    t[1] = _abi.pack_traj([([], [_abi.ACT_DO_NOTHING] * 20)] * 26)
+    t[2] = _abi.pack_traj([([], [15, 45, 57, 40, 3] if y % 3 == 0 else []) for y in range(26)])
+    t[3] = _abi.pack_traj([([24, 21], [])] + [([], [])] * 25)  # too few deficit actions: battery fallback completes the year
     res, sites, yearly = gpu_ctx.replay(t)
     eres, etraj, esites, eyearly = oracle_world.replay(t)
     assert sites.tobytes() == esites.tobytes()

@@ -14,8 +14,8 @@ ASSETS = os.path.join(ROOT, "tests", "golden", "ireland_map")
 
 
 def _best_lists(w):
-    has, nb, b, nd, d = w.best()
-    return [b[y, :nb[y]].tolist() for y in range(26)], [d[y, :nd[y]].tolist() for y in range(26)]
+    has, b, d = w.best()
+    return [x.tolist() for x in b], [x.tolist() for x in d]
 
 
 @pytest.mark.parametrize("iwi", [0, 40, 900])
@@ -65,10 +65,9 @@ def test_trainer_steps_learn_and_are_deterministic():
     assert (res["flags"] == 0).all() and (res["power_reliability"] == 1.0).all()
     # the stored best strategy is the batch winner's record
     k = s1.batch_best_episode
-    has, nb, b, nd, d = tr.weights.best()
-    for y in range(26):
-        n = int(traj[k]["n_deficit"][y]) + int(traj[k]["n_additional"][y])
-        assert nb[y] == n and b[y, :n].tolist() == traj[k]["actions"][y, :n].tolist()
+    has, b, d = tr.weights.best()
+    for y, (dd, aa) in enumerate(_abi.traj_rows(traj[k])):
+        assert b[y].tolist() == dd.tolist() + aa.tolist() and d[y].tolist() == dd.tolist()
     s2 = tr.step()
     assert tr.weights.table().iteration_count == 8192
     assert s2.best_score >= s1.best_score
@@ -114,8 +113,8 @@ def test_flagged_episodes_are_counted(gpu_ctx):
     rs = np.random.RandomState(5)
     n = 64
     t = np.zeros(n, _abi.TRAJ_DTYPE)
-    t["n_additional"][:8, :] = 40
-    t["actions"][:8] = rs.randint(0, 45, (8, 26, 40))   # 1040 plants: over the 560-plant capacity
+    t["n_additional"][:8, :] = 37
+    t["actions"][:8, :26 * 37] = rs.randint(0, 45, (8, 26 * 37))   # 962 plants: over the 560-plant capacity
     t["n_additional"][8:, 0] = 1
     res, _, _ = gpu_ctx.replay(t)
     assert int((res["flags"] != 0).sum()) == 8

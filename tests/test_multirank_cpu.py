@@ -25,8 +25,8 @@ def _free_port():
 
 
 def _best_lists(w):
-    has, nb, b, nd, d = w.best()
-    return [b[y, :nb[y]].tolist() for y in range(26)], [d[y, :nd[y]].tolist() for y in range(26)]
+    has, b, d = w.best()
+    return [x.tolist() for x in b], [x.tolist() for x in d]
 
 
 def _setup_weights():

@@ -133,10 +133,11 @@ def test_episode_invariants(oracle_world):
     assert (y["total_population"] == np.array(README_POP)[None, :]).all()
     # 2025 starts with no plant online (quirk Q1): every episode needs deficit actions that year
     assert (traj["n_deficit"][:, 0] >= 4).all()
-    n_gen_actions = ((traj["actions"] < 45) & (np.arange(40)[None, None, :] < (traj["n_deficit"] + traj["n_additional"])[:, :, None])).sum((1, 2))
+    used = _abi.traj_row_starts(traj)[:, -1]
+    n_gen_actions = ((traj["actions"] < 45) & (np.arange(_abi.TRAJ_CAPACITY)[None, :] < used[:, None])).sum(1)
     assert (n_gen_actions == res["n_generators"]).all()
     placed = sites["site"] != _abi.SITE_NONE
-    assert (placed.sum((1, 2)) == res["n_generators"]).all()
+    assert (placed.sum(1) == res["n_generators"]).all()
     # a site is never reused inside an episode: a plant on the site zeroes its score
     for e in range(8):
         s = sites["site"][e][placed[e]]
@@ -149,16 +150,14 @@ def test_update_sequence_properties(oracle_world):
     st = w.update(res, traj)
     t = w.table()
     assert t.has_best and t.iteration_count == 32 and st.n_improvements >= 1
-    has, nb, b, nd, d = w.best()
+    has, b, d = w.best()
     assert has
     k = st.batch_best_episode
     # the stored best strategy is the best episode's record (best_actions = deficit actions then additional ones)
     last_improve = max(i for i in range(32) if res["score"][i] == res["score"][:i + 1].max() and (i == 0 or res["score"][i] > res["score"][:i].max()))
     e = traj[last_improve]
-    for y in range(26):
-        n = int(e["n_deficit"][y]) + int(e["n_additional"][y])
-        assert nb[y] == n and b[y, :n].tolist() == e["actions"][y, :n].tolist()
-        assert nd[y] == e["n_deficit"][y]
+    for y, (dd, aa) in enumerate(_abi.traj_rows(e)):
+        assert b[y].tolist() == dd.tolist() + aa.tolist() and d[y].tolist() == dd.tolist()
     assert res["score"][k] == res["score"].max()
     w_arr = t.arrays()[0]
     assert w_arr.min() >= 0.0001 and w_arr.max() <= 0.999
@@ -166,16 +165,30 @@ def test_update_sequence_properties(oracle_world):
 
 def test_oracle_outputs_are_frozen():
     """The oracle is the definition the CUDA path is held to wherever the reference pins nothing. Its outputs
-    for a fixed set of inputs are frozen in tests/golden/oracle_frozen_r01.npz (made by make_oracle_frozen.py): a change of
-    the oracle, of the compiler flags or of libm underneath it must show up here, not move the target silently."""
+    for a fixed set of inputs are frozen in tests/golden/oracle_frozen_r02.npz (made by make_oracle_frozen.py): a change of
+    the oracle, of the compiler flags or of libm underneath it must show up here, not move the target silently. Round 2 changed
+    the LAYOUT of the action record (year rows back to back instead of 40 slots a year); round 1's fixture is still held:
+    everything that does not depend on the layout byte for byte, and its records after conversion to the new layout."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_oracle_frozen", os.path.join(GOLDEN, "make_oracle_frozen.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     now = mod.frozen_outputs()
-    frozen = np.load(os.path.join(GOLDEN, "oracle_frozen_r01.npz"))
+    frozen = np.load(os.path.join(GOLDEN, "oracle_frozen_r02.npz"))
     assert sorted(frozen.files) == sorted(now.keys())
     for k in frozen.files:
         a, b = frozen[k], now[k]
         assert a.dtype == b.dtype and a.shape == b.shape, k
         assert a.tobytes() == b.tobytes(), k
+    r01 = np.load(os.path.join(GOLDEN, "oracle_frozen_r01.npz"))
+    for k in r01.files:
+        if k == "initial_traj":  # round 1 layout: actions[26][40] with u8 counts
+            old = r01[k]
+            conv = np.zeros(len(old), _abi.TRAJ_DTYPE)
+            for e in range(len(old)):
+                conv[e] = _abi.pack_traj([(old["actions"][e, y, :old["n_deficit"][e, y]],
+                                           old["actions"][e, y, old["n_deficit"][e, y]:old["n_deficit"][e, y] + old["n_additional"][e, y]])
+                                          for y in range(26)])
+            assert conv.tobytes() == now[k].tobytes()
+        elif not k.endswith("traj_sha1") and not k.endswith("sites_sha1"):
+            assert r01[k].tobytes() == now[k].tobytes(), k

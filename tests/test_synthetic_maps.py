@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from eirgrid_b200 import _lib, synthetic
+from eirgrid_b200 import _abi, _lib, synthetic
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ASSETS = os.path.join(ROOT, "tests", "golden", "ireland_map")
@@ -51,7 +51,9 @@ def test_oracle_runs_on_a_synthetic_map():
     w = O.World.from_arrays(*m)
     res, traj, sites, yearly = w.rollout(O.Weights(), 16, seed=3)
     assert (res["flags"] == 0).all() and (res["n_generators"] > 0).all()
-    assert sites["site"][traj["n_deficit"][:, :, None].astype(int) > np.arange(40)[None, None, :]].max() < 21 * 21
+    used = _abi.traj_row_starts(traj)[:, -1]
+    placed = (np.arange(_abi.TRAJ_CAPACITY)[None, :] < used[:, None]) & (traj["actions"] < 45)
+    assert sites["site"][placed].max() < 21 * 21
 
 
 def _compare(m, n, seed):

@@ -1,4 +1,4 @@
-"""CUDA path against the COMMITTED golden vectors (tests/golden/oracle_frozen_r01.npz), without the oracle in the loop.
+"""CUDA path against the COMMITTED golden vectors (tests/golden/oracle_frozen_r02.npz), without the oracle in the loop.
 
 The fixture holds what the oracle produced when it was frozen (make_oracle_frozen.py); test_oracle.py checks on the CPU that
 the oracle still produces it, this file checks that the GPU does. (Runs last: the file name sorts after the other suites.)
@@ -12,7 +12,7 @@ import pytest
 from eirgrid_b200 import _lib
 
 pytestmark = pytest.mark.gpu
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_frozen_r01.npz")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_frozen_r02.npz")
 EXACT = ("net_emissions", "public_opinion", "total_cost", "power_reliability", "n_generators", "n_offsets", "n_deficit_actions",
          "n_additional_actions", "flags")
 
