@@ -21,6 +21,7 @@ EXPORTS = [
     "eg_rollout_batch_device", "eg_replay_batch", "eg_replay_batch_device", "eg_update", "eg_update_stats_device",
     "eg_update_apply_stats", "eg_location_analysis", "eg_update_stats_clear_device", "eg_update_pack_best_device",
     "eg_location_analysis_year", "eg_microbench_fp64", "eg_export_best_run_csv", "eg_weights_history_append", "eg_train_batch_begin", "eg_train_batch_end", "eg_train_batch_results", "eg_update_combine_apply",
+    "eg_update_device", "eg_train_batch_inorder", "eg_rule_math",
 ]
 
 
@@ -73,10 +74,13 @@ def lib():
     L.eg_replay_batch.argtypes = [vp, C.POINTER(_abi.RunCfg), vp, u32, vp, vp, vp]
     L.eg_replay_batch_device.argtypes = [vp, C.POINTER(_abi.RunCfg), vp, u32, vp, vp, vp]
     L.eg_update.argtypes = [vp, vp, vp, u32, u32, u64, C.POINTER(_abi.UpdateStats)]
+    L.eg_update_device.argtypes = [vp, vp, vp, vp, u32, u32, u64, C.POINTER(_abi.UpdateStats)]
+    L.eg_train_batch_inorder.argtypes = [vp, vp, C.POINTER(_abi.RunCfg), u64, u64, u32, u64, C.POINTER(_abi.UpdateStats)]
     L.eg_update_stats_device.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp]
     L.eg_update_stats_clear_device.argtypes = [vp, vp]
     L.eg_update_pack_best_device.argtypes = [vp, vp, vp, u32, vp, vp, u64, vp]
     L.eg_weights_history_append.argtypes = [vp, u64, C.c_char_p]
+    L.eg_rule_math.argtypes = [C.c_int, u32, vp, vp, u32, vp]
     L.eg_microbench_fp64.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.eg_export_best_run_csv.argtypes = [vp, vp, C.POINTER(_abi.RunCfg), C.c_char_p, C.c_char_p]
     L.eg_train_batch_begin.argtypes = [vp, vp, C.POINTER(_abi.RunCfg), u64, u64, u32]
@@ -103,6 +107,15 @@ def _dev_ptr(t):
     if isinstance(t, int):
         return t
     return t.data_ptr()
+
+
+def rule_math(fn, x, y=None, device=-1):
+    """Test aid: csrc/eg_math.hpp / csrc/update_rule.hpp evaluated on the host (device < 0) or on a GPU."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.zeros_like(x) if y is None else np.ascontiguousarray(np.broadcast_to(np.asarray(y, dtype=np.float64), x.shape))
+    out = np.zeros_like(x)
+    check(lib().eg_rule_math(int(device), int(fn), _abi.ptr(x), _abi.ptr(y), x.size, _abi.ptr(out)))
+    return out
 
 
 class Weights:
@@ -283,6 +296,21 @@ class Context:
         cfg = cfg or _abi.RunCfg()
         check(self.L.eg_replay_batch_device(self.h, C.byref(cfg), _dev_ptr(d_traj_in), n, _dev_ptr(d_results),
                                             _dev_ptr(d_sites), _dev_ptr(d_yearly)))
+
+    def update_device(self, weights, n, d_results, d_traj, replay_best=False, rng_seed=0):
+        """The write-lock section of multi_simulation.rs:494-508 for a batch, in episode order, on the GPU (device buffers)."""
+        st = _abi.UpdateStats()
+        check(self.L.eg_update_device(self.h, weights.h, _dev_ptr(d_results), _dev_ptr(d_traj), int(n), int(replay_best),
+                                      int(rng_seed), C.byref(st)))
+        return st
+
+    def train_batch_inorder(self, weights, n, seed, first_episode, cfg=None, rng_seed=0):
+        """Snapshot upload, rollout of n episodes from it and the in-order update, all on the GPU."""
+        cfg = cfg or _abi.RunCfg()
+        st = _abi.UpdateStats()
+        check(self.L.eg_train_batch_inorder(self.h, weights.h, C.byref(cfg), int(seed), int(first_episode), int(n),
+                                            int(rng_seed), C.byref(st)))
+        return st
 
     def update_stats_device(self, weights, n, d_results, d_traj, d_stats, d_best_score, d_best_index):
         check(self.L.eg_update_stats_device(self.h, weights.h, _dev_ptr(d_results), _dev_ptr(d_traj), n,

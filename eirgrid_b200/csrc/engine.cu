@@ -17,6 +17,7 @@
 #include "site_tables.cuh"
 #include "stats.cuh"
 #include "suitability.cuh"
+#include "update.cuh"
 #include "weights.hpp"
 
 static_assert(sizeof(EgPolicyDevice) == 38784, "bench.py and eirgrid_b200/_abi.py quote this size");
@@ -73,6 +74,11 @@ struct eg_ctx {
   unsigned char* h_record = nullptr;
   uint32_t train_n = 0;
   bool train_pending = false;
+  // eg_update_device: scratch of the in-order update (update.cu) and its pinned host mirrors
+  EgUpdBuffers upd{};
+  EgUpdState* h_upd_state = nullptr;
+  EgUpdSlot* h_upd_slot = nullptr;
+  EgUpdImprovement* h_upd_imp = nullptr;
   EgDeviceMap dmap{};
   // scratch for the host-buffer entry points
   size_t cap = 0;
@@ -266,6 +272,12 @@ void eg_destroy(eg_ctx* c) {
     if (c->h_policy[b]) cudaFreeHost(c->h_policy[b]);
     if (c->policy_copied[b]) cudaEventDestroy(c->policy_copied[b]);
   }
+  if (c->h_upd_state) cudaFreeHost(c->h_upd_state);
+  if (c->h_upd_slot) cudaFreeHost(c->h_upd_slot);
+  if (c->h_upd_imp) cudaFreeHost(c->h_upd_imp);
+  void* upd_ptrs[] = {c->upd.state, c->upd.slots, c->upd.score, c->upd.pre, c->upd.ctl, c->upd.counts, c->upd.factors, c->upd.improvements};
+  for (void* p : upd_ptrs)
+    if (p) cudaFree(p);
   void* ptrs[] = {c->d_policy, c->d_next_episode, c->d_stats, c->d_best_score, c->d_best_index, c->d_record, c->s_out, c->s_traj, c->s_traj_in, c->s_sites, c->s_yearly};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -507,6 +519,95 @@ int eg_train_batch_results(eg_ctx* c, eg_result* out, eg_traj* traj_out) {
   if (traj_out) EG_CUDA(cudaMemcpyAsync(traj_out, c->s_traj, (size_t)c->train_n * sizeof(eg_traj), cudaMemcpyDeviceToHost, c->stream));
   EG_CUDA(cudaStreamSynchronize(c->stream));
   return EG_OK;
+}
+
+// ---- in-order update on the device (update.cu) ----------------------------------------------------------------------
+namespace {
+
+int ensure_update_buffers(eg_ctx* c, uint32_t n) {
+  EgUpdBuffers& u = c->upd;
+  if (!u.state) {
+    EG_CUDA(cudaMalloc((void**)&u.state, sizeof(EgUpdState)));
+    EG_CUDA(cudaMalloc((void**)&u.slots, (size_t)(EG_UPD_CHUNK + 1) * sizeof(EgUpdSlot)));
+    EG_CUDA(cudaMalloc((void**)&u.score, (size_t)EG_UPD_CHUNK * sizeof(double)));
+    EG_CUDA(cudaMalloc((void**)&u.pre, (size_t)EG_UPD_CHUNK * sizeof(EgUpdPre)));
+    EG_CUDA(cudaMalloc((void**)&u.ctl, (size_t)EG_UPD_CHUNK * sizeof(EgUpdCtl)));
+    EG_CUDA(cudaMalloc((void**)&u.counts, (size_t)EG_NY * EG_UPD_CHUNK * EG_UPD_ROW));
+    EG_CUDA(cudaMalloc((void**)&u.factors, (size_t)EG_NY * EG_UPD_CHUNK * EG_UPD_ENTRIES * sizeof(double)));
+    EG_CUDA(cudaMallocHost((void**)&c->h_upd_state, sizeof(EgUpdState)));
+    EG_CUDA(cudaMallocHost((void**)&c->h_upd_slot, sizeof(EgUpdSlot)));
+    EG_CUDA(cudaMallocHost((void**)&c->h_upd_imp, (size_t)EG_UPD_IMP_INLINE * sizeof(EgUpdImprovement)));
+  }
+  if (n > u.improvements_capacity) {
+    if (u.improvements) cudaFree(u.improvements);
+    u.improvements = nullptr; u.improvements_capacity = 0;
+    const uint32_t cap = std::max<uint32_t>(n, EG_UPD_IMP_INLINE);
+    EG_CUDA(cudaMalloc((void**)&u.improvements, (size_t)cap * sizeof(EgUpdImprovement)));
+    u.improvements_capacity = cap;
+  }
+  return EG_OK;
+}
+
+}  // namespace
+
+int eg_update_device(eg_ctx* c, eg_weights* w, const eg_result* d_results, const eg_traj* d_trajs, uint32_t n, uint32_t replay_best,
+                     uint64_t rng_seed, eg_update_stats* stats_out) {
+  if (!c || !w || (n && (!d_results || !d_trajs))) return eg_fail(EG_ERR_INVALID, "eg_update_device: NULL argument");
+  EG_CUDA(cudaSetDevice(c->device));
+  int rc = ensure_update_buffers(c, n);
+  if (rc) return rc;
+  // the pinned mirrors are free again: every call ends with a stream synchronisation
+  if (!eg_weights_fill_update_state(*w, c->h_upd_state, c->h_upd_slot))
+    return eg_fail(EG_ERR_OVERFLOW, "eg_update_device: the best-strategy lists exceed EG_UPD_CAT_CAPACITY entries");
+  const uint32_t iteration0 = w->iteration_count;
+  EG_CUDA(cudaMemcpyAsync(c->upd.state, c->h_upd_state, sizeof(EgUpdState), cudaMemcpyHostToDevice, c->stream));
+  EG_CUDA(cudaMemcpyAsync(c->upd.slots, c->h_upd_slot, sizeof(EgUpdSlot), cudaMemcpyHostToDevice, c->stream));
+  for (uint32_t base = 0; base < n; base += EG_UPD_CHUNK) {
+    const uint32_t cnt = std::min<uint32_t>(EG_UPD_CHUNK, n - base);
+    int launches = 0;
+    EG_CUDA(eg_launch_update_pass(c->upd, d_results + base, d_trajs + base, cnt, base, replay_best, rng_seed, c->stream, &launches));
+    c->launches += (uint64_t)launches;
+  }
+  EG_CUDA(cudaMemcpyAsync(c->h_upd_state, c->upd.state, sizeof(EgUpdState), cudaMemcpyDeviceToHost, c->stream));
+  EG_CUDA(cudaMemcpyAsync(c->h_upd_slot, c->upd.slots, sizeof(EgUpdSlot), cudaMemcpyDeviceToHost, c->stream));
+  EG_CUDA(cudaMemcpyAsync(c->h_upd_imp, c->upd.improvements, (size_t)EG_UPD_IMP_INLINE * sizeof(EgUpdImprovement), cudaMemcpyDeviceToHost, c->stream));
+  EG_CUDA(cudaStreamSynchronize(c->stream));
+  const EgUpdState& st = *c->h_upd_state;
+  std::vector<EgUpdImprovement> more;
+  const EgUpdImprovement* imps = c->h_upd_imp;
+  if (st.n_improvements > EG_UPD_IMP_INLINE) {  // rare: more improving episodes than the inline window
+    more.resize(st.n_improvements);
+    EG_CUDA(cudaMemcpy(more.data(), c->upd.improvements, (size_t)st.n_improvements * sizeof(EgUpdImprovement), cudaMemcpyDeviceToHost));
+    imps = more.data();
+  }
+  eg_weights_apply_update_state(*w, st, *c->h_upd_slot, imps, st.n_improvements, iteration0);
+  if (stats_out) {
+    eg_update_stats so;
+    std::memset(&so, 0, sizeof(so));
+    so.n_episodes = n;
+    so.n_improvements = st.n_improvements;
+    so.n_contrast_applied = st.n_applied;
+    so.iterations_without_improvement = st.iwi;
+    so.best_score = st.has_best ? st.best_score : 0.0;
+    so.batch_best_score = st.batch_best_index >= 0 ? st.batch_best_score : 0.0;
+    so.batch_best_episode = st.batch_best_index;
+    so.n_flagged = st.n_flagged;
+    *stats_out = so;
+  }
+  return EG_OK;
+}
+
+int eg_train_batch_inorder(eg_ctx* c, eg_weights* w, const eg_run_cfg* cfg, uint64_t seed, uint64_t first_episode, uint32_t n,
+                           uint64_t rng_seed, eg_update_stats* stats_out) {
+  int rc = check_cfg(c, cfg);
+  if (rc) return rc;
+  if (!w) return eg_fail(EG_ERR_INVALID, "eg_train_batch_inorder: weights are NULL");
+  if (c->train_pending) return eg_fail(EG_ERR_STATE, "eg_train_batch_inorder: a batch is already in flight on this context");
+  if ((rc = eg_weights_upload(c, w))) return rc;
+  if ((rc = ensure_scratch(c, n, false, false, false))) return rc;
+  if ((rc = eg_rollout_batch_device(c, cfg, seed, first_episode, n, c->s_out, c->s_traj, nullptr, nullptr))) return rc;
+  c->train_n = n;
+  return eg_update_device(c, w, c->s_out, c->s_traj, n, cfg->replay_best, rng_seed, stats_out);
 }
 
 // ---- CSV export of the best run (utils/csv_export.rs) ------------------------------------------------------------

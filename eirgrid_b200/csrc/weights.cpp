@@ -9,6 +9,8 @@
 #include "weights.hpp"
 #include "json_min.hpp"
 #include "common.hpp"
+#include "update_rule.hpp"
+#include "update.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -250,42 +252,29 @@ struct UpdateRng {  // Philox4x32-10 stream for the randomisation branch (learni
 
 void contrast(eg_weights& W, const Recorded& rec, const double metrics[4], UpdateRng* rng, uint32_t* applied) {  // learning.rs:131-283
   if (!W.has_best) return;
-  const double best_score = eg_score_default(W.best_metrics);
-  const double current_score = eg_score_default(metrics);
-  const double deterioration = best_score > 0.0 ? (best_score - current_score) / best_score : 0.0;
-  const double iterations = (double)W.iwi;
-  const double threshold = 0.1 * std::max(std::exp(-iterations / 500.0), 0.00001 / 0.1);
-  const bool force = W.iwi > 800;
-  if (!(deterioration > threshold || force)) return;
+  // thresholds and factors: update_rule.hpp, the source the device form (update.cu) shares
+  const egrule::Contrast c = egrule::contrast(eg_score_default(W.best_metrics), eg_score_default(metrics), W.iwi, W.learning_rate);
+  if (!c.applied) return;
   if (applied) (*applied)++;
-  const double stagnation = 1.0 + (0.2 * std::pow((double)W.iwi / 10.0, 1.8));
-  const double combined = std::pow(deterioration, 0.3) * stagnation;
-  const double alr = W.learning_rate * (1.0 + 0.1 * (double)W.iwi);
-  const double penalty = 1.0 / (1.0 + alr * 1.5 * combined);
-  const double boost = 1.0 + (alr * 2.0 * stagnation);
   for (int y = 0; y < EG_NY; y++) {
     std::vector<uint8_t> cur = rec.run[y];
     cur.insert(cur.end(), rec.deficit[y].begin(), rec.deficit[y].end());
     std::vector<uint8_t> best = W.best_actions[y];
     best.insert(best.end(), W.best_deficit_actions[y].begin(), W.best_deficit_actions[y].end());
     double* row = W.w[y];
-    for (uint8_t a : best) row[a] = std::min(row[a] * boost, kMaxWeight);
+    for (uint8_t a : best) row[a] = std::min(row[a] * c.boost, kMaxWeight);
     for (size_t i = 0; i < cur.size(); i++) {
       const uint8_t a = cur[i];
       if (!contains(best, a)) {
-        row[a] = std::fmax(row[a] * penalty, kMinWeight);  // NaN penalty collapses to MIN_WEIGHT like f64::max (quirk Q9)
+        row[a] = std::fmax(row[a] * c.penalty, kMinWeight);  // NaN penalty collapses to MIN_WEIGHT like f64::max (quirk Q9)
       } else if (i < best.size() && a != best[i]) {
-        const double mild = 1.0 / (1.0 + alr * combined * 0.5);
-        row[a] = std::fmax(row[a] * mild, kMinWeight);
+        row[a] = std::fmax(row[a] * c.mild, kMinWeight);
       }
     }
   }
-  if (W.iwi > 1200 && rng)
+  if (c.randomise && rng)
     for (int y = 0; y < EG_NY; y++)
-      for (int k = 0; k < EG_N_ACTIONS; k++) {
-        const double f = 1.0 + 0.25 * (rng->f64() * 2.0 - 1.0);
-        W.w[y][k] = std::min(std::max(W.w[y][k] * f, kMinWeight), kMaxWeight);
-      }
+      for (int k = 0; k < EG_N_ACTIONS; k++) W.w[y][k] = egrule::randomise(W.w[y][k], rng->f64());
 }
 
 std::string now_string() {
@@ -319,49 +308,29 @@ bool best_strategy(eg_weights& W, const Recorded& rec, const double metrics[4]) 
 
 void deficit_contrast(eg_weights& W, const Recorded& rec, UpdateRng* rng) {  // learning.rs:285-373
   if (!W.has_best) return;
-  const double deterioration = (double)W.iwi / 10.0;
-  const double threshold = 0.05 * std::max(std::exp(-(double)W.iwi / 400.0), 0.00001 / 0.05);
-  const bool force = W.iwi > 800;
-  if (!(deterioration > threshold || force)) return;
-  const double stagnation = 1.0 + (0.2 * std::pow((double)W.iwi / 10.0, 1.8));
-  const double combined = std::pow(deterioration, 0.3) * stagnation;
-  const double alr = W.learning_rate * (1.0 + 0.1 * (double)W.iwi);
-  const double penalty = 1.0 / (1.0 + alr * 1.5 * combined);
-  const double boost = 1.0 + (alr * 2.0 * stagnation * 1.5);
+  const egrule::Contrast c = egrule::deficit_contrast(W.iwi, W.learning_rate);
+  if (!c.applied) return;
   for (int y = 0; y < EG_NY; y++) {
     const std::vector<uint8_t>& best = W.best_deficit_actions[y];
     double* row = W.dw[y];
     for (uint8_t a : best) {
       int k = deficit_key_of_action(a);
-      if (k >= 0) row[k] = std::min(row[k] * boost, kMaxWeight);
+      if (k >= 0) row[k] = std::min(row[k] * c.boost, kMaxWeight);
     }
     for (uint8_t a : rec.deficit[y])
       if (!contains(best, a)) {
         int k = deficit_key_of_action(a);
-        if (k >= 0) row[k] = std::fmax(row[k] * penalty, kMinWeight);
+        if (k >= 0) row[k] = std::fmax(row[k] * c.penalty, kMinWeight);
       }
   }
-  if (W.iwi > 1200 && rng)
+  if (c.randomise && rng)
     for (int y = 0; y < EG_NY; y++)
-      for (int k = 0; k < EG_N_DEFICIT_KEYS; k++) {
-        const double f = 1.0 + 0.25 * (rng->f64() * 2.0 - 1.0);
-        W.dw[y][k] = std::min(std::max(W.dw[y][k] * f, kMinWeight), kMaxWeight);
-      }
+      for (int k = 0; k < EG_N_DEFICIT_KEYS; k++) W.dw[y][k] = egrule::randomise(W.dw[y][k], rng->f64());
 }
 
 }  // namespace
 
-double eg_score(const double m[4], bool cost_only) {  // ai/metrics/scoring.rs:5-45
-  const double normalized_cost = std::max(m[2] / kMaxCost, 1.0);
-  const double log_cost = std::log(normalized_cost);
-  const double max_expected_log_cost = std::log(kMaxCost * 100.0 / kMaxCost);
-  if (cost_only) return 2.0 - std::min(log_cost / max_expected_log_cost, 1.0);
-  if (m[0] > 0.0) return 1.0 - std::min(m[0] / kMaxEmissions, 1.0);
-  const double cost_score = 1.0 - std::min(log_cost / max_expected_log_cost, 1.0);
-  const double cost_weight = normalized_cost > 8.0 ? 0.8 : 0.5;
-  const double opinion_weight = 1.0 - cost_weight;
-  return 1.0 + (cost_score * cost_weight + m[1] * opinion_weight);
-}
+double eg_score(const double m[4], bool cost_only) { return egrule::score(m, cost_only); }  // ai/metrics/scoring.rs:5-45
 double eg_score_default(const double m[4]) { return eg_score(m, false); }
 
 eg_weights::eg_weights() {  // ActionWeights::new, weights/core.rs:25-250
@@ -450,6 +419,60 @@ bool eg_weights_fill_policy(const eg_weights& W, EgPolicyDevice* out) {
     ob += nb; obd += nbd;
   }
   return fits;
+}
+
+bool eg_weights_fill_update_state(const eg_weights& W, EgUpdState* st, EgUpdSlot* slot0) {
+  std::memset(st, 0, sizeof(*st));
+  std::memset(slot0, 0, sizeof(*slot0));
+  std::memcpy(st->w, W.w, sizeof(st->w));
+  std::memcpy(st->dw, W.dw, sizeof(st->dw));
+  if (W.best_weights.size() == (size_t)EG_NY * EG_N_ACTIONS) std::memcpy(st->best_w, W.best_weights.data(), sizeof(st->best_w));
+  std::memcpy(st->best_metrics, W.best_metrics, sizeof(st->best_metrics));
+  st->best_score = W.has_best ? eg_score_default(W.best_metrics) : 0.0;
+  st->learning_rate = W.learning_rate;
+  st->batch_best_index = -1;
+  st->has_best = W.has_best ? 1u : 0u;
+  st->iwi = W.iwi;
+  st->iteration_count = W.iteration_count;
+  st->pass_last_improver = -1;
+  if (!W.has_best) return true;
+  size_t off = 0;
+  for (int y = 0; y < EG_NY; y++) {
+    const std::vector<uint8_t>& run = W.best_actions[y];
+    const std::vector<uint8_t>& def = W.best_deficit_actions[y];
+    if (off + run.size() + def.size() > EG_UPD_CAT_CAPACITY) return false;
+    slot0->len_run[y] = (uint16_t)run.size();
+    slot0->len_def[y] = (uint16_t)def.size();
+    slot0->off[y] = (uint32_t)off;
+    unsigned long long mall = 0ull, mdef = 0ull;
+    for (uint8_t a : run) { slot0->cat[off++] = a; mall |= 1ull << a; }
+    for (uint8_t a : def) { slot0->cat[off++] = a; mdef |= 1ull << a; }
+    slot0->mask_all[y] = mall | mdef;
+    slot0->mask_def[y] = mdef;
+  }
+  return true;
+}
+
+void eg_weights_apply_update_state(eg_weights& W, const EgUpdState& st, const EgUpdSlot& slot0, const EgUpdImprovement* improvements,
+                                   uint32_t n_improvements, uint32_t iteration0) {
+  std::memcpy(W.w, st.w, sizeof(W.w));
+  std::memcpy(W.dw, st.dw, sizeof(W.dw));
+  W.iwi = st.iwi;
+  W.iteration_count = st.iteration_count;
+  if (!n_improvements) return;
+  const std::string now = now_string();
+  for (uint32_t i = 0; i < n_improvements; i++) {
+    const EgUpdImprovement& r = improvements[i];
+    W.history.push_back({iteration0 + (uint32_t)r.episode + 1u, r.score, r.metrics[0], r.metrics[2], r.metrics[1], r.metrics[3], now});
+  }
+  W.has_best = true;
+  std::memcpy(W.best_metrics, st.best_metrics, sizeof(W.best_metrics));
+  W.best_weights.assign(&st.best_w[0][0], &st.best_w[0][0] + EG_NY * EG_N_ACTIONS);
+  for (int y = 0; y < EG_NY; y++) {
+    const uint8_t* p = slot0.cat + slot0.off[y];
+    W.best_actions[y].assign(p, p + slot0.len_run[y]);
+    W.best_deficit_actions[y].assign(p + slot0.len_run[y], p + slot0.len_run[y] + slot0.len_def[y]);
+  }
 }
 
 EgContrastConsts eg_contrast_consts(const eg_weights& W) {

@@ -51,6 +51,16 @@ struct EgContrastConsts {
 };
 EgContrastConsts eg_contrast_consts(const eg_weights& w);
 
+// host <-> device marshalling of the in-order device update (update.cu): fill = the fields of `w` the rule touches plus its
+// best strategy as slot 0 (false: the lists exceed EG_UPD_CAT_CAPACITY); apply = the state after the passes back into `w`,
+// with one improvement_history entry per improving episode (iteration0 = w.iteration_count before the call)
+struct EgUpdState;
+struct EgUpdSlot;
+struct EgUpdImprovement;
+bool eg_weights_fill_update_state(const eg_weights& w, EgUpdState* st, EgUpdSlot* slot0);
+void eg_weights_apply_update_state(eg_weights& w, const EgUpdState& st, const EgUpdSlot& slot0, const EgUpdImprovement* improvements,
+                                   uint32_t n_improvements, uint32_t iteration0);
+
 #define EG_STATS_FIXED_SCALE 16777216.0  // 2^24: fixed-point scale of the summed log-factors
 #define EG_STATS_YEAR_STRIDE (3 * EG_N_ACTIONS + EG_N_DEFICIT_KEYS)
 #define EG_STATS_HEADER 8

@@ -271,6 +271,20 @@ int eg_replay_batch_device(eg_ctx* ctx, const eg_run_cfg* cfg, const eg_traj* d_
 int eg_update(eg_weights* w, const eg_result* results, const eg_traj* trajs, uint32_t n,
               uint32_t replay_best, uint64_t rng_seed, eg_update_stats* stats_out);
 
+/* The same rule with DEVICE buffers, applied on the GPU in episode-index order (update.cu): `w` ends with the same table,
+ * best strategy, counters and improvement history as after eg_update on the same records, bit for bit — both forms take
+ * their thresholds and factors from one source (csrc/update_rule.hpp) — at ~20-40 ns per episode instead of 4-11 us. The
+ * rule stays sequential in the episodes; the device form finds the running best with a scan over the scores, derives each
+ * episode's factors and multiplication counts in parallel and walks the table once, one thread per table entry.
+ * Synchronous: returns after `w` has been updated. */
+int eg_update_device(eg_ctx* ctx, eg_weights* w, const eg_result* d_results, const eg_traj* d_trajs, uint32_t n,
+                     uint32_t replay_best, uint64_t rng_seed, eg_update_stats* stats_out);
+/* One batch of the reference's loop on one GPU (the par_iter closure for n episodes that share one snapshot,
+ * multi_simulation.rs:457-508): snapshot H2D, rollout of episodes first_episode..+n, in-order update on the device, state
+ * D2H. Episode results stay on the device: eg_train_batch_results copies them out. */
+int eg_train_batch_inorder(eg_ctx* ctx, eg_weights* w, const eg_run_cfg* cfg, uint64_t seed, uint64_t first_episode, uint32_t n,
+                           uint64_t rng_seed, eg_update_stats* stats_out);
+
 /* Batch-synchronous update for sharded episodes: statistics are accumulated on the
  * device by eg_update_stats_device into a table of EG_STATS_WORDS int64 words that the caller sums
  * across ranks (NCCL allreduce SUM), then eg_update_apply_stats applies the identical update on every
@@ -338,6 +352,12 @@ int eg_location_analysis_year(eg_ctx* ctx, int use_loaded_map, uint32_t year_ind
 /* ---- measurement aid (not on the path): double-precision multiply+add issue rate of `device` in TFLOP/s WITHOUT fused
  * multiply-add — the arithmetic ceiling of kernels compiled with --fmad=false like the episode kernel. */
 int eg_microbench_fp64(int device, double* tflops_out);
+/* ---- test aid (not on the path): the update rule's shared arithmetic (csrc/eg_math.hpp, csrc/update_rule.hpp), evaluated on
+ * the host (device < 0) or on GPU `device`, so that tests can hold the host and the device form to the same bits and to
+ * high-precision references. fn: 0 exp(x), 1 ln(x), 2 pow(x, y), 3 score_metrics(net x, opinion 0.5, cost y), 4/5/6 penalty /
+ * boost / mild penalty of apply_contrast_learning for (best score 2.0, current score x, stagnation counter y, lr 0.2), 7/8
+ * penalty / boost of apply_deficit_contrast_learning for counter y, 9 one draw of the update's Philox stream. */
+int eg_rule_math(int device, uint32_t fn, const double* x, const double* y, uint32_t n, double* out);
 
 #ifdef __cplusplus
 }
