@@ -337,6 +337,13 @@ class Context:
         check(self.L.eg_location_analysis_year(self.h, int(use_loaded_map), int(year_index), half_steps, step, _abi.ptr(out), first_point, n))
         return out
 
+    def train_batch_results(self, n, want_traj=True):
+        """Results (and records) of the last eg_train_batch_* call, copied to the host."""
+        res = np.zeros(n, _abi.RESULT_DTYPE)
+        traj = np.zeros(n, _abi.TRAJ_DTYPE) if want_traj else None
+        check(self.L.eg_train_batch_results(self.h, _abi.ptr(res), _abi.ptr(traj)))
+        return res, traj
+
     def sync(self):
         check(self.L.eg_sync(self.h))
 

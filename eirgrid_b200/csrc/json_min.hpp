@@ -2,6 +2,7 @@
 // settlements.json, coastline_points.json (inputs of the reference's loaders) and the weights
 // checkpoints (SerializableWeights, ai/learning/serialization.rs:37-51). Host-only.
 #pragma once
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <cstdio>
@@ -172,16 +173,44 @@ inline bool read_file(const char* path, std::string* out) {
   return got == (size_t)(n > 0 ? n : 0);
 }
 
-// shortest decimal text that parses back to exactly `v` (what serde_json's ryu output guarantees)
+// A double as serde_json prints it (ryu's `format64`): the shortest digit string that parses back to exactly `v`, laid out as
+//   digits followed by ".0" for integral values below 1e16      1234e7  -> 12340000000.0
+//   a decimal point inside the digits                           1234e-2 -> 12.34
+//   leading zeros for values down to 1e-5                       1234e-8 -> 0.00001234
+//   scientific otherwise, no '+' and no padding in the exponent 1e-6, 1.234e-7, 1.2e16
+// NaN and the infinities become null like serde_json's.
 inline std::string fmt_double(double v) {
+  if (v != v || v == HUGE_VAL || v == -HUGE_VAL) return "null";
+  if (v == 0.0) return std::signbit(v) ? "-0.0" : "0.0";
   char buf[40];
-  for (int prec = 1; prec <= 17; prec++) {
-    std::snprintf(buf, sizeof(buf), "%.*g", prec, v);
+  for (int prec = 0; prec <= 16; prec++) {  // %.{prec}e has prec + 1 significant digits
+    std::snprintf(buf, sizeof(buf), "%.*e", prec, v);
     if (std::strtod(buf, nullptr) == v) break;
   }
-  std::string s(buf);
-  if (s.find_first_of(".eEni") == std::string::npos) s += ".0";  // serde_json prints floats with a fraction
-  return s;
+  // buf = [-]d[.ddd]e[+-]xx
+  std::string text(buf), digits, out;
+  const bool negative = text[0] == '-';
+  const size_t epos = text.find('e');
+  for (size_t i = negative ? 1 : 0; i < epos; i++)
+    if (text[i] != '.') digits += text[i];
+  while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+  const int exp10 = std::atoi(text.c_str() + epos + 1);
+  const int length = (int)digits.size();
+  const int kk = exp10 + 1;           // position of the decimal point relative to the first digit
+  const int k = kk - length;          // value = digits * 10^k
+  if (negative) out += '-';
+  if (k >= 0 && kk <= 16) {
+    out += digits + std::string((size_t)k, '0') + ".0";
+  } else if (kk > 0 && kk <= 16) {
+    out += digits.substr(0, (size_t)kk) + "." + digits.substr((size_t)kk);
+  } else if (kk > -5 && kk <= 0) {
+    out += "0." + std::string((size_t)(-kk), '0') + digits;
+  } else {
+    out += digits.substr(0, 1);
+    if (length > 1) out += "." + digits.substr(1);
+    out += "e" + std::to_string(kk - 1);
+  }
+  return out;
 }
 
 }  // namespace egjson

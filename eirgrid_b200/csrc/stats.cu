@@ -17,7 +17,8 @@ namespace {
 
 constexpr double kMaxAcceptableCost = 50000000000.0, kMaxAcceptableEmissions = 1000000.0;
 
-__device__ __forceinline__ double default_score(const eg_result& r, double ln100) {  // scoring.rs:18-44
+__device__ __forceinline__ double default_score(const eg_result& r, double ln100, bool cost_only = false) {  // scoring.rs:5-44
+  if (cost_only) return 2.0 - fmin(log(fmax(r.total_cost / kMaxAcceptableCost, 1.0)) / ln100, 1.0);
   if (r.net_emissions > 0.0) return 1.0 - fmin(r.net_emissions / kMaxAcceptableEmissions, 1.0);
   const double normalized_cost = fmax(r.total_cost / kMaxAcceptableCost, 1.0);
   const double cost_score = 1.0 - fmin(log(normalized_cost) / ln100, 1.0);
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(256) eg_stats_kernel(const EgStatsParams p) {
     const eg_result* rp = p.results + ep;
     eg_result r;  // every lane reads the same 40 bytes (one broadcast transaction)
     r.net_emissions = rp->net_emissions; r.public_opinion = rp->public_opinion; r.total_cost = rp->total_cost;
-    const double score = default_score(r, p.ln100);
+    const double score = default_score(r, p.ln100, p.consts.cost_only != 0);
     warp_best = fmax(warp_best, score);
     bool pass = false;
     long long log_pen = 0, log_mild = 0;
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(256) eg_stats_kernel(const EgStatsParams p) {
 __global__ void __launch_bounds__(256) eg_stats_argbest_kernel(const EgStatsParams p) {
   const uint32_t ep = blockIdx.x * blockDim.x + threadIdx.x;
   if (ep >= p.n) return;
-  const double score = default_score(p.results[ep], p.ln100);
+  const double score = default_score(p.results[ep], p.ln100, p.consts.cost_only != 0);
   if (score == *p.best_score) atomicMin(p.best_index, (unsigned long long)ep);
 }
 

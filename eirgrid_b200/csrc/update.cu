@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) upd_score_kernel(const eg_result* results
   if (e >= n) return;
   const eg_result* r = results + e;
   const double m[4] = {r->net_emissions, r->public_opinion, r->total_cost, r->power_reliability};
-  score[e] = egrule::score(m, false);
+  score[e] = egrule::score(m, st->cost_only != 0);
   if (r->flags) atomicAdd(&st->n_flagged, 1u);
 }
 
@@ -482,6 +482,33 @@ __device__ __forceinline__ void walk_tile(const EgUpdCtl* ctl, const unsigned ch
         boost[u] = DEFICIT ? ctl[j0 + u].d_boost : ctl[j0 + u].boost;
         pen[u] = DEFICIT ? ctl[j0 + u].d_penalty : ctl[j0 + u].penalty;
         mild[u] = DEFICIT ? 1.0 : ctl[j0 + u].mild;
+      }
+      if (!gi) {
+        // No best-strategy change inside the group (all but a handful of groups): every step is computed and then kept or
+        // dropped by a select, so the only thing a step waits for is the entry's value. Repeated multiplications beyond
+        // the first (an action the strategy holds twice, an action sampled twice) branch out only while they still change
+        // the value: MAX_WEIGHT / MIN_WEIGHT are fixed points of the boost / penalty step.
+        const bool in_best = occ != 0;
+#pragma unroll
+        for (int u = 0; u < kGroup; u++) {
+          const bool app = (ga >> u) & 1u;
+          const double wb = egrule::min_std(w * boost[u], egrule::kMaxWeight);
+          w = (app && in_best) ? wb : w;
+          if (app && occ > 1 && !(w == egrule::kMaxWeight && boost[u] >= 1.0)) w = walk_boost(w, boost[u], occ - 1);
+          int mm = m[u];
+          if (app && mm == 255) mm = walk_recount<DEFICIT>(trajs + first + j0 + u, y, key, rp, cur);  // more than the byte holds
+          const double p = (!DEFICIT && in_best) ? mild[u] : pen[u];
+          const double t = w * p;
+          const double wp = (t >= egrule::kMinWeight) ? t : egrule::kMinWeight;  // f64::max(t, MIN_WEIGHT), NaN -> MIN_WEIGHT (quirk Q9)
+          w = (app && mm != 0) ? wp : w;
+          if (app && mm > 1 && !(w == egrule::kMinWeight && !(p > 1.0))) w = walk_penalty(w, p, mm - 1);
+          if ((gr >> u) & 1u) {  // std::min(std::max(t, MIN_WEIGHT), MAX_WEIGHT) with both comparisons on t itself
+            const double tr = w * f[u];
+            const bool below = tr < egrule::kMinWeight, above = egrule::kMaxWeight < tr;
+            w = below ? egrule::kMinWeight : (above ? egrule::kMaxWeight : tr);
+          }
+        }
+        continue;
       }
 #pragma unroll
       for (int u = 0; u < kGroup; u++) {

@@ -26,7 +26,7 @@ struct EgUpdState {
   uint32_t pass_has_best, pass_iwi, pass_iteration_count;
   int32_t pass_last_improver;           // last improving episode of the pass (index inside the pass), -1 if none
   uint32_t pass_any_random;             // some episode of the pass takes the randomisation branch
-  uint32_t pad;
+  uint32_t cost_only;                   // ActionWeights.optimization_mode == "cost_only" (score_metrics' mode, quirk Q12)
 };
 
 // One best strategy as the rule compares against it: per year best_actions ++ best_deficit_actions.

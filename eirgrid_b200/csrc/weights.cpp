@@ -36,6 +36,10 @@ int deficit_key_of_action(int code) {
   return -1;
 }
 
+// score_metrics(metrics, self.optimization_mode) as the weights object itself scores (learning.rs:134-135, strategy.rs:20,58):
+// the mode only ever comes from a checkpoint file, the reference's driver never sets it (quirk Q12)
+double score_w(const eg_weights& W, const double m[4]) { return eg_score(m, W.optimization_mode == "cost_only"); }
+
 bool contains(const std::vector<uint8_t>& v, uint8_t a) { return std::find(v.begin(), v.end(), a) != v.end(); }
 
 // ---- JSON <-> action code ---------------------------------------------------------------------------------
@@ -253,7 +257,7 @@ struct UpdateRng {  // Philox4x32-10 stream for the randomisation branch (learni
 void contrast(eg_weights& W, const Recorded& rec, const double metrics[4], UpdateRng* rng, uint32_t* applied) {  // learning.rs:131-283
   if (!W.has_best) return;
   // thresholds and factors: update_rule.hpp, the source the device form (update.cu) shares
-  const egrule::Contrast c = egrule::contrast(eg_score_default(W.best_metrics), eg_score_default(metrics), W.iwi, W.learning_rate);
+  const egrule::Contrast c = egrule::contrast(score_w(W, W.best_metrics), score_w(W, metrics), W.iwi, W.learning_rate);
   if (!c.applied) return;
   if (applied) (*applied)++;
   for (int y = 0; y < EG_NY; y++) {
@@ -287,9 +291,9 @@ std::string now_string() {
 }
 
 bool best_strategy(eg_weights& W, const Recorded& rec, const double metrics[4]) {  // strategy.rs:19-258
-  const double current_score = eg_score_default(metrics);
+  const double current_score = score_w(W, metrics);
   W.iteration_count += 1;
-  const bool should_update = !W.has_best || current_score > eg_score_default(W.best_metrics);
+  const bool should_update = !W.has_best || current_score > score_w(W, W.best_metrics);
   if (should_update) {
     W.history.push_back({W.iteration_count, current_score, metrics[0], metrics[2], metrics[1], metrics[3], now_string()});
     std::memcpy(W.best_metrics, metrics, sizeof(W.best_metrics));
@@ -428,7 +432,8 @@ bool eg_weights_fill_update_state(const eg_weights& W, EgUpdState* st, EgUpdSlot
   std::memcpy(st->dw, W.dw, sizeof(st->dw));
   if (W.best_weights.size() == (size_t)EG_NY * EG_N_ACTIONS) std::memcpy(st->best_w, W.best_weights.data(), sizeof(st->best_w));
   std::memcpy(st->best_metrics, W.best_metrics, sizeof(st->best_metrics));
-  st->best_score = W.has_best ? eg_score_default(W.best_metrics) : 0.0;
+  st->best_score = W.has_best ? score_w(W, W.best_metrics) : 0.0;
+  st->cost_only = W.optimization_mode == "cost_only" ? 1u : 0u;
   st->learning_rate = W.learning_rate;
   st->batch_best_index = -1;
   st->has_best = W.has_best ? 1u : 0u;
@@ -479,7 +484,8 @@ EgContrastConsts eg_contrast_consts(const eg_weights& W) {
   EgContrastConsts c;
   c.has_best = W.has_best ? 1 : 0;
   c.force = W.iwi > 800 ? 1 : 0;
-  c.best_score = W.has_best ? eg_score_default(W.best_metrics) : 0.0;
+  c.best_score = W.has_best ? score_w(W, W.best_metrics) : 0.0;
+  c.cost_only = W.optimization_mode == "cost_only" ? 1u : 0u;
   c.threshold = 0.1 * std::max(std::exp(-(double)W.iwi / 500.0), 0.00001 / 0.1);
   c.stagnation = 1.0 + (0.2 * std::pow((double)W.iwi / 10.0, 1.8));
   c.alr = W.learning_rate * (1.0 + 0.1 * (double)W.iwi);
@@ -703,12 +709,12 @@ int eg_update(eg_weights* w, const eg_result* results, const eg_traj* trajs, uin
     contrast(*w, rec, m, &rng, &st.n_contrast_applied);    // apply_contrast_learning
     if (best_strategy(*w, rec, m)) st.n_improvements++;    // update_best_strategy
     deficit_contrast(*w, rec, &rng);                       // apply_deficit_contrast_learning
-    const double sc = eg_score_default(m);
+    const double sc = score_w(*w, m);
     if (st.batch_best_episode < 0 || sc > st.batch_best_score) { st.batch_best_score = sc; st.batch_best_episode = i; }
     if (results[i].flags) st.n_flagged++;
   }
   st.iterations_without_improvement = w->iwi;
-  st.best_score = w->has_best ? eg_score_default(w->best_metrics) : 0.0;
+  st.best_score = w->has_best ? score_w(*w, w->best_metrics) : 0.0;
   if (stats_out) *stats_out = st;
   return EG_OK;
 }
@@ -756,9 +762,9 @@ int eg_update_apply_stats(eg_weights* w, const int64_t* stats, uint64_t n_total,
   bool improved = false;
   if (best_result && best_traj && n_total > 0) {
     const double m[4] = {best_result->net_emissions, best_result->public_opinion, best_result->total_cost, best_result->power_reliability};
-    const double sc = eg_score_default(m);
+    const double sc = score_w(*w, m);
     st.batch_best_score = sc;
-    improved = !w->has_best || sc > eg_score_default(w->best_metrics);
+    improved = !w->has_best || sc > score_w(*w, w->best_metrics);
     if (improved) {
       Recorded rec;
       rec.from_traj(*best_traj, false);
@@ -810,7 +816,7 @@ int eg_update_apply_stats(eg_weights* w, const int64_t* stats, uint64_t n_total,
     }
   }
   st.iterations_without_improvement = w->iwi;
-  st.best_score = w->has_best ? eg_score_default(w->best_metrics) : 0.0;
+  st.best_score = w->has_best ? score_w(*w, w->best_metrics) : 0.0;
   if (stats_out) *stats_out = st;
   return EG_OK;
 }

@@ -43,6 +43,8 @@ bool eg_weights_fill_policy(const eg_weights& w, EgPolicyDevice* out);
 struct EgContrastConsts {
   uint32_t has_best;
   uint32_t force;            // iwi > 800
+  uint32_t cost_only;        // the weights' own optimization_mode is "cost_only" (only ever set by a checkpoint file, quirk Q12)
+  uint32_t pad;
   double best_score;
   double threshold;          // 0.1 * max(exp(-iwi/500), 1e-4)
   double stagnation;         // 1 + 0.2 * (iwi/10)^1.8

@@ -64,12 +64,16 @@ def find_start_iteration(checkpoint_dir):
         return 0
 
 
-def load_initial_weights(checkpoint_dir, continue_from_checkpoint=True, log=print):
-    """latest_weights.json overlaid with every thread_*_weights.json (multi_simulation.rs:237-290)."""
+_LOOK = object()
+
+
+def load_initial_weights(checkpoint_dir, continue_from_checkpoint=True, log=print, resume_dir=_LOOK):
+    """latest_weights.json overlaid with every thread_*_weights.json (multi_simulation.rs:237-290).
+    resume_dir: the directory to resume from when the caller has already chosen it (None = none found)."""
     if not continue_from_checkpoint:
         log("Starting fresh simulation (--no-continue specified)")
         return _lib.Weights()
-    latest = find_resume_dir(checkpoint_dir)
+    latest = find_resume_dir(checkpoint_dir) if resume_dir is _LOOK else resume_dir
     if latest is None:
         log("No checkpoint directories found, starting fresh")
         return _lib.Weights()
@@ -115,8 +119,10 @@ def run_multi_simulation(asset_dir, num_iterations, parallel=True, continue_from
     """Run `num_iterations` episodes (total across all ranks) and learn the action weights.
 
     update_mode "batch": device-side statistics + one allreduce per batch.
-    update_mode "sequential": every episode's record is copied to the host and the reference's per-episode update
-    is applied in episode order (exact reference arithmetic with `batch_size` episodes of staleness; single GPU).
+    update_mode "sequential": the reference's per-episode update in episode order, applied on the GPU (eg_update_device:
+    exact reference rule with `batch_size` episodes sampled per snapshot; replicated on every rank).
+    update_mode "sequential-host": the same rule through eg_update on the host (every record copied back; the slow twin).
+    The replay phase (last 10 % of the iterations) always runs the per-episode rule.
     Returns a summary dict; checkpoints are written like the reference's.
     """
     import torch
@@ -126,24 +132,35 @@ def run_multi_simulation(asset_dir, num_iterations, parallel=True, continue_from
     distributed = dist.is_available() and dist.is_initialized()
     rank = dist.get_rank() if distributed else 0
     world = dist.get_world_size() if distributed else 1
-    if update_mode not in ("batch", "sequential"):
-        raise ValueError("update_mode must be 'batch' or 'sequential'")
-    if update_mode == "sequential" and world > 1:
-        raise ValueError("update_mode='sequential' is single-GPU")
+    if update_mode not in ("batch", "sequential", "sequential-host"):
+        raise ValueError("update_mode must be 'batch', 'sequential' or 'sequential-host'")
     os.makedirs(checkpoint_dir, exist_ok=True)
-    weights = load_initial_weights(checkpoint_dir, continue_from_checkpoint, log if rank == 0 else (lambda *a: None))
-    start_iteration = find_start_iteration(checkpoint_dir) if continue_from_checkpoint else 0
-    run_dir = os.path.join(checkpoint_dir, run_dir_name())
+    # Everything a run derives from the clock or from the checkpoint directory is decided by rank 0 and broadcast: ranks that
+    # looked for themselves could pick different seeds, or see rank 0's new (empty) run directory as the one to resume from.
+    same_stream = seed is not None  # quirk Q8: --seed re-seeds every episode with the same value
+    if rank == 0:
+        plan = {"resume_dir": find_resume_dir(checkpoint_dir) if continue_from_checkpoint else None,
+                "start_iteration": find_start_iteration(checkpoint_dir) if continue_from_checkpoint else 0,
+                "run_dir": os.path.join(checkpoint_dir, run_dir_name()),
+                "cache_loaded": os.path.exists(os.path.join(cache_dir, "location_analysis.json")),  # load_location_analysis, :149-154
+                "rng_seed": int(seed) if seed is not None else int(master_seed if master_seed is not None else time.time_ns() & 0xFFFFFFFFFFFF)}
+    else:
+        plan = None
+    if distributed and world > 1:
+        box = [plan]
+        dist.broadcast_object_list(box, src=0)
+        plan = box[0]
+    weights = load_initial_weights(checkpoint_dir, continue_from_checkpoint, log if rank == 0 else (lambda *a: None),
+                                   resume_dir=plan["resume_dir"])
+    if distributed and world > 1:
+        dist.barrier()  # every rank has read the old checkpoint before rank 0 creates the new directory next to it
+    start_iteration, run_dir, cache_loaded, rng_seed = plan["start_iteration"], plan["run_dir"], plan["cache_loaded"], plan["rng_seed"]
     if rank == 0:
         os.makedirs(run_dir, exist_ok=True)
         if track_weight_history and not os.path.exists(os.path.join(run_dir, "weight_history.json")):
             open(os.path.join(run_dir, "weight_history.json"), "w").write("[]")
-    cache_loaded = os.path.exists(os.path.join(cache_dir, "location_analysis.json"))  # load_location_analysis, :149-154
     if rank == 0 and not cache_loaded:
         log("Warning: Location analysis cache not found in %s. All simulations will use full mode." % cache_dir)
-    # quirk Q8: --seed re-seeds every episode with the same value
-    same_stream = seed is not None
-    rng_seed = int(seed) if seed is not None else int(master_seed if master_seed is not None else time.time_ns() & 0xFFFFFFFFFFFF)
     per_gpu = max(1, min(int(batch_size), (max(num_iterations - start_iteration, 1) + world - 1) // world))
     trainer = BatchTrainer(per_gpu, seed=rng_seed, device=device, weights=weights, asset_dir=asset_dir,
                            distributed=distributed)
@@ -163,26 +180,28 @@ def run_multi_simulation(asset_dir, num_iterations, parallel=True, continue_from
         trainer.cfg = _abi.RunCfg(cost_only=optimization_mode == "cost_only", enable_energy_sales=enable_energy_sales,
                                   enable_construction_delays=enable_construction_delays, replay_best=replay_best,
                                   same_stream_all_episodes=same_stream)
-        # never past the requested iteration count, nor past the start of the replay phase: the last batch is smaller
+        # never past the requested iteration count, nor past the start of the replay phase: the last batch is smaller, and
+        # ragged over the ranks (the first `remainder` ranks take one episode more)
         phase_end = num_iterations if (is_full_run or final_full >= num_iterations) else num_iterations - final_full
-        trainer.n = max(1, min(per_gpu, (phase_end - completed + world - 1) // world))
-        advance = trainer.n * world
         if update_mode == "batch" and not replay_best:
+            advance = min(per_gpu * world, phase_end - completed)
+            trainer.set_batch(advance)
             st = trainer.step()
         else:
-            # replay batches and the sequential mode go through the host update (it rebuilds the doubled records of
-            # replay iterations, quirk Q10)
-            # The per-episode rule is sequential, so with several ranks every rank rolls out the SAME episode ids and applies the
-            # same update to its own copy of the weights: identical kernels on identical inputs give identical tables on every
-            # rank without an exchange (the extra GPUs add nothing in this phase, they only stay consistent).
-            if world > 1:
-                trainer.n = max(1, min(per_gpu, phase_end - completed))
-                advance = trainer.n
-            trainer.upload_weights()
-            trainer.launch_rollout(first_episode=trainer.next_episode)
-            res, traj = trainer.fetch_results()
-            st = weights.update(res, traj, replay_best=replay_best, rng_seed=rng_seed)
-            trainer.next_episode += trainer.n
+            # Replay batches and the sequential modes run the reference's per-episode rule (it rebuilds the doubled records of
+            # replay iterations, quirk Q10). The rule is sequential in the episodes, so with several ranks every rank rolls out
+            # the SAME episode ids and applies the same update to its own copy of the weights: identical kernels on identical
+            # inputs give identical tables on every rank without an exchange (the extra GPUs add nothing in this phase).
+            advance = min(per_gpu, phase_end - completed)
+            if update_mode == "sequential-host":
+                trainer.n = advance
+                trainer.upload_weights()
+                trainer.launch_rollout(first_episode=trainer.next_episode)
+                res, traj = trainer.fetch_results()
+                st = weights.update(res, traj, replay_best=replay_best, rng_seed=rng_seed)
+                trainer.next_episode += advance
+            else:
+                st = trainer.step_inorder(advance, rng_seed=rng_seed)
         completed += advance
         n_flagged += int(st.n_flagged)
         if st.n_flagged and rank == 0:

@@ -74,6 +74,8 @@ class BatchTrainer:
         self.cfg = cfg or _abi.RunCfg()
         self.weights = weights or _lib.Weights()
         self.next_episode = 0  # global id of the first episode of the next batch
+        self.offset = self.rank * self.n  # this rank's first episode inside the batch
+        self.n_total = self.n * self.world
         u8 = torch.uint8
         self.d_results = torch.empty(self.n * _abi.RESULT_DTYPE.itemsize, dtype=u8, device=self.device)
         self.d_traj = torch.empty(self.n * _abi.TRAJ_DTYPE.itemsize, dtype=u8, device=self.device)
@@ -92,12 +94,21 @@ class BatchTrainer:
         self.last_stats = None
         torch.cuda.synchronize(self.device)  # allocations above ran on the default stream
 
+    def set_batch(self, total):
+        """Split a batch of `total` episodes over the ranks: rank r takes total // world episodes, the first total % world
+        ranks one more (a ragged last batch never runs past the requested iteration count). At most episodes_per_gpu each."""
+        base, rem = divmod(int(total), self.world)
+        assert base + (1 if rem else 0) <= self.d_results.numel() // _abi.RESULT_DTYPE.itemsize, "batch larger than the buffers"
+        self.n = base + (1 if self.rank < rem else 0)
+        self.offset = self.rank * base + min(self.rank, rem)
+        self.n_total = int(total)
+
     # -- pieces (also used by bench.py to time the device-resident part alone) --
     def upload_weights(self):
         self.ctx.weights_upload(self.weights)
 
     def launch_rollout(self, first_episode=None):
-        first = self.next_episode + self.rank * self.n if first_episode is None else first_episode
+        first = self.next_episode + self.offset if first_episode is None else first_episode
         self.ctx.rollout_device(self.n, self.seed, first, self.d_results, self.d_traj, self.d_sites, None, self.cfg)
 
     def launch_stats(self):
@@ -107,7 +118,7 @@ class BatchTrainer:
 
     def _pack_best(self):
         self.ctx.update_pack_best_device(self.n, self.d_results, self.d_traj, self.d_best_score, self.d_best_index,
-                                         self.next_episode + self.rank * self.n, self.d_rec)
+                                         self.next_episode + self.offset, self.d_rec)
 
     def reduce_stats(self):
         """Sum the statistics table over ranks (the path's only exchange step)."""
@@ -144,9 +155,20 @@ class BatchTrainer:
             self.h_stats.copy_(self.d_stats, non_blocking=True)
             self.h_all_rec.copy_(self.d_all_rec, non_blocking=True)
         self.stream.synchronize()
-        n_total = self.n * self.world
+        n_total = self.n_total
         st = combine_and_apply(self.weights, self.h_stats.numpy(), self.h_all_rec.numpy(), n_total, self.next_episode)
         self.next_episode += n_total
+        self.last_stats = st
+        return st
+
+    def step_inorder(self, n=None, rng_seed=0):
+        """One batch under the reference's own rule: `n` episodes (default episodes_per_gpu) sampled from one snapshot, then
+        the per-episode update in episode order on the GPU (eg_train_batch_inorder; learning.rs:131-373 applied by
+        csrc/update.cu). The rule is sequential in the episodes, so under several ranks every rank runs the SAME episodes
+        and ends with the same table without an exchange (replicas)."""
+        n = self.n if n is None else int(n)
+        st = self.ctx.train_batch_inorder(self.weights, n, self.seed, self.next_episode, self.cfg, rng_seed)
+        self.next_episode += n
         self.last_stats = st
         return st
 

@@ -89,7 +89,7 @@ void usage() {
       "      --enable-csv-export         (always on: summary, improvement history and settlements CSVs of the best run)\n"
       "      --debug-logging, --debug-weights, --track-weight-history\n"
       "      --enable-construction-delays\n"
-      "additions: --assets <DIR> --batch-size <N> --update-mode batch|sequential --master-seed <S> --devices 0,1,..");
+      "additions: --assets <DIR> --batch-size <N> --update-mode batch|sequential|sequential-host --master-seed <S> --devices 0,1,..");
 }
 
 Args parse(int argc, char** argv) {
@@ -146,8 +146,9 @@ Args parse(int argc, char** argv) {
     } else if (f == "-h" || f == "--help") { usage(); std::exit(0); }
     else die("unknown argument " + f);
   }
-  if (a.update_mode != "batch" && a.update_mode != "sequential") die("--update-mode must be batch or sequential");
-  if (a.update_mode == "sequential" && a.devices.size() > 1) die("--update-mode sequential is single-GPU");
+  if (a.update_mode != "batch" && a.update_mode != "sequential" && a.update_mode != "sequential-host")
+    die("--update-mode must be batch, sequential or sequential-host");
+  if (a.update_mode != "batch" && a.devices.size() > 1) die("--update-mode sequential is single-GPU");
   if (a.batch_size == 0) die("--batch-size must be positive");
   return a;
 }
@@ -321,6 +322,8 @@ int main(int argc, char** argv) {
   uint64_t n_flagged = 0;
   double t_train = 0.0;        // wall time of the training batches (device statistics path)
   uint64_t n_train = 0;
+  double t_inorder = 0.0;      // wall time of the batches under the per-episode rule (replay phase, sequential modes)
+  uint64_t n_inorder = 0;
   while (completed < a.iterations) {
     const double t_batch = now_s();
     const bool is_full_run = a.force_full_simulation || !cache_loaded || completed + final_full >= a.iterations;
@@ -336,29 +339,39 @@ int main(int argc, char** argv) {
     cfg.same_stream_all_episodes = same_stream;
     uint64_t done_now = 0;
     if (a.update_mode == "batch" && !cfg.replay_best) {
-      // never past the requested iteration count, nor past the start of the replay phase: the last batch is smaller
+      // never past the requested iteration count, nor past the start of the replay phase: the last batch is smaller, and
+      // ragged over the GPUs (the first `rem` devices take one episode more)
       const uint64_t phase_end = (is_full_run || final_full >= a.iterations) ? a.iterations : a.iterations - final_full;
-      const uint32_t n_g = (uint32_t)std::min<uint64_t>(per_gpu, (phase_end - completed + G - 1) / G);
+      done_now = std::min<uint64_t>((uint64_t)per_gpu * G, phase_end - completed);
+      const uint64_t base = done_now / G, rem = done_now % G;
       for (size_t g = 0; g < G; g++)
-        check(eg_train_batch_begin(ctx[g], weights, &cfg, rng_seed, completed + g * n_g, n_g), "eg_train_batch_begin");
+        check(eg_train_batch_begin(ctx[g], weights, &cfg, rng_seed, completed + g * base + std::min<uint64_t>(g, rem), (uint32_t)(base + (g < rem ? 1 : 0))),
+              "eg_train_batch_begin");
       std::fill(stats.begin(), stats.end(), 0);
       for (size_t g = 0; g < G; g++) {
         check(eg_train_batch_end(ctx[g], shard_stats.data(), records.data() + g * EG_BEST_RECORD_BYTES), "eg_train_batch_end");
         for (size_t i = 0; i < stats.size(); i++) stats[i] += shard_stats[i];
       }
-      done_now = (uint64_t)n_g * G;
       check(eg_update_combine_apply(weights, stats.data(), records.data(), (uint32_t)G, done_now, completed, &st), "eg_update_combine_apply");
       t_train += now_s() - t_batch;
       n_train += done_now;
     } else {
-      // replay batches and the sequential mode: every episode's record comes to the host and the reference's per-episode
-      // update is applied in episode order (it rebuilds the doubled records of replay iterations, quirk Q10)
-      const uint32_t n_s = (uint32_t)std::min<uint64_t>(per_gpu, a.iterations - completed);
-      results.resize(n_s);
-      trajs.resize(n_s);
-      check(eg_rollout_batch(ctx[0], weights, &cfg, rng_seed, completed, n_s, results.data(), trajs.data(), nullptr, nullptr), "eg_rollout_batch");
-      check(eg_update(weights, results.data(), trajs.data(), n_s, cfg.replay_best, rng_seed, &st), "eg_update");
+      // replay batches and the sequential modes: the reference's per-episode update in episode order (it rebuilds the doubled
+      // records of replay iterations, quirk Q10) — on the GPU (eg_update_device behind eg_train_batch_inorder), or with
+      // --update-mode sequential-host on the host after copying every record back (eg_update, the slow twin)
+      const uint64_t phase_end = (is_full_run || final_full >= a.iterations) ? a.iterations : a.iterations - final_full;
+      const uint32_t n_s = (uint32_t)std::min<uint64_t>(per_gpu, phase_end - completed);
+      if (a.update_mode == "sequential-host") {
+        results.resize(n_s);
+        trajs.resize(n_s);
+        check(eg_rollout_batch(ctx[0], weights, &cfg, rng_seed, completed, n_s, results.data(), trajs.data(), nullptr, nullptr), "eg_rollout_batch");
+        check(eg_update(weights, results.data(), trajs.data(), n_s, cfg.replay_best, rng_seed, &st), "eg_update");
+      } else {
+        check(eg_train_batch_inorder(ctx[0], weights, &cfg, rng_seed, completed, n_s, rng_seed, &st), "eg_train_batch_inorder");
+      }
       done_now = n_s;
+      t_inorder += now_s() - t_batch;
+      n_inorder += done_now;
     }
     completed += done_now;
     if (st.n_flagged) {
@@ -395,10 +408,11 @@ int main(int argc, char** argv) {
   uint64_t launches = 0;
   for (size_t g = 0; g < G; g++) launches += eg_kernel_launches(ctx[g]);
   std::printf("{\"run_dir\": \"%s\", \"iterations\": %llu, \"start_iteration\": %llu, \"elapsed_s\": %.3f, \"episodes_per_s\": %.1f, "
-              "\"training_batches\": {\"episodes\": %llu, \"episodes_per_s\": %.1f}, "
+              "\"training_batches\": {\"episodes\": %llu, \"episodes_per_s\": %.1f}, \"per_episode_rule_batches\": {\"episodes\": %llu, \"seconds\": %.3f}, "
               "\"best_score\": %s, \"iterations_without_improvement\": %u, \"flagged_episodes\": %llu, \"n_gpus\": %zu, \"kernel_launches\": %llu}\n",
               run_dir.c_str(), (unsigned long long)completed, (unsigned long long)start_iteration, elapsed,
               (double)(completed - start_iteration) / std::max(elapsed, 1e-9), (unsigned long long)n_train, (double)n_train / std::max(t_train, 1e-9),
+              (unsigned long long)n_inorder, t_inorder,
               has_best ? std::to_string(best).c_str() : "null",
               st.iterations_without_improvement, (unsigned long long)n_flagged, G, (unsigned long long)launches);
   eg_weights_free(weights);
