@@ -144,6 +144,197 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+SUIT_METRIC = "candidate generator sites analysed per second (15 types x 26 years each)"
+SUIT_UNIT = "sites/s"
+
+
+def suitability_workload_text(args, info):
+    return ("location suitability of every candidate generator site: %d x %d sites over the 50 km map (%.1f m apart) x 15 generator types x 26 "
+            "simulated years, %s map (%d settlements, %d existing plants, %d coastline points), sites sharded over the ranks"
+            % (args.sites_per_axis, args.sites_per_axis, 50000.0 / max(args.sites_per_axis - 1, 1), args.suitability_map,
+               info["n_settlements"], info["n_existing"], info["n_coast"]))
+
+
+def cpu_suitability_rate(seconds_target):
+    """sites/s (26 years each) of the CPU oracle's calculate_generator_suitability port on a bounded sample: the oracle
+    analyses analyze_map's 51 x 51 grid of one year per call, as the reference does."""
+    import oracle_lib as O
+    w = O.World.ireland(fast=False)
+    t0 = time.perf_counter()
+    w.location_analysis(1)
+    one = time.perf_counter() - t0
+    calls = int(max(1, min(seconds_target / max(one, 1e-9), 2000)))
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        w.location_analysis(1)
+    dt = time.perf_counter() - t0
+    site_years = calls * 2601
+    return site_years / 26.0 / dt, "%d calls x 2601 points x 1 year in %.1f s (= %d site-years), 1 thread" % (calls, dt, site_years)
+
+
+def run_reference_suitability(args):
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    rate, sample = cpu_suitability_rate(min(2.0 * max(args.steps, 1), 60.0))
+    line = {"impl": "reference", "metric": SUIT_METRIC, "value": rate, "unit": SUIT_UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "location suitability of every candidate generator site x 15 types x 26 years (BASELINE configs[4])",
+                       "reference_arm": "CPU oracle port of Map::calculate_generator_suitability (the Rust reference cannot be built here), one "
+                                        "analyze_map pass per simulated year like the reference; bounded sample"},
+            "cpu_baseline": {"value": rate, "unit": SUIT_UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": SUIT_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_suitability(args, emit):
+    """BASELINE configs[4]: all candidate sites x 15 types x 26 years, sharded by site over the ranks, one final all-gather."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from eirgrid_b200 import _lib, synthetic, trainer as T
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(dev)
+    ctx = _lib.Context(local, stream.cuda_stream)
+    if args.suitability_map == "scaled10":
+        ctx.map_set(*synthetic.scaled_map(ASSETS, factor=10))
+    else:
+        ctx.map_load_dir(ASSETS)
+    info = ctx.map_info()
+    side = args.sites_per_axis
+    step = 50000.0 / max(side - 1, 1)
+    n_sites = side * side
+    NY, NT = 26, 15
+    first, n_mine = T.shard_of(n_sites, rank, world)
+    per_site = NY * NT  # doubles
+    # equal-sized slots for the gather: the largest shard
+    slot = T.shard_of(n_sites, 0, world)[1]
+    d_mine = torch.zeros(slot * per_site, dtype=torch.float64, device=dev)
+    d_all = torch.zeros(world * slot * per_site, dtype=torch.float64, device=dev) if world > 1 else d_mine
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def one_pass():
+        ctx.location_analysis_sites(True, side, step, 0, NY, first, n_mine, d_scores=d_mine)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(d_all, d_mine)
+
+    W, K = max(args.warmup, 3), args.steps
+    for _ in range(W):
+        one_pass()
+    barrier()
+    with ClockSampler(local) as clocks:
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+        launches0 = ctx.kernel_launches()
+        barrier()
+        for k in range(K):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            ev[k][0].record(stream)
+            ctx.location_analysis_sites(True, side, step, 0, NY, first, n_mine, d_scores=d_mine)
+            ev[k][1].record(stream)
+            if world > 1:
+                with torch.cuda.stream(stream):
+                    dist.all_gather_into_tensor(d_all, d_mine)
+            ev[k][2].record(stream)
+        barrier()
+        launches = ctx.kernel_launches() - launches0
+        t = torch.tensor([sum(ev[k][0].elapsed_time(ev[k][2]) for k in range(K)), sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(K))],
+                         dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms, kernel_ms = float(t[0].item()) / K, float(t[1].item()) / K
+        value = n_sites / (step_ms / 1e3)
+        # e2e: the host-buffer entry point (scores copied to the host inside the call), this rank's shard
+        Ke = min(K, 3)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            host_scores = ctx.location_analysis_sites(True, side, step, 0, NY, first, n_mine)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = n_sites * Ke / float(t.item())
+        # the placement search's own candidate grid (51 x 51 sites at 1 km), all 26 years: a single small launch
+        small = torch.zeros(2601 * per_site, dtype=torch.float64, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.location_analysis_sites(True, 51, 1000.0, 0, NY, 0, 2601, d_scores=small)
+        barrier()
+        e0.record(stream)
+        for _ in range(20):
+            ctx.location_analysis_sites(True, 51, 1000.0, 0, NY, 0, 2601, d_scores=small)
+        e1.record(stream)
+        barrier()
+        small_ms = e0.elapsed_time(e1) / 20
+    clock_summary = clocks.summary()
+    # a checksum of the gathered scores: every rank must hold the same table
+    import hashlib
+    torch.cuda.synchronize()
+    if world > 1:
+        # ranks' slots are `slot` sites long; drop the padding of the shorter shards
+        parts = [d_all[r * slot * per_site:(r * slot + T.shard_of(n_sites, r, world)[1]) * per_site] for r in range(world)]
+        full = torch.cat(parts)
+    else:
+        full = d_mine[:n_sites * per_site]
+    sha = hashlib.sha256(full.cpu().numpy().tobytes()).hexdigest()[:16]
+    water_sites = int((full.view(-1, NY, NT)[:, 0, 1] > 0).sum().item())  # OffshoreWind scores > 0 exactly on water tiles
+    if world > 1:
+        shas = [None] * world
+        dist.all_gather_object(shas, sha)
+        assert len(set(shas)) == 1, "ranks hold different score tables: %s" % shas
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = load_peaks()
+    n_coast = info["n_coast"]
+    # algorithmic work of one launch: every site tests 1 + 9 + 9 probes against every polygon edge, a site on water 441 more
+    # (get_distance_to_nearest_land); the scores are written once, 15 x 26 doubles per site (DESIGN.md)
+    mine_frac = n_mine / n_sites
+    edge_tests = n_coast * (19 * n_sites + 441 * water_sites) * mine_frac
+    algo_bytes = n_mine * per_site * 8 + (2 * n_coast + 2 * info["n_settlements"]) * 8 + 26 * info["n_settlements"] * 12
+    achieved = algo_bytes / (kernel_ms / 1e3) / 1e9
+    line = {"metric": SUIT_METRIC, "value": value, "unit": SUIT_UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": suitability_workload_text(args, info), "sites": n_sites, "sites_on_water": water_sites,
+                       "scores_per_step": n_sites * per_site, "kernel_ms": kernel_ms, "gather_ms": step_ms - kernel_ms,
+                       "l2": "256 MiB buffer written between timed steps (L2 flush)",
+                       "timing": "CUDA events on the launching stream per step, max over ranks",
+                       "placement_grid_51x51_all_years_ms": small_ms, "scores_sha256_16": sha},
+            "e2e": {"value": e2e, "unit": SUIT_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": n_mine * per_site * 8,
+                    "what": "eg_location_analysis_sites with a HOST output buffer: kernel + device-to-host copy of this rank's scores inside the call"},
+            "gpu_launches": int(launches), "clocks": clock_summary,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "eg_suitability_kernel<STAGED=true>", "algorithmic_bytes_per_launch": algo_bytes,
+                         "edge_tests": {"per_launch": edge_tests, "g_per_s": edge_tests / (kernel_ms / 1e3) / 1e9,
+                                        "what": "point-in-polygon edge tests (const_funcs.rs:143-158): 19 probes per site + 441 per site on water, "
+                                                "each against every coastline edge; what the kernel's time goes to"},
+                         "note": "the scores written (3.1 KB per site) are the only HBM traffic that scales; the kernel is bound by the FP64 compare / "
+                                 "issue rate of the edge tests, see roofline.edge_tests and profiles/"}}
+    if world == 1 and not args.no_cpu_baseline:
+        rate, sample = cpu_suitability_rate(args.cpu_seconds)
+        line["cpu_baseline"] = {"value": rate, "unit": SUIT_UNIT, "cores": 1, "kind": "port", "sample": sample}
+    emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -154,12 +345,18 @@ def main():
     ap.add_argument("--seed", type=int, default=20250101)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", choices=["ireland", "scaled10"], default="ireland",
+    ap.add_argument("--workload", choices=["ireland", "scaled10", "suitability"], default="ireland",
                     help="ireland: shipped map, 65,536 episodes in flight per GPU (BASELINE configs[2] batch shape, the headline); "
-                         "scaled10: synthetic 10x scaled grid of configs[3] (eirgrid_b200/synthetic.py)")
+                         "scaled10: synthetic 10x scaled grid of configs[3] (eirgrid_b200/synthetic.py); "
+                         "suitability: configs[4], every candidate site x 15 types x 26 years, sharded by site over the ranks")
+    ap.add_argument("--total-episodes", type=int, default=0,
+                    help="fixed-total mode (configs[3]: 1,000,000): every step is this many episodes split over the ranks (strong scaling)")
+    ap.add_argument("--sites-per-axis", type=int, default=1001,
+                    help="suitability workload: candidate sites per axis over the 50 km map (51 = the placement search's own 1 km grid)")
+    ap.add_argument("--suitability-map", choices=["ireland", "scaled10"], default="ireland")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference_suitability(args) if args.workload == "suitability" else run_reference(args)
 
     # stdout carries exactly one JSON line: libraries that print to fd 1 (NCCL's version banner) go to stderr
     sys.stdout.flush()
@@ -168,6 +365,9 @@ def main():
 
     def emit(line):
         os.write(json_fd, (json.dumps(line) + "\n").encode())
+
+    if args.workload == "suitability":
+        return run_suitability(args, emit)
 
     import torch
     import torch.distributed as dist
@@ -183,9 +383,16 @@ def main():
     if args.workload == "scaled10":
         from eirgrid_b200 import synthetic
         map_arrays = synthetic.scaled_map(ASSETS, factor=10)
+    strong = args.total_episodes > 0
+    if strong:  # fixed total per step, split over the ranks (the first total % world ranks take one episode more)
+        args.episodes = T.shard_of(args.total_episodes, 0, world)[1]
     tr = T.BatchTrainer(args.episodes, seed=args.seed, device=local, asset_dir=ASSETS, map_arrays=map_arrays, distributed=world > 1)
-    n_total = args.episodes * world
+    n_total = args.total_episodes if strong else args.episodes * world
+    tr.set_batch(n_total)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=tr.device)  # > 126 MB L2
+
+    def first_of(step_index):  # global id of this rank's first episode in batch `step_index` (batches never share ids)
+        return step_index * n_total + tr.offset
 
     def barrier():
         torch.cuda.synchronize()
@@ -197,7 +404,7 @@ def main():
     K = args.steps
     tr.upload_weights()  # value is measured on the initial action-weight table (first batch of a training run)
     for k in range(W):
-        tr.launch_rollout(first_episode=(k * world + rank) * args.episodes)
+        tr.launch_rollout(first_episode=first_of(k))
         tr.launch_stats()
         tr.reduce_stats()
         tr.warm_exchange()  # first-use costs of the small torch ops / collectives of step(), weights untouched
@@ -205,22 +412,25 @@ def main():
 
     with ClockSampler(local) as clocks:
         # ---- value: device-resident step (rollout + statistics kernels [+ allreduce]), CUDA events per step -------
-        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
         launches0 = tr.ctx.kernel_launches()
         barrier()
         for k in range(K):
             with torch.cuda.stream(tr.stream):
                 flush.zero_()
             ev[k][0].record(tr.stream)
-            tr.launch_rollout(first_episode=((W + k) * world + rank) * args.episodes)
+            tr.launch_rollout(first_episode=first_of(W + k))
             ev[k][1].record(tr.stream)
             tr.launch_stats()
-            tr.reduce_stats()
+            tr._pack_best()
+            ev[k][3].record(tr.stream)
+            tr.exchange()  # the one collective of the step: all-gather of [statistics | best-episode record]
             ev[k][2].record(tr.stream)
         barrier()
         launches = tr.ctx.kernel_launches() - launches0
         step_ms = sum(ev[k][0].elapsed_time(ev[k][2]) for k in range(K))
         rollout_ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(K)) / K
+        collective_us = sum(ev[k][3].elapsed_time(ev[k][2]) for k in range(K)) / K * 1e3
         t = torch.tensor([step_ms], dtype=torch.float64, device=tr.device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -239,6 +449,13 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
         e2e = n_total * K / e2e_s
+        # every rank applied the same update to its own copy of the weights: the tables must be identical, bit for bit
+        import hashlib
+        weights_sha = hashlib.sha256(bytes(tr.weights.table())).hexdigest()[:16]
+        if world > 1:
+            shas = [None] * world
+            dist.all_gather_object(shas, weights_sha)
+            assert len(set(shas)) == 1, "ranks ended the e2e steps with different weight tables: %s" % shas
 
         # ---- e2e with every episode's result and action record copied to the host (SimulationResult per episode)
         res_h = torch.empty(args.episodes * RESULT_BYTES, dtype=torch.uint8).pin_memory()
@@ -255,6 +472,44 @@ def main():
         barrier()
         full_s = time.perf_counter() - t0
 
+        # ---- the general kernel: every year's YearlyMetrics computed and written (eg_yearly, 3.7 KB per episode) -----------
+        KY = min(K, 10)
+        d_yearly = torch.empty(tr.n * 3744, dtype=torch.uint8, device=tr.device)
+        evy = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(KY)]
+        tr.ctx.rollout_device(tr.n, tr.seed, first_of(5000), tr.d_results, tr.d_traj, None, d_yearly, tr.cfg)
+        barrier()
+        for k in range(KY):
+            with torch.cuda.stream(tr.stream):
+                flush.zero_()
+            evy[k][0].record(tr.stream)
+            tr.ctx.rollout_device(tr.n, tr.seed, first_of(5001 + k), tr.d_results, tr.d_traj, None, d_yearly, tr.cfg)
+            evy[k][1].record(tr.stream)
+        barrier()
+        t = torch.tensor([sum(evy[k][0].elapsed_time(evy[k][1]) for k in range(KY))], dtype=torch.float64, device=tr.device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        value_yearly = n_total * KY / (float(t.item()) / 1e3)
+        del d_yearly
+
+        # ---- the reference's own update rule: one snapshot, the batch rolled out, every record applied in episode order on
+        # the GPU (eg_train_batch_inorder). Sequential in the episodes, so several ranks would only replicate: rank-local.
+        inorder = None
+        if world == 1:
+            KI = min(K, 10)
+            w_keep = tr.weights
+            tr.weights = T._lib.Weights()
+            tr.step_inorder(tr.n, rng_seed=args.seed)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(KI):
+                tr.step_inorder(tr.n, rng_seed=args.seed)
+            barrier()
+            dt = time.perf_counter() - t0
+            inorder = {"value": tr.n * KI / dt, "unit": UNIT, "ms_per_step": dt / KI * 1e3,
+                       "what": "eg_train_batch_inorder: snapshot H2D, rollout, the reference's per-episode update (learning.rs:131-373) applied "
+                               "in episode order by the GPU, state D2H; bit-identical to the host rule (tests/test_gpu_update_inorder.py)"}
+            tr.weights = w_keep
+
         # ---- the device-resident step again on the table the e2e steps have trained (what explains e2e vs value) ---------
         KT = min(K, 20)
         tr.upload_weights()
@@ -264,7 +519,7 @@ def main():
             with torch.cuda.stream(tr.stream):
                 flush.zero_()
             evt[k][0].record(tr.stream)
-            tr.launch_rollout(first_episode=((W + K + k) * world + rank + 1000) * args.episodes)
+            tr.launch_rollout(first_episode=first_of(W + K + k + 1000))
             tr.launch_stats()
             tr.reduce_stats()
             evt[k][1].record(tr.stream)
@@ -287,7 +542,7 @@ def main():
     # once; the static tables (walk lists 16 B + order 2 B per (class, year, site), per-site factors, plant terms, small
     # tables, stamp pattern, policy snapshot) are read once and then live in L2
     static_bytes = 7 * 26 * ns * (16 + 2) + ns * 16 + 26 * 15 * 3 * 26 * 16 + 40000 + 3200 + POLICY_BYTES
-    algo_bytes = args.episodes * (RESULT_BYTES + TRAJ_BYTES) + static_bytes
+    algo_bytes = tr.n * (RESULT_BYTES + TRAJ_BYTES) + static_bytes
     achieved = algo_bytes / (rollout_ms / 1e3) / 1e9
     traffic, issue = None, None
     tp = os.path.join(ROOT, "profiles", "rollout_traffic.json")
@@ -303,8 +558,8 @@ def main():
             sms, sched = torch.cuda.get_device_properties(local).multi_processor_count, 4
             ipe = prof["warp_instructions_per_episode"]
             peak_issue = sms * sched * (clock_summary.get("sm_mhz") or 1965.0) * 1e6
-            issue = {"warp_instructions_per_episode": ipe, "achieved_ginst_s": ipe * args.episodes / (rollout_ms / 1e3) / 1e9,
-                     "peak_ginst_s": peak_issue / 1e9, "frac": ipe * args.episodes / (rollout_ms / 1e3) / peak_issue,
+            issue = {"warp_instructions_per_episode": ipe, "achieved_ginst_s": ipe * tr.n / (rollout_ms / 1e3) / 1e9,
+                     "peak_ginst_s": peak_issue / 1e9, "frac": ipe * tr.n / (rollout_ms / 1e3) / peak_issue,
                      "source": "profiles/rollout_traffic.json (ncu smsp__inst_executed.sum) x live kernel time"}
             # FP64 ceiling without FMA (the path is compiled --fmad=false), measured live; the kernel's share of it from ncu
             import ctypes
@@ -316,7 +571,7 @@ def main():
             traffic, issue = None, None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "policy rollout + scoring + batch weight-update statistics, %d episodes in flight per GPU "
                                "(BASELINE configs[2] batch shape), %s" % (args.episodes, "Irish map: 130 settlements, 59 existing plants, 2601 candidate sites"
@@ -327,14 +582,20 @@ def main():
                    "episodes_per_gpu": args.episodes, "l2": "256 MiB buffer written between timed steps (L2 flush)",
                    "timing": "CUDA events on the launching stream per step, max over ranks",
                    "rollout_kernel_ms": rollout_ms,
-                   "value_on_trained_table": value_trained},
+                   "value_on_trained_table": value_trained,
+                   "value_with_yearly_metrics": value_yearly,
+                   "collective": {"what": "one all-gather of [statistics int64[5156] | best-episode record 1168 B] per step, summed locally in rank order",
+                                  "bytes_per_rank": tr.pack_words * 8, "us_per_step": collective_us if world > 1 else 0.0},
+                   "weights_sha256_16_after_e2e": weights_sha,
+                   "episodes_per_step_total": n_total},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": POLICY_BYTES, "d2h_bytes_per_step": tr.d2h_bytes_per_step,
                 "what": "BatchTrainer.step(): weights H2D from the host, rollout + statistics + winner-record kernels, statistics and "
                         "winner record D2H (pinned), host-side weight update applied. The weights learn during these steps (stagnation-mode "
                         "tables sample ~20 % more actions and plants per episode), so the rollout itself is slower here than in `value`, "
                         "which is timed on the initial table",
-                "with_all_results_to_host": {"value": args.episodes * world * K / full_s, "unit": UNIT,
-                                             "d2h_bytes_per_step": args.episodes * (RESULT_BYTES + TRAJ_BYTES)}},
+                "with_all_results_to_host": {"value": n_total * K / full_s, "unit": UNIT,
+                                             "d2h_bytes_per_step": args.episodes * (RESULT_BYTES + TRAJ_BYTES)},
+                "reference_rule_in_order_on_gpu": inorder},
         "gpu_launches": int(launches),
         "clocks": clock_summary,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -343,6 +604,8 @@ def main():
                      "note": "the path moves ~1.2 KB per episode and is bound by warp-instruction issue/latency, not HBM: "
                              "see roofline.issue, DESIGN.md §4.1 and profiles/"},
     }
+    if strong:
+        line["config"]["workload"] += "; fixed total of %d episodes per step split over the ranks" % n_total
     if world == 1 and not args.no_cpu_baseline and args.workload == "ireland":
         threads = os.cpu_count() or 1
         rate, n_cpu, dt = cpu_reference_rate(args.cpu_seconds, threads, literal=True)

@@ -22,6 +22,7 @@ EXPORTS = [
     "eg_update_apply_stats", "eg_location_analysis", "eg_update_stats_clear_device", "eg_update_pack_best_device",
     "eg_location_analysis_year", "eg_microbench_fp64", "eg_export_best_run_csv", "eg_weights_history_append", "eg_train_batch_begin", "eg_train_batch_end", "eg_train_batch_results", "eg_update_combine_apply",
     "eg_update_device", "eg_train_batch_inorder", "eg_rule_math",
+    "eg_location_analysis_sites", "eg_location_analysis_sites_device", "eg_location_analysis_write",
 ]
 
 
@@ -80,6 +81,9 @@ def lib():
     L.eg_update_stats_clear_device.argtypes = [vp, vp]
     L.eg_update_pack_best_device.argtypes = [vp, vp, vp, u32, vp, vp, u64, vp]
     L.eg_weights_history_append.argtypes = [vp, u64, C.c_char_p]
+    L.eg_location_analysis_sites.argtypes = [vp, C.c_int, u32, C.c_double, u32, u32, u32, u32, vp]
+    L.eg_location_analysis_sites_device.argtypes = [vp, C.c_int, u32, C.c_double, u32, u32, u32, u32, vp]
+    L.eg_location_analysis_write.argtypes = [vp, C.c_int, C.c_double, C.c_char_p, C.c_char_p]
     L.eg_rule_math.argtypes = [C.c_int, u32, vp, vp, u32, vp]
     L.eg_microbench_fp64.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.eg_export_best_run_csv.argtypes = [vp, vp, C.POINTER(_abi.RunCfg), C.c_char_p, C.c_char_p]
@@ -336,6 +340,26 @@ class Context:
         out = np.zeros((n, _abi.N_GEN_TYPES))
         check(self.L.eg_location_analysis_year(self.h, int(use_loaded_map), int(year_index), half_steps, step, _abi.ptr(out), first_point, n))
         return out
+
+    def location_analysis_sites(self, use_loaded_map, sites_per_axis, step, year_first=0, n_years=26, first_site=0, n_sites=None,
+                                d_scores=None):
+        """All candidate sites x years x 15 types in one pass (BASELINE configs[4]); returns [n_sites, n_years, 15], or
+        queues the kernel into the device buffer `d_scores` and returns None."""
+        n = sites_per_axis * sites_per_axis - first_site if n_sites is None else n_sites
+        if d_scores is not None:
+            check(self.L.eg_location_analysis_sites_device(self.h, int(use_loaded_map), sites_per_axis, float(step), year_first,
+                                                           n_years, first_site, n, _dev_ptr(d_scores)))
+            return None
+        out = np.zeros((n, n_years, _abi.N_GEN_TYPES))
+        check(self.L.eg_location_analysis_sites(self.h, int(use_loaded_map), sites_per_axis, float(step), year_first, n_years,
+                                                first_site, n, _abi.ptr(out)))
+        return out
+
+    def location_analysis_write(self, use_loaded_map, min_suitability=0.3, cache_dir=None, text_path=None):
+        """analyze_locations + save_cache + save_to_file (bin/analyze_locations.rs)"""
+        check(self.L.eg_location_analysis_write(self.h, int(use_loaded_map), float(min_suitability),
+                                                os.fsencode(cache_dir) if cache_dir else None,
+                                                os.fsencode(text_path) if text_path else None))
 
     def train_batch_results(self, n, want_traj=True):
         """Results (and records) of the last eg_train_batch_* call, copied to the host."""

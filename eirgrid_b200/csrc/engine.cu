@@ -14,6 +14,7 @@
 #include "common.hpp"
 #include "episode.cuh"
 #include "host_tables.hpp"
+#include "json_min.hpp"
 #include "site_tables.cuh"
 #include "stats.cuh"
 #include "suitability.cuh"
@@ -60,6 +61,8 @@ struct eg_ctx {
   int* d_r2_limit = nullptr;
   double *d_sx = nullptr, *d_sy = nullptr, *d_ex = nullptr, *d_ey = nullptr, *d_cx = nullptr, *d_cy = nullptr;
   uint32_t* d_pop = nullptr;
+  double* d_urban_r = nullptr;         // [26][S] sqrt(pop) * 5 (is_urban_area, map_handler.rs:1199-1209)
+  double urban_r_max = 0.0;
   EgPolicyDevice* d_policy = nullptr;
   EgPolicyDevice* h_policy[2] = {nullptr, nullptr};   // pinned staging of the snapshot, used in turn
   cudaEvent_t policy_copied[2] = {nullptr, nullptr};  // the H2D copy issued from h_policy[b] has completed
@@ -94,9 +97,10 @@ namespace {
 
 void free_map(eg_ctx* c) {
   void* ptrs[] = {c->d_small, c->d_plant_terms, c->d_site_opinion, c->d_coast, c->d_prefix, c->d_static_unsorted, c->d_order,
-                  c->d_static_sorted, c->d_prefix_sorted, c->d_walk, c->d_near, c->d_r2_limit, c->d_sx, c->d_sy, c->d_ex, c->d_ey, c->d_cx, c->d_cy, c->d_pop};
+                  c->d_static_sorted, c->d_prefix_sorted, c->d_walk, c->d_near, c->d_r2_limit, c->d_sx, c->d_sy, c->d_ex, c->d_ey, c->d_cx, c->d_cy, c->d_pop, c->d_urban_r};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  c->d_urban_r = nullptr;
   c->d_small = nullptr; c->d_plant_terms = nullptr; c->d_site_opinion = nullptr; c->d_coast = nullptr; c->d_prefix = nullptr;
   c->d_static_unsorted = nullptr; c->d_order = nullptr; c->d_static_sorted = nullptr; c->d_prefix_sorted = nullptr; c->d_walk = nullptr;
   c->d_near = nullptr; c->d_r2_limit = nullptr; c->d_sx = c->d_sy = c->d_ex = c->d_ey = c->d_cx = c->d_cy = nullptr; c->d_pop = nullptr;
@@ -105,7 +109,9 @@ void free_map(eg_ctx* c) {
 
 template <typename T>
 int upload(T** dst, const T* src, size_t n, cudaStream_t s) {
-  EG_CUDA(cudaMalloc((void**)dst, std::max<size_t>(n, 1) * sizeof(T)));
+  // two spare elements, zeroed: the suitability kernel stages these arrays with bulk copies in 16-byte units
+  EG_CUDA(cudaMalloc((void**)dst, (n + 2) * sizeof(T)));
+  EG_CUDA(cudaMemsetAsync(*dst, 0, (n + 2) * sizeof(T), s));
   if (n) EG_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
   return EG_OK;
 }
@@ -130,6 +136,16 @@ int build_device_map(eg_ctx* c) {
   if ((rc = upload(&c->d_cx, m.cx.data(), m.cx.size(), s))) return rc;
   if ((rc = upload(&c->d_cy, m.cy.data(), m.cy.size(), s))) return rc;
   if ((rc = upload(&c->d_pop, c->htab.pop.data(), c->htab.pop.size(), s))) return rc;
+  {
+    std::vector<double> urban_r(c->htab.pop.size());
+    c->urban_r_max = 0.0;
+    for (size_t i = 0; i < urban_r.size(); i++) {
+      urban_r[i] = std::sqrt((double)c->htab.pop[i]) * 5.0;
+      c->urban_r_max = std::max(c->urban_r_max, urban_r[i]);
+    }
+    if ((rc = upload(&c->d_urban_r, urban_r.data(), urban_r.size(), s))) return rc;
+    EG_CUDA(cudaStreamSynchronize(s));  // urban_r is a local
+  }
   EG_CUDA(cudaMalloc((void**)&c->d_site_opinion, ns * sizeof(double)));
   EG_CUDA(cudaMalloc((void**)&c->d_coast, ns * sizeof(double)));
   EG_CUDA(cudaMalloc((void**)&c->d_prefix, (size_t)EG_N_RCLASS * EG_NY * ns * sizeof(double)));
@@ -878,6 +894,41 @@ int eg_export_best_run_csv(eg_ctx* c, const eg_weights* w, const eg_run_cfg* cfg
   return EG_OK;
 }
 
+namespace {
+
+EgSuitabilityParams suitability_params(const eg_ctx* c, int use_loaded_map, int mode, int half, int side, double step, uint32_t year_first,
+                                       uint32_t n_years, uint32_t first, uint32_t n, double* d_scores) {
+  EgSuitabilityParams p{};
+  p.mode = mode; p.half = half; p.side = side; p.step = step; p.first = first; p.n = n;
+  p.year_first = (int)year_first; p.n_years = (int)n_years;
+  p.n_settlements = use_loaded_map ? (int)c->hmap.sx.size() : 0;
+  p.sx = c->d_sx; p.sy = c->d_sy; p.pop = c->d_pop; p.urban_r = c->d_urban_r; p.urban_r_max = c->urban_r_max;
+  p.n_generators = use_loaded_map ? (int)c->hmap.ex.size() : 0;
+  p.gx = c->d_ex; p.gy = c->d_ey;
+  p.n_coast = (int)c->hmap.cx.size(); p.cx = c->d_cx; p.cy = c->d_cy;
+  p.scores = d_scores;
+  return p;
+}
+
+// runs the kernel into a temporary device buffer and copies the scores to the host
+int suitability_to_host(eg_ctx* c, const EgSuitabilityParams& p0, double* scores_out) {
+  EG_CUDA(cudaSetDevice(c->device));
+  EgSuitabilityParams p = p0;
+  const size_t count = (size_t)p.n * p.n_years * EG_NT;
+  double* d_scores = nullptr;
+  EG_CUDA(cudaMalloc((void**)&d_scores, std::max<size_t>(count, 1) * sizeof(double)));
+  p.scores = d_scores;
+  cudaError_t err = eg_launch_suitability(p, c->stream);
+  if (err == cudaSuccess && count) c->launches++;
+  if (err == cudaSuccess) err = cudaMemcpyAsync(scores_out, d_scores, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
+  cudaFree(d_scores);
+  if (err != cudaSuccess) return eg_fail(EG_ERR_CUDA, cudaGetErrorString(err));
+  return EG_OK;
+}
+
+}  // namespace
+
 int eg_location_analysis(eg_ctx* c, int use_loaded_map, int32_t half_steps, double step, double* scores_out,
                          uint32_t first_point, uint32_t n_points) {
   return eg_location_analysis_year(c, use_loaded_map, 0, half_steps, step, scores_out, first_point, n_points);
@@ -891,23 +942,138 @@ int eg_location_analysis_year(eg_ctx* c, int use_loaded_map, uint32_t year_index
   if (half_steps < 0 || half_steps > 1000) return eg_fail(EG_ERR_INVALID, "half_steps out of range");
   const uint32_t side = (uint32_t)(2 * half_steps + 1);
   if ((uint64_t)first_point + n_points > (uint64_t)side * side) return eg_fail(EG_ERR_INVALID, "point range exceeds the analysis grid");
+  return suitability_to_host(c, suitability_params(c, use_loaded_map, 0, half_steps, 0, step, year_index, 1, first_point, n_points, nullptr), scores_out);
+}
+
+int eg_location_analysis_sites_device(eg_ctx* c, int use_loaded_map, uint32_t sites_per_axis, double step, uint32_t year_first,
+                                      uint32_t n_years, uint32_t first_site, uint32_t n_sites, double* d_scores) {
+  if (!c || !d_scores) return eg_fail(EG_ERR_INVALID, "eg_location_analysis_sites_device: NULL argument");
+  if (!c->map_ready) return eg_fail(EG_ERR_STATE, "no map loaded (the coastline polygon is needed)");
+  if (year_first >= EG_NY || n_years > EG_NY - year_first) return eg_fail(EG_ERR_INVALID, "year range outside 2025..2050");
+  if (sites_per_axis == 0 || sites_per_axis > 65535u) return eg_fail(EG_ERR_INVALID, "sites_per_axis out of range");
+  if ((uint64_t)first_site + n_sites > (uint64_t)sites_per_axis * sites_per_axis) return eg_fail(EG_ERR_INVALID, "site range exceeds the grid");
   EG_CUDA(cudaSetDevice(c->device));
-  double* d_scores = nullptr;
-  EG_CUDA(cudaMalloc((void**)&d_scores, std::max<size_t>((size_t)n_points * EG_NT, 1) * sizeof(double)));
-  EgSuitabilityParams p{};
-  p.half = half_steps; p.step = step; p.first = first_point; p.n = n_points;
-  p.n_settlements = use_loaded_map ? (int)c->hmap.sx.size() : 0;
-  p.sx = c->d_sx; p.sy = c->d_sy; p.pop = c->d_pop + (size_t)year_index * c->hmap.sx.size();  // pop[y][s]: populations of that year
-  p.n_generators = use_loaded_map ? (int)c->hmap.ex.size() : 0;
-  p.gx = c->d_ex; p.gy = c->d_ey;
-  p.n_coast = (int)c->hmap.cx.size(); p.cx = c->d_cx; p.cy = c->d_cy;
-  p.scores = d_scores;
-  cudaError_t err = eg_launch_suitability(p, c->stream);
-  if (err == cudaSuccess && n_points) c->launches++;
-  if (err == cudaSuccess) err = cudaMemcpyAsync(scores_out, d_scores, (size_t)n_points * EG_NT * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-  if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
-  cudaFree(d_scores);
-  if (err != cudaSuccess) return eg_fail(EG_ERR_CUDA, cudaGetErrorString(err));
+  const EgSuitabilityParams p = suitability_params(c, use_loaded_map, 1, 0, (int)sites_per_axis, step, year_first, n_years, first_site, n_sites, d_scores);
+  EG_CUDA(eg_launch_suitability(p, c->stream));
+  if (n_sites && n_years) c->launches++;
+  return EG_OK;
+}
+
+int eg_location_analysis_sites(eg_ctx* c, int use_loaded_map, uint32_t sites_per_axis, double step, uint32_t year_first, uint32_t n_years,
+                               uint32_t first_site, uint32_t n_sites, double* scores_out) {
+  if (!c || !scores_out) return eg_fail(EG_ERR_INVALID, "eg_location_analysis_sites: NULL argument");
+  if (!c->map_ready) return eg_fail(EG_ERR_STATE, "no map loaded (the coastline polygon is needed)");
+  if (year_first >= EG_NY || n_years > EG_NY - year_first) return eg_fail(EG_ERR_INVALID, "year range outside 2025..2050");
+  if (sites_per_axis == 0 || sites_per_axis > 65535u) return eg_fail(EG_ERR_INVALID, "sites_per_axis out of range");
+  if ((uint64_t)first_site + n_sites > (uint64_t)sites_per_axis * sites_per_axis) return eg_fail(EG_ERR_INVALID, "site range exceeds the grid");
+  return suitability_to_host(c, suitability_params(c, use_loaded_map, 1, 0, (int)sites_per_axis, step, year_first, n_years, first_site, n_sites, nullptr), scores_out);
+}
+
+// LocationAnalysis::analyze_map + save_cache + save_to_file (map_handler.rs:61-142,208-248; bin/analyze_locations.rs:19-46)
+int eg_location_analysis_write(eg_ctx* c, int use_loaded_map, double min_suitability, const char* cache_dir, const char* text_path) {
+  if (!c) return eg_fail(EG_ERR_INVALID, "eg_location_analysis_write: ctx is NULL");
+  const int half = 25;          // ceil(MAP_MAX_X / (2 * GRID_CELL_SIZE)) = ceil(50000 / 2000)
+  const double step = 2000.0;   // GRID_CELL_SIZE * 2
+  const int side = 2 * half + 1;
+  std::vector<double> scores((size_t)side * side * EG_NT);
+  int rc = eg_location_analysis_year(c, use_loaded_map, 0, half, step, scores.data(), 0, (uint32_t)(side * side));
+  if (rc) return rc;
+  struct Loc { double x, y; std::vector<int> types; };
+  std::vector<Loc> locations;
+  size_t type_counts[EG_NT] = {0};
+  std::vector<size_t> type_to_locations[EG_NT];
+  size_t multi = 0;
+  auto clamp_map = [](double v) { return std::min(std::max(v, 0.0), 50000.0); };  // Coordinate::new, data/poi.rs:11-15
+  for (int i = -half; i <= half; i++)
+    for (int j = -half; j <= half; j++) {
+      const double* sc = &scores[((size_t)(i + half) * side + (size_t)(j + half)) * EG_NT];
+      Loc loc{clamp_map((double)i * step), clamp_map((double)j * step), {}};
+      for (int t = 0; t < EG_NT; t++)
+        if (sc[t] >= min_suitability) {
+          loc.types.push_back(t);
+          type_counts[t]++;
+          type_to_locations[t].push_back(locations.size());
+        }
+      if (!loc.types.empty()) {
+        if (loc.types.size() > 1) multi++;
+        locations.push_back(loc);
+      }
+    }
+  // scores of a stored location, by its position in the scan
+  auto score_of = [&](const Loc& l, int t) {
+    // locations keep their coordinates only; find the scan cell again through the coordinate (first cell with it: the
+    // clamped duplicates share their scores)
+    const int i = (int)(l.x / step), j = (int)(l.y / step);
+    return scores[((size_t)(i + half) * side + (size_t)(j + half)) * EG_NT + t];
+  };
+  if (cache_dir) {
+    if (!mkdir_p(cache_dir)) return eg_fail(EG_ERR_IO, std::string("cannot create ") + cache_dir);
+    // serde_json::to_string_pretty(LocationAnalysis): fields in declaration order; the HashMaps (unordered in the
+    // reference) are written in generator-type order
+    std::string o = "{\n  \"locations\": [";
+    for (size_t k = 0; k < locations.size(); k++) {
+      const Loc& l = locations[k];
+      o += k ? ",\n    {\n" : "\n    {\n";
+      o += "      \"coordinate\": {\n        \"x\": " + egjson::fmt_double(l.x) + ",\n        \"y\": " + egjson::fmt_double(l.y) + "\n      },\n";
+      o += "      \"suitability_scores\": {";
+      for (size_t q = 0; q < l.types.size(); q++)
+        o += std::string(q ? ",\n" : "\n") + "        \"" + kCsvGenNames[l.types[q]] + "\": " + egjson::fmt_double(score_of(l, l.types[q]));
+      o += "\n      }\n    }";
+    }
+    o += locations.empty() ? "],\n" : "\n  ],\n";
+    auto count_map = [&](const char* name) {
+      o += std::string("  \"") + name + "\": {";
+      bool first = true;
+      for (int t = 0; t < EG_NT; t++)
+        if (type_counts[t]) {
+          o += std::string(first ? "\n" : ",\n") + "    \"" + kCsvGenNames[t] + "\": " + std::to_string(type_counts[t]);
+          first = false;
+        }
+      o += first ? "},\n" : "\n  },\n";
+    };
+    count_map("type_counts");
+    o += "  \"multi_type_locations\": [";
+    bool first_multi = true;
+    for (const Loc& l : locations) {
+      if (l.types.size() < 2) continue;
+      o += first_multi ? "\n    [\n" : ",\n    [\n";
+      first_multi = false;
+      o += "      {\n        \"x\": " + egjson::fmt_double(l.x) + ",\n        \"y\": " + egjson::fmt_double(l.y) + "\n      },\n      [";
+      for (size_t q = 0; q < l.types.size(); q++) o += std::string(q ? ",\n" : "\n") + "        \"" + kCsvGenNames[l.types[q]] + "\"";
+      o += "\n      ]\n    ]";
+    }
+    o += first_multi ? "],\n" : "\n  ],\n";
+    count_map("remaining_spaces");
+    o += "  \"exhausted_types\": [],\n  \"type_to_locations\": {";
+    bool first_type = true;
+    for (int t = 0; t < EG_NT; t++) {
+      if (type_to_locations[t].empty()) continue;
+      o += std::string(first_type ? "\n" : ",\n") + "    \"" + kCsvGenNames[t] + "\": [";
+      first_type = false;
+      for (size_t q = 0; q < type_to_locations[t].size(); q++) o += std::string(q ? ",\n" : "\n") + "      " + std::to_string(type_to_locations[t][q]);
+      o += "\n    ]";
+    }
+    o += first_type ? "}\n}" : "\n  }\n}";
+    const std::string path = std::string(cache_dir) + "/location_analysis.json";
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f || std::fwrite(o.data(), 1, o.size(), f) != o.size()) { if (f) std::fclose(f); return eg_fail(EG_ERR_IO, "cannot write " + path); }
+    std::fclose(f);
+  }
+  if (text_path) {
+    std::string o = "Location Analysis Results\n========================\n\n";
+    o += "Total suitable locations: " + std::to_string(locations.size()) + "\nMulti-type locations: " + std::to_string(multi) + "\n\n";
+    o += "Locations by Generator Type:\n--------------------------\n";
+    for (int t = 0; t < EG_NT; t++)
+      if (type_counts[t]) o += std::string(kCsvGenNames[t]) + ": " + std::to_string(type_counts[t]) + "\n";
+    o += "\nDetailed Location Data:\n---------------------\n";
+    for (const Loc& l : locations) {
+      o += "\nCoordinate: (" + rust_display(l.x) + ", " + rust_display(l.y) + ")\n";
+      for (int t : l.types) o += std::string("  ") + kCsvGenNames[t] + ": " + fixed(score_of(l, t), 3) + "\n";
+    }
+    FILE* f = std::fopen(text_path, "wb");
+    if (!f || std::fwrite(o.data(), 1, o.size(), f) != o.size()) { if (f) std::fclose(f); return eg_fail(EG_ERR_IO, std::string("cannot write ") + text_path); }
+    std::fclose(f);
+  }
   return EG_OK;
 }
 

@@ -4,8 +4,9 @@ One process per GPU. Each step every rank
   1. uploads the shared weights snapshot        (== local_weights = shared.read().clone(), :457-460)
   2. rolls out `episodes_per_gpu` episodes       (== run_iteration for its shard of iteration ids, :472)
   3. accumulates the update statistics on the GPU (== the write-lock section :494-508, batch-synchronous form)
-  4. sums the statistics table over ranks        (one NCCL allreduce, int64) and gathers each rank's best episode
-  5. applies the identical update on every rank  (eg_update_apply_stats)
+  4. exchanges them: ONE NCCL all-gather of [statistics table | this rank's best episode record] (42 KB per rank);
+     every rank adds the tables up in rank order (integers: the same sum everywhere) and picks the batch winner
+  5. applies the identical update on every rank  (eg_update_combine_apply)
 
 PyTorch is used for device buffers, streams and torch.distributed only.
 """
@@ -23,6 +24,7 @@ def _torch():
 
 
 REC_BYTES = 16 + _abi.RESULT_DTYPE.itemsize + _abi.TRAJ_DTYPE.itemsize  # [score f64 | global id i64 | eg_result | eg_traj]
+assert REC_BYTES % 8 == 0
 
 
 def pack_record(score, global_index, result, traj):
@@ -46,6 +48,34 @@ def combine_and_apply(weights, stats_sum, all_records, n_total, first_episode):
     _lib.check(_lib.lib().eg_update_combine_apply(weights.h, _abi.ptr(stats), _abi.ptr(rec), rec.shape[0], int(n_total),
                                                   int(first_episode), C.byref(st)))
     return st
+
+
+PACK_WORDS = _abi.STATS_WORDS + REC_BYTES // 8  # int64 words a rank contributes to the exchange step
+
+
+def shard_of(total, rank, world):
+    """(first episode inside the batch, episode count) of `rank` when a batch of `total` episodes is split over `world`
+    ranks: total // world each, the first total % world ranks one more (a ragged last batch never runs past the
+    requested iteration count)."""
+    base, rem = divmod(int(total), int(world))
+    return rank * base + min(rank, rem), base + (1 if rank < rem else 0)
+
+
+def pack_buffer(stats, record):
+    """[statistics int64[STATS_WORDS] | candidate record] as one int64 array: what a rank sends in the exchange step."""
+    out = np.zeros(PACK_WORDS, np.int64)
+    out[:_abi.STATS_WORDS] = stats
+    out[_abi.STATS_WORDS:] = np.ascontiguousarray(record, dtype=np.uint8).view(np.int64)
+    return out
+
+
+def sum_and_apply(weights, all_packs, n_total, first_episode):
+    """Host side of the exchange step after the all-gather, identical on every rank: add the ranks' statistics tables up
+    in rank order (integers: the same sum everywhere), pick the winner among their candidate records and apply."""
+    packs = np.ascontiguousarray(all_packs, dtype=np.int64).reshape(-1, PACK_WORDS)
+    stats_sum = packs[:, :_abi.STATS_WORDS].sum(axis=0, dtype=np.int64)
+    records = np.ascontiguousarray(packs[:, _abi.STATS_WORDS:]).view(np.uint8)
+    return combine_and_apply(weights, stats_sum, records, n_total, first_episode)
 
 
 class BatchTrainer:
@@ -80,27 +110,27 @@ class BatchTrainer:
         self.d_results = torch.empty(self.n * _abi.RESULT_DTYPE.itemsize, dtype=u8, device=self.device)
         self.d_traj = torch.empty(self.n * _abi.TRAJ_DTYPE.itemsize, dtype=u8, device=self.device)
         self.d_sites = torch.empty(self.n * _abi.SITES_DTYPE.itemsize, dtype=u8, device=self.device) if want_sites else None
-        self.d_stats = torch.zeros(_abi.STATS_WORDS, dtype=torch.int64, device=self.device)
+        # what a rank contributes to the exchange step, one flat buffer: [statistics table int64[STATS_WORDS] | candidate
+        # record: score f64, global index i64, eg_result, eg_traj]
+        self.rec_bytes = REC_BYTES
+        self.pack_words = PACK_WORDS
+        self.d_pack = torch.zeros(self.pack_words, dtype=torch.int64, device=self.device)
+        self.d_stats = self.d_pack[:_abi.STATS_WORDS]
+        self.d_rec = self.d_pack[_abi.STATS_WORDS:].view(u8)
         self.d_best_score = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.d_best_index = torch.zeros(1, dtype=torch.int64, device=self.device)
-        # per-rank candidate record: [score f64 | global index i64 | eg_result | eg_traj]
-        self.rec_bytes = REC_BYTES
-        self.d_rec = torch.zeros(self.rec_bytes, dtype=u8, device=self.device)
-        self.d_all_rec = torch.zeros(self.world * self.rec_bytes, dtype=u8, device=self.device)
-        self.h_stats = torch.zeros(_abi.STATS_WORDS, dtype=torch.int64).pin_memory()
-        self.h_all_rec = torch.zeros(self.world * self.rec_bytes, dtype=u8).pin_memory()
+        self.d_all_pack = torch.zeros(self.world * self.pack_words, dtype=torch.int64, device=self.device)
+        self.h_all_pack = torch.zeros(self.world * self.pack_words, dtype=torch.int64).pin_memory()
         self.h2d_bytes_per_step = 0
-        self.d2h_bytes_per_step = self.h_stats.numel() * 8 + self.h_all_rec.numel()
+        self.d2h_bytes_per_step = self.h_all_pack.numel() * 8
         self.last_stats = None
         torch.cuda.synchronize(self.device)  # allocations above ran on the default stream
 
     def set_batch(self, total):
         """Split a batch of `total` episodes over the ranks: rank r takes total // world episodes, the first total % world
         ranks one more (a ragged last batch never runs past the requested iteration count). At most episodes_per_gpu each."""
-        base, rem = divmod(int(total), self.world)
-        assert base + (1 if rem else 0) <= self.d_results.numel() // _abi.RESULT_DTYPE.itemsize, "batch larger than the buffers"
-        self.n = base + (1 if self.rank < rem else 0)
-        self.offset = self.rank * base + min(self.rank, rem)
+        self.offset, self.n = shard_of(total, self.rank, self.world)
+        assert self.n <= self.d_results.numel() // _abi.RESULT_DTYPE.itemsize, "batch larger than the buffers"
         self.n_total = int(total)
 
     # -- pieces (also used by bench.py to time the device-resident part alone) --
@@ -120,23 +150,26 @@ class BatchTrainer:
         self.ctx.update_pack_best_device(self.n, self.d_results, self.d_traj, self.d_best_score, self.d_best_index,
                                          self.next_episode + self.offset, self.d_rec)
 
+    def exchange(self):
+        """The path's only exchange step: one all-gather of every rank's [statistics | best-episode record] buffer,
+        queued on the trainer's stream (a device copy when there is one rank)."""
+        with _torch().cuda.stream(self.stream):
+            if self.dist and self.world > 1:
+                self.dist.all_gather_into_tensor(self.d_all_pack, self.d_pack)
+            else:
+                self.d_all_pack.copy_(self.d_pack)
+
     def reduce_stats(self):
-        """Sum the statistics table over ranks (the path's only exchange step)."""
-        if self.dist and self.world > 1:
-            with _torch().cuda.stream(self.stream):
-                self.dist.all_reduce(self.d_stats, op=self.dist.ReduceOp.SUM)
+        """Exchange step of the device-resident pipeline (bench.py's `value`): winner record packed, buffers gathered."""
+        self._pack_best()
+        self.exchange()
 
     def warm_exchange(self):
         """Run the gather / copy part of step() once without applying anything (warm-up)."""
-        torch = _torch()
         self._pack_best()
-        with torch.cuda.stream(self.stream):
-            if self.dist and self.world > 1:
-                self.dist.all_gather_into_tensor(self.d_all_rec, self.d_rec)
-            else:
-                self.d_all_rec.copy_(self.d_rec)
-            self.h_stats.copy_(self.d_stats, non_blocking=True)
-            self.h_all_rec.copy_(self.d_all_rec, non_blocking=True)
+        self.exchange()
+        with _torch().cuda.stream(self.stream):
+            self.h_all_pack.copy_(self.d_all_pack, non_blocking=True)
         self.stream.synchronize()
 
     def step(self):
@@ -146,17 +179,12 @@ class BatchTrainer:
         self.launch_rollout()
         self.launch_stats()
         self._pack_best()
-        self.reduce_stats()
+        self.exchange()
         with torch.cuda.stream(self.stream):
-            if self.dist and self.world > 1:
-                self.dist.all_gather_into_tensor(self.d_all_rec, self.d_rec)
-            else:
-                self.d_all_rec.copy_(self.d_rec)
-            self.h_stats.copy_(self.d_stats, non_blocking=True)
-            self.h_all_rec.copy_(self.d_all_rec, non_blocking=True)
+            self.h_all_pack.copy_(self.d_all_pack, non_blocking=True)
         self.stream.synchronize()
         n_total = self.n_total
-        st = combine_and_apply(self.weights, self.h_stats.numpy(), self.h_all_rec.numpy(), n_total, self.next_episode)
+        st = sum_and_apply(self.weights, self.h_all_pack.numpy(), n_total, self.next_episode)
         self.next_episode += n_total
         self.last_stats = st
         return st

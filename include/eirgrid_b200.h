@@ -349,6 +349,25 @@ int eg_location_analysis(eg_ctx* ctx, int use_loaded_map, int32_t half_steps, do
 int eg_location_analysis_year(eg_ctx* ctx, int use_loaded_map, uint32_t year_index, int32_t half_steps, double step,
                               double* scores_out, uint32_t first_point, uint32_t n_points);
 
+/* BASELINE configs[4]: every candidate generator site x 15 types x simulated years in ONE pass. Sites are the points
+ * (i * step, j * step) for i, j in [0, sites_per_axis) (clamped to the 50 km map like Coordinate::new), site = i * sites_per_axis + j:
+ * the placement search's candidate grid is sites_per_axis = 51, step = 1000 (metal_location_search.rs:120-124 after the clamp). A
+ * site's geometry (water / near-water / coastal tests, distance to the nearest land — all point-in-polygon work) does not depend on
+ * the year and is evaluated once; years year_first .. year_first + n_years - 1 (0 = 2025) differ in the settlements' populations.
+ * scores[(site - first_site) * n_years * 15 + y * 15 + type]. The site range [first_site, first_site + n_sites) is what a rank of a
+ * sharded run takes; shards need no exchange. HOST output / DEVICE output (asynchronous on the ctx stream). */
+int eg_location_analysis_sites(eg_ctx* ctx, int use_loaded_map, uint32_t sites_per_axis, double step, uint32_t year_first,
+                               uint32_t n_years, uint32_t first_site, uint32_t n_sites, double* scores_out);
+int eg_location_analysis_sites_device(eg_ctx* ctx, int use_loaded_map, uint32_t sites_per_axis, double step, uint32_t year_first,
+                                      uint32_t n_years, uint32_t first_site, uint32_t n_sites, double* d_scores);
+/* Map::analyze_locations(min_suitability) followed by LocationAnalysis::save_cache(cache_dir) — <cache_dir>/location_analysis.json,
+ * the file load_location_analysis reads (map_handler.rs:243-248, core/multi_simulation.rs:149-154) — and save_to_file(text_path), the
+ * report of bin/analyze_locations.rs:19-46 (map_handler.rs:208-241). Either path may be NULL. The JSON is
+ * serde_json::to_string_pretty of LocationAnalysis (map_handler.rs:48-60): locations, type_counts, multi_type_locations,
+ * remaining_spaces, exhausted_types, type_to_locations; the HashMap-typed fields, unordered in the reference, are written in
+ * generator-type order. use_loaded_map = 0 is the empty map the reference's tool analyses (the shipped cache). */
+int eg_location_analysis_write(eg_ctx* ctx, int use_loaded_map, double min_suitability, const char* cache_dir, const char* text_path);
+
 /* ---- measurement aid (not on the path): double-precision multiply+add issue rate of `device` in TFLOP/s WITHOUT fused
  * multiply-add — the arithmetic ceiling of kernels compiled with --fmad=false like the episode kernel. */
 int eg_microbench_fp64(int device, double* tflops_out);

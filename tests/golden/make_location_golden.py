@@ -27,5 +27,10 @@ for k, e in enumerate(locs):
         scores[k, TYPES.index(name)] = v
 counts = np.array([d["type_counts"].get(t, 0) for t in TYPES])
 out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "location_analysis_scores.npz")
-np.savez_compressed(out, scores=scores, xy=xy, type_counts=counts)
+remaining = np.array([d["remaining_spaces"].get(t, 0) for t in TYPES])
+multi_xy = np.array([[c["x"], c["y"]] for c, _ in d["multi_type_locations"]])
+multi_n_types = np.array([len(ts) for _, ts in d["multi_type_locations"]])
+np.savez_compressed(out, scores=scores, xy=xy, type_counts=counts, remaining_spaces=remaining, multi_xy=multi_xy,
+                    multi_n_types=multi_n_types, n_exhausted=np.array(len(d["exhausted_types"])),
+                    top_level_keys=np.array(sorted(d.keys())))
 print("wrote", out, scores.shape, counts)

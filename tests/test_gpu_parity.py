@@ -5,6 +5,8 @@ the yearly metrics and final metrics bit-exact as well (the kernels reproduce th
 and are compiled without FMA contraction); only `score` goes through the device's log() and is compared with
 a 1e-12 relative tolerance (north_star tolerance: 1e-5).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -206,3 +208,58 @@ def test_batch_shape_edge_cases(gpu_ctx, oracle_world):
     assert_results_equal(rr, res[5:6])
     r_empty, s_empty, _ = gpu_ctx.replay(traj[:0])
     assert len(r_empty) == 0
+
+
+def test_location_analysis_files_match_the_shipped_cache(gpu_ctx, tmp_path):
+    """eg_location_analysis_write = analyze_locations + save_cache + save_to_file (map_handler.rs:61-142,208-248,
+    bin/analyze_locations.rs:19-46) on the empty map: the JSON must hold what the reference's shipped
+    cache/location_analysis.json holds (frozen in tests/golden/location_analysis_scores.npz by make_location_golden.py)."""
+    import json
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "location_analysis_scores.npz"))
+    cache = str(tmp_path / "cache")
+    txt = str(tmp_path / "location_analysis.txt")
+    gpu_ctx.location_analysis_write(0, min_suitability=0.2, cache_dir=cache, text_path=txt)
+    d = json.load(open(os.path.join(cache, "location_analysis.json")))
+    # the shipped file predates type_to_locations (serde default on load, map_handler.rs:57-59); every other key is there
+    assert sorted(k for k in d if k != "type_to_locations") == list(g["top_level_keys"])
+    types = _abi.GEN_TYPES
+    assert len(d["locations"]) == len(g["xy"]) == 2601
+    scores = np.full((2601, 15), np.nan)
+    for k, e in enumerate(d["locations"]):
+        assert (e["coordinate"]["x"], e["coordinate"]["y"]) == tuple(g["xy"][k])
+        for name, v in e["suitability_scores"].items():
+            scores[k, types.index(name)] = v
+    assert ((scores == g["scores"]) | (np.isnan(scores) & np.isnan(g["scores"]))).all()
+    assert [d["type_counts"].get(t, 0) for t in types] == g["type_counts"].tolist()
+    assert [d["remaining_spaces"].get(t, 0) for t in types] == g["remaining_spaces"].tolist()
+    assert d["exhausted_types"] == [] and int(g["n_exhausted"]) == 0
+    assert np.array_equal(np.array([[c["x"], c["y"]] for c, _ in d["multi_type_locations"]]), g["multi_xy"])
+    assert [len(ts) for _, ts in d["multi_type_locations"]] == g["multi_n_types"].tolist()
+    for t in types:  # type_to_locations: indices into `locations` of the entries that list the type
+        idx = d["type_to_locations"].get(t, [])
+        assert idx == [k for k in range(2601) if not np.isnan(scores[k, types.index(t)])]
+    # serde_json's number layout: floats keep a fraction, shortest round-trip digits
+    raw = open(os.path.join(cache, "location_analysis.json")).read()
+    assert '"x": 24000.0' in raw and "0.5599999999999999" in raw
+    report = open(txt).read().splitlines()
+    assert report[0] == "Location Analysis Results" and report[3] == "Total suitable locations: 2601" and report[4] == "Multi-type locations: 2601"
+    assert "Coordinate: (0, 24000)" in report and "  OffshoreWind: 0.560" in report
+
+
+def test_all_sites_all_years_in_one_pass(gpu_ctx):
+    """BASELINE configs[4]: every candidate site x 26 years x 15 types from one launch equals the per-year analysis of the same
+    points, and a run sharded by site (8 ranks' ranges) equals the unsharded one."""
+    side, step = 51, 1000.0
+    full = gpu_ctx.location_analysis_sites(True, side, step)
+    assert full.shape == (2601, 26, 15)
+    # the candidate grid (i, j in [0, 51) x 1 km) is the non-negative quadrant of analyze_map's grid at half = 50, step = 1000
+    for y in (0, 7, 25):
+        ref = gpu_ctx.location_analysis(True, half_steps=50, step=step, year_index=y).reshape(101, 101, 15)[50:, 50:].reshape(2601, 15)
+        assert np.array_equal(full[:, y], ref), y
+    assert (full[:, 0] != full[:, 25]).any(), "population growth must move at least one decision by 2050"
+    parts = [gpu_ctx.location_analysis_sites(True, side, step, first_site=r * 2601 // 8, n_sites=(r + 1) * 2601 // 8 - r * 2601 // 8) for r in range(8)]
+    assert np.array_equal(np.concatenate(parts), full)
+    sub = gpu_ctx.location_analysis_sites(True, side, step, year_first=3, n_years=5)
+    assert np.array_equal(sub, full[:, 3:8])
+    empty = gpu_ctx.location_analysis_sites(False, side, step, n_years=2)
+    assert np.array_equal(empty[:, 0], empty[:, 1])  # no settlements: nothing depends on the year
