@@ -321,12 +321,14 @@ def run_suitability(args, emit):
                     "what": "eg_location_analysis_sites with a HOST output buffer: kernel + device-to-host copy of this rank's scores inside the call"},
             "gpu_launches": int(launches), "clocks": clock_summary,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "kernel": "eg_suitability_kernel<STAGED=true>", "algorithmic_bytes_per_launch": algo_bytes,
+                         "peak_source": peak_src, "kernel": "eg_suitability_kernel (+ eg_suit_rows_kernel, the crossing lists)", "algorithmic_bytes_per_launch": algo_bytes,
                          "edge_tests": {"per_launch": edge_tests, "g_per_s": edge_tests / (kernel_ms / 1e3) / 1e9,
-                                        "what": "point-in-polygon edge tests (const_funcs.rs:143-158): 19 probes per site + 441 per site on water, "
-                                                "each against every coastline edge; what the kernel's time goes to"},
-                         "note": "the scores written (3.1 KB per site) are the only HBM traffic that scales; the kernel is bound by the FP64 compare / "
-                                 "issue rate of the edge tests, see roofline.edge_tests and profiles/"}}
+                                        "what": "ALGORITHMIC point-in-polygon edge tests (const_funcs.rs:143-158): 19 probes per site + 441 per site on "
+                                                "water, each against every coastline edge, as the reference performs them; the kernel answers a probe by "
+                                                "binary search in the sorted crossing list of its row instead (same result, ~7 comparisons)"},
+                         "note": "the scores written (3.1 KB per site) are the only HBM traffic that scales; after the crossing-list restructuring the "
+                                 "kernel's time is the per-site settlement / plant distance loops, the reductions over years and the score stores "
+                                 "(profiles/r02_suitability.md)"}}
     if world == 1 and not args.no_cpu_baseline:
         rate, sample = cpu_suitability_rate(args.cpu_seconds)
         line["cpu_baseline"] = {"value": rate, "unit": SUIT_UNIT, "cores": 1, "kind": "port", "sample": sample}

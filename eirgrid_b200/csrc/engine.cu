@@ -61,6 +61,8 @@ struct eg_ctx {
   int* d_r2_limit = nullptr;
   double *d_sx = nullptr, *d_sy = nullptr, *d_ex = nullptr, *d_ey = nullptr, *d_cx = nullptr, *d_cy = nullptr;
   uint32_t* d_pop = nullptr;
+  double* d_suit_rows = nullptr;       // scratch of the suitability kernel: crossing lists per site row
+  size_t suit_rows_cap = 0;
   double* d_urban_r = nullptr;         // [26][S] sqrt(pop) * 5 (is_urban_area, map_handler.rs:1199-1209)
   double urban_r_max = 0.0;
   EgPolicyDevice* d_policy = nullptr;
@@ -291,6 +293,7 @@ void eg_destroy(eg_ctx* c) {
   if (c->h_upd_state) cudaFreeHost(c->h_upd_state);
   if (c->h_upd_slot) cudaFreeHost(c->h_upd_slot);
   if (c->h_upd_imp) cudaFreeHost(c->h_upd_imp);
+  if (c->d_suit_rows) cudaFree(c->d_suit_rows);
   void* upd_ptrs[] = {c->upd.state, c->upd.slots, c->upd.score, c->upd.pre, c->upd.ctl, c->upd.counts, c->upd.factors, c->upd.improvements};
   for (void* p : upd_ptrs)
     if (p) cudaFree(p);
@@ -910,6 +913,17 @@ EgSuitabilityParams suitability_params(const eg_ctx* c, int use_loaded_map, int 
   return p;
 }
 
+int ensure_suit_rows(eg_ctx* c, const EgSuitabilityParams& p) {
+  const size_t need = eg_suitability_rows_bytes(p.mode == 0 ? 2 * p.half + 1 : p.side);
+  if (need > c->suit_rows_cap) {
+    if (c->d_suit_rows) cudaFree(c->d_suit_rows);
+    c->d_suit_rows = nullptr; c->suit_rows_cap = 0;
+    EG_CUDA(cudaMalloc((void**)&c->d_suit_rows, need));
+    c->suit_rows_cap = need;
+  }
+  return EG_OK;
+}
+
 // runs the kernel into a temporary device buffer and copies the scores to the host
 int suitability_to_host(eg_ctx* c, const EgSuitabilityParams& p0, double* scores_out) {
   EG_CUDA(cudaSetDevice(c->device));
@@ -918,8 +932,10 @@ int suitability_to_host(eg_ctx* c, const EgSuitabilityParams& p0, double* scores
   double* d_scores = nullptr;
   EG_CUDA(cudaMalloc((void**)&d_scores, std::max<size_t>(count, 1) * sizeof(double)));
   p.scores = d_scores;
-  cudaError_t err = eg_launch_suitability(p, c->stream);
-  if (err == cudaSuccess && count) c->launches++;
+  cudaError_t err = cudaSuccess;
+  if (ensure_suit_rows(c, p) != EG_OK) err = cudaErrorMemoryAllocation;
+  if (err == cudaSuccess) err = eg_launch_suitability(p, c->d_suit_rows, c->stream);
+  if (err == cudaSuccess && count) c->launches += 2;
   if (err == cudaSuccess) err = cudaMemcpyAsync(scores_out, d_scores, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
   if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
   cudaFree(d_scores);
@@ -954,8 +970,10 @@ int eg_location_analysis_sites_device(eg_ctx* c, int use_loaded_map, uint32_t si
   if ((uint64_t)first_site + n_sites > (uint64_t)sites_per_axis * sites_per_axis) return eg_fail(EG_ERR_INVALID, "site range exceeds the grid");
   EG_CUDA(cudaSetDevice(c->device));
   const EgSuitabilityParams p = suitability_params(c, use_loaded_map, 1, 0, (int)sites_per_axis, step, year_first, n_years, first_site, n_sites, d_scores);
-  EG_CUDA(eg_launch_suitability(p, c->stream));
-  if (n_sites && n_years) c->launches++;
+  int rc = ensure_suit_rows(c, p);
+  if (rc) return rc;
+  EG_CUDA(eg_launch_suitability(p, c->d_suit_rows, c->stream));
+  if (n_sites && n_years) c->launches += 2;
   return EG_OK;
 }
 

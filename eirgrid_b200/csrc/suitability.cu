@@ -6,11 +6,12 @@
 // and is_point_inside_polygon (config/const_funcs.rs:143-158). It is the CUDA counterpart of the never-dispatched
 // Metal kernel computeSuitability (aiSimulator/assets/metal_location_search.metal:239-258).
 //
-// One warp per point, persistent blocks. What dominates is the point-in-polygon test: 1 + 9 + 9 probes per point and, for a
-// point on water, the 21 x 21 probes of the nearest-land scan, each against every edge of the coastline polygon. The polygon
-// (and the settlement coordinates) are therefore staged ONCE per block into shared memory with bulk asynchronous copies
-// (cp.async.bulk + mbarrier) and every probe of every point the block handles reads them there; the probes of a point are
-// dealt out to the lanes, so a polygon edge is one broadcast read per warp.
+// One warp per point. What dominates in the reference is the point-in-polygon test: 1 + 9 + 9 probes per point and, for a
+// point on water, the 21 x 21 probes of the nearest-land scan, each against every edge of the coastline polygon. Here the
+// edges a horizontal probe line crosses are found once per (row of sites, probe row) — "crossing lists" below — and a block
+// handles sites of ONE row: it stages that row's 25 lists, the settlement coordinates and (for the rare overlong list) the
+// polygon into shared memory with bulk asynchronous copies (cp.async.bulk + mbarrier); the probes of a point are dealt out
+// to the lanes and each compares its x with a handful of abscissae.
 // The geometry of a point does not depend on the year; only the settlements' populations do (urban test, nearby-population
 // rule). One pass therefore serves all requested years: lane y evaluates the 15 type rules of year y.
 // Compiled with --fmad=false: every score is the reference's IEEE arithmetic.
@@ -40,16 +41,6 @@ __device__ __forceinline__ bool inside_polygon(double px, double py, const Poly&
 }
 __device__ __forceinline__ bool water_tile(double px, double py, const Poly& poly) { return !inside_polygon(px, py, poly); }
 
-// any of the 9 probes (x, y in {-d, 0, +d}, each clamped by Coordinate::new) lies on water; lanes 0..8 take one probe each
-__device__ __forceinline__ bool any9_water(double px, double py, double d, const Poly& poly, int lane) {
-  bool w = false;
-  if (lane < 9) {
-    const int ix = lane / 3 - 1, iy = lane % 3 - 1;
-    w = water_tile(clamp_map(px + ((double)ix * d)), clamp_map(py + ((double)iy * d)), poly);
-  }
-  return __any_sync(0xFFFFFFFFu, w);
-}
-
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // bulk copy global -> shared, completion counted on the mbarrier (sizes are multiples of 16 bytes)
@@ -59,58 +50,141 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-template <bool STAGED>
-__global__ void __launch_bounds__(128) eg_suitability_kernel(const EgSuitabilityParams p) {
+// ---- crossing lists ---------------------------------------------------------------------------------------------------
+// is_point_inside_polygon toggles on every edge i with (yi > y) != (yj > y) whose intersection abscissa
+// X_i(y) = (xj - xi) * (y - yi) / (yj - yi) + xi lies to the right of the probe. Both the set of such edges and the values
+// X_i(y) depend on the probe's y alone, and the probes of a row of sites use only 25 different y: the site's own, +-5 km
+// and +-8 km (clamped), and the 21 rows of the nearest-land scan. They are evaluated ONCE per (site row, probe row) by
+// eg_suit_rows_kernel — the same expression, so the same bits, as inside the reference's loop — sorted, and a probe then
+// finds by binary search how many of them lie to its right instead of testing every edge: the parity of that count is the
+// reference's result.
+constexpr int kSlots = 25;                 // probe rows per site row
+constexpr int kListStride = 129;           // doubles per list: [count | up to 128 abscissae, ascending]; odd, so lanes on different lists hit different banks
+constexpr int kMaxCrossings = 128;         // (the shipped coastline is 200 unordered points: a horizontal line crosses it ~50 times, at most 96)
+constexpr int kRowDoubles = kSlots * kListStride + 1;   // 3226 doubles = 25,808 bytes, a multiple of 16 (bulk copy)
+static_assert((kRowDoubles * 8) % 16 == 0, "a site row's lists are staged by one bulk copy");
+constexpr int kSitesPerBlock = 64;
+
+// y of probe row `slot` for a site row at py, and whether the nearest-land scan may use it (it skips rows outside the map)
+__device__ __forceinline__ double slot_y(double py, int slot, bool* in_map) {
+  if (slot < 21) {
+    const double y = py + ((double)(slot - 10) * 1000.0);
+    *in_map = y >= 0.0 && y <= 50000.0;
+    return clamp_map(y);
+  }
+  *in_map = true;
+  const double d = slot < 23 ? 5000.0 : 8000.0;
+  return clamp_map(py + ((slot & 1) ? -1.0 : 1.0) * d);   // slots 21 / 23: -d, slots 22 / 24: +d
+}
+
+__device__ __forceinline__ double site_coord(const EgSuitabilityParams& p, int index) {
+  return clamp_map((double)(index - (p.mode == 0 ? p.half : 0)) * p.step);
+}
+
+__global__ void __launch_bounds__(128) eg_suit_rows_kernel(const EgSuitabilityParams p, int side, double* rows) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= side * kSlots) return;
+  const int j = t / kSlots, slot = t - j * kSlots;
+  bool in_map;
+  const double y = slot_y(site_coord(p, j), slot, &in_map);
+  double* list = rows + (size_t)j * kRowDoubles + slot * kListStride;
+  int c = 0;
+  if (p.n_coast > 0) {
+    double xj = p.cx[p.n_coast - 1], yj = p.cy[p.n_coast - 1];
+    for (int i = 0; i < p.n_coast; i++) {
+      const double xi = p.cx[i], yi = p.cy[i];
+      if ((yi > y) != (yj > y)) {
+        if (c < kMaxCrossings) {  // insertion into the ascending list
+          const double x = (xj - xi) * (y - yi) / (yj - yi) + xi;
+          int t = c;
+          while (t > 0 && list[t] > x) { list[1 + t] = list[t]; t--; }
+          list[1 + t] = x;
+        }
+        c++;
+      }
+      xj = xi; yj = yi;
+    }
+  }
+  list[0] = c <= kMaxCrossings ? (double)c : -1.0;   // -1: more crossings than a list holds, probes of this row test every edge
+  if (slot == 0) rows[(size_t)j * kRowDoubles + kSlots * kListStride] = 0.0;  // the pad element
+}
+
+// water test of one probe from its row's crossing list (inside = odd number of crossings to the right)
+__device__ __forceinline__ bool water_from_list(const double* lists, int slot, double x, double y, const Poly& poly) {
+  const double* list = lists + slot * kListStride;
+  const int c = (int)list[0];
+  if (c < 0) return water_tile(x, y, poly);
+  // crossings to the right of the probe: the entries with x < X; the list is ascending
+  int lo = 0, hi = c;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (x < list[1 + mid]) hi = mid;
+    else lo = mid + 1;
+  }
+  return ((c - lo) & 1) == 0;   // inside = odd count; water = not inside
+}
+
+// One block = one row of sites (same y) x up to 64 consecutive site rows in x; one warp per site.
+__global__ void __launch_bounds__(128) eg_suitability_kernel(const EgSuitabilityParams p, const double* rows, int side, int i_lo, int i_hi) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bar;
-  const int lane = threadIdx.x & 31;
-  Poly poly{p.cx, p.cy, p.n_coast};
-  const double* sx = p.sx;
-  const double* sy = p.sy;
-  if (STAGED) {
-    // layout: coast x | coast y | settlement x | settlement y, each padded to a multiple of 16 bytes (the device arrays are too)
-    const uint32_t cb = (uint32_t)((p.n_coast * 8 + 15) & ~15), sb = (uint32_t)((p.n_settlements * 8 + 15) & ~15);
-    double* s_cx = (double*)smem_raw;
-    double* s_cy = (double*)(smem_raw + cb);
-    double* s_sx = (double*)(smem_raw + 2 * cb);
-    double* s_sy = (double*)(smem_raw + 2 * cb + sb);
-    const uint32_t b = smem_addr(&bar);
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(2 * cb + 2 * sb) : "memory");
-      if (cb) { bulk_g2s(s_cx, p.cx, cb, b); bulk_g2s(s_cy, p.cy, cb, b); }
-      if (sb) { bulk_g2s(s_sx, p.sx, sb, b); bulk_g2s(s_sy, p.sy, sb, b); }
-    }
-    __syncthreads();
-    uint32_t done = 0;
-    while (!done)
-      asm volatile("{\n .reg .pred q;\n mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n selp.u32 %0, 1, 0, q;\n}" : "=r"(done) : "r"(b) : "memory");
-    poly.x = s_cx; poly.y = s_cy;
-    sx = s_sx; sy = s_sy;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x % side, chunk = blockIdx.x / side;
+  // staged per block: this site row's 25 crossing lists | coast x | coast y | settlement x | settlement y
+  const uint32_t lb = kRowDoubles * 8, cb = (uint32_t)((p.n_coast * 8 + 15) & ~15), sb = (uint32_t)((p.n_settlements * 8 + 15) & ~15);
+  double* s_lists = (double*)smem_raw;
+  double* s_cx = (double*)(smem_raw + lb);
+  double* s_cy = (double*)(smem_raw + lb + cb);
+  double* s_sx = (double*)(smem_raw + lb + 2 * cb);
+  double* s_sy = (double*)(smem_raw + lb + 2 * cb + sb);
+  const uint32_t b = smem_addr(&bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(lb + 2 * cb + 2 * sb) : "memory");
+    bulk_g2s(s_lists, rows + (size_t)j * kRowDoubles, lb, b);
+    if (cb) { bulk_g2s(s_cx, p.cx, cb, b); bulk_g2s(s_cy, p.cy, cb, b); }
+    if (sb) { bulk_g2s(s_sx, p.sx, sb, b); bulk_g2s(s_sy, p.sy, sb, b); }
   }
-  const int side = p.mode == 0 ? 2 * p.half + 1 : p.side;
-  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
-  for (uint32_t k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < p.n; k += warps) {
-    const uint32_t pt = p.first + k;
-    // analyze_map: i, j in [-half, half] (negative coordinates clamp to 0); candidate-site grid: i, j in [0, side)
-    const int i = (int)(pt / side) - (p.mode == 0 ? p.half : 0), j = (int)(pt % side) - (p.mode == 0 ? p.half : 0);
-    const double px = clamp_map((double)i * p.step), py = clamp_map((double)j * p.step);
+  __syncthreads();
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n .reg .pred q;\n mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n selp.u32 %0, 1, 0, q;\n}" : "=r"(done) : "r"(b) : "memory");
+  const Poly poly{s_cx, s_cy, p.n_coast};
+  const double* sx = s_sx;
+  const double* sy = s_sy;
+  const double py = site_coord(p, j);
+  for (int i = i_lo + chunk * kSitesPerBlock + warp; i <= i_hi && i < i_lo + (chunk + 1) * kSitesPerBlock; i += 4) {
+    const long long pt = (long long)i * side + j;
+    if (pt < (long long)p.first || pt >= (long long)p.first + p.n) continue;
+    const uint32_t k = (uint32_t)(pt - p.first);
+    const double px = site_coord(p, i);
 
-    const bool water = water_tile(px, py, poly);
-    const bool near_water = any9_water(px, py, 5000.0, poly, lane);   // is_near_water, :1211-1226
-    const bool coastal = any9_water(px, py, 8000.0, poly, lane);      // is_coastal_region, :1178-1193
+    const bool water = water_from_list(s_lists, 10, px, py, poly);
+    // is_near_water (:1211-1226) / is_coastal_region (:1178-1193): any of the 9 probes (x, y in {-d, 0, +d}, each clamped by
+    // Coordinate::new) on water; lanes 0..8 take the 5 km probes, lanes 9..17 the 8 km probes
+    bool w9 = false;
+    if (lane < 18) {
+      const int q = lane < 9 ? lane : lane - 9;
+      const double d = lane < 9 ? 5000.0 : 8000.0;
+      const int ix = q / 3 - 1, iy = q % 3 - 1;
+      const double x = clamp_map(px + ((double)ix * d)), y = clamp_map(py + ((double)iy * d));
+      const int slot = iy == 0 ? 10 : (lane < 9 ? (iy < 0 ? 21 : 22) : (iy < 0 ? 23 : 24));
+      w9 = water_from_list(s_lists, slot, x, y, poly);
+    }
+    const unsigned w9_mask = __ballot_sync(0xFFFFFFFFu, w9);
+    const bool near_water = (w9_mask & 0x1FFu) != 0, coastal = (w9_mask & 0x3FE00u) != 0;
 
     // get_distance_to_nearest_land (:1398-1421): 21 x 21 probes at 1 km, lanes stride over them
     double min_distance = 1.7976931348623157e308;
     if (water) {
       for (int q = lane; q < 441; q += 32) {
-        const int a = q / 21 - 10, b = q % 21 - 10;
-        const double x = px + ((double)a * 1000.0), y = py + ((double)b * 1000.0);
+        const int a = q / 21 - 10, bb = q % 21 - 10;
+        const double x = px + ((double)a * 1000.0), y = py + ((double)bb * 1000.0);
         if (x >= 0.0 && x <= 50000.0 && y >= 0.0 && y <= 50000.0) {
           const double tx = clamp_map(x), ty = clamp_map(y);
-          if (!water_tile(tx, ty, poly)) {
+          if (!water_from_list(s_lists, bb + 10, tx, ty, poly)) {
             const double dx = px - tx, dy = py - ty;
             min_distance = fmin(min_distance, sqrt(dx * dx + dy * dy));
           }
@@ -204,26 +278,24 @@ __global__ void __launch_bounds__(128) eg_suitability_kernel(const EgSuitability
 
 }  // namespace
 
-cudaError_t eg_launch_suitability(const EgSuitabilityParams& p, cudaStream_t stream) {
+size_t eg_suitability_rows_bytes(int side) { return (size_t)side * kRowDoubles * sizeof(double); }
+
+cudaError_t eg_launch_suitability(const EgSuitabilityParams& p, double* d_rows, cudaStream_t stream) {
   if (p.n == 0 || p.n_years == 0) return cudaSuccess;
   if (p.n_years > EG_SUIT_MAX_YEARS) return cudaErrorInvalidValue;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const uint32_t warps_needed = p.n;
-  // persistent blocks of 4 warps, 8 blocks per SM at most; fewer when there are fewer points than warps
-  const uint32_t blocks = (uint32_t)std::min<uint64_t>((uint64_t)sms * 8, ((uint64_t)warps_needed + 3) / 4);
-  const size_t staged_bytes = 2 * (size_t)((p.n_coast * 8 + 15) & ~15) + 2 * (size_t)((p.n_settlements * 8 + 15) & ~15);
-  if (staged_bytes <= 96 * 1024) {
-    static bool opted = false;
-    if (!opted) {
-      cudaError_t e = cudaFuncSetAttribute(eg_suitability_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      if (e != cudaSuccess) return e;
-      opted = true;
-    }
-    eg_suitability_kernel<true><<<blocks, 128, staged_bytes, stream>>>(p);
-  } else {
-    eg_suitability_kernel<false><<<blocks, 128, 0, stream>>>(p);  // a coastline too long for shared memory is read through L1
+  const int side = p.mode == 0 ? 2 * p.half + 1 : p.side;
+  const size_t staged_bytes = (size_t)kRowDoubles * 8 + 2 * (size_t)((p.n_coast * 8 + 15) & ~15) + 2 * (size_t)((p.n_settlements * 8 + 15) & ~15);
+  if (staged_bytes > 200 * 1024) return cudaErrorInvalidValue;  // (a coastline of 10,000 points: not a map this path is for)
+  eg_suit_rows_kernel<<<(side * kSlots + 127) / 128, 128, 0, stream>>>(p, side, d_rows);
+  static bool opted = false;
+  if (!opted) {
+    cudaError_t e = cudaFuncSetAttribute(eg_suitability_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    opted = true;
   }
+  // site = i * side + j: the rows of sites i_lo..i_hi intersect the requested range
+  const int i_lo = (int)(p.first / (uint32_t)side), i_hi = (int)(((uint64_t)p.first + p.n - 1) / (uint32_t)side);
+  const int chunks = (i_hi - i_lo + kSitesPerBlock) / kSitesPerBlock;
+  eg_suitability_kernel<<<(uint32_t)side * (uint32_t)chunks, 128, staged_bytes, stream>>>(p, d_rows, side, i_lo, i_hi);
   return cudaGetLastError();
 }

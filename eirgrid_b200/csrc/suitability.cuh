@@ -27,4 +27,7 @@ struct EgSuitabilityParams {
   double* scores;      // [n][n_years][15]
 };
 
-cudaError_t eg_launch_suitability(const EgSuitabilityParams& p, cudaStream_t stream);
+// bytes of the per-site-row crossing lists the launch needs as scratch (`side` = points per axis of the grid)
+size_t eg_suitability_rows_bytes(int side);
+// 2 launches: the crossing lists of every site row, then the analysis itself
+cudaError_t eg_launch_suitability(const EgSuitabilityParams& p, double* d_rows, cudaStream_t stream);

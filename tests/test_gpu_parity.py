@@ -263,3 +263,35 @@ def test_all_sites_all_years_in_one_pass(gpu_ctx):
     assert np.array_equal(sub, full[:, 3:8])
     empty = gpu_ctx.location_analysis_sites(False, side, step, n_years=2)
     assert np.array_equal(empty[:, 0], empty[:, 1])  # no settlements: nothing depends on the year
+
+
+def test_location_analysis_on_a_comb_coastline(oracle_world):
+    """a coastline whose horizontal lines cross it up to 140 times: rows with more crossings than a crossing list holds (128)
+    fall back to testing every edge; rows below the teeth use their lists. Both must equal the oracle's edge-by-edge test."""
+    teeth = 70
+    xs, ys = [1000.0], [1000.0]
+    for k in range(teeth):  # a comb: teeth from y = 20 km up to y = 45 km, 1 km pitch
+        x0 = 2000.0 + k * 650.0
+        xs += [x0, x0, x0 + 300.0, x0 + 300.0]
+        ys += [20000.0, 45000.0, 45000.0, 20000.0]
+    xs += [49000.0, 49000.0]
+    ys += [20000.0, 1000.0]
+    sx, sy, spop, ex, ey, et, ec, _, _ = _ireland_arrays()
+    ctx = _lib.Context(0)
+    ctx.map_set(sx, sy, spop, ex, ey, et, ec, np.array(xs), np.array(ys), 51, 1000.0)
+    world = O.World.from_arrays(sx, sy, spop, ex, ey, et, ec, np.array(xs), np.array(ys), 51, 1000.0, fast=False)
+    for loaded in (0, 1):
+        got = ctx.location_analysis(loaded)
+        assert np.array_equal(got, world.location_analysis(loaded)), loaded
+    # every kind of point occurs: land, water near land, open water
+    marine = ctx.location_analysis(0)[:, 1]
+    assert (marine == 0.0).any() and (marine == 0.8 * 0.3).any() and (marine == 0.8 * 0.7).any()
+    sites = ctx.location_analysis_sites(True, 51, 1000.0, n_years=3)
+    ref = ctx.location_analysis(True, half_steps=50, step=1000.0, year_index=2).reshape(101, 101, 15)[50:, 50:].reshape(2601, 15)
+    assert np.array_equal(sites[:, 2], ref)
+    ctx.close()
+
+
+def _ireland_arrays():
+    from eirgrid_b200 import synthetic
+    return synthetic.load_ireland_arrays(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ireland_map"))
