@@ -187,6 +187,15 @@ __global__ void __launch_bounds__(128) upd_ctl_kernel(uint32_t n, EgUpdBuffers b
       c.flags |= EG_UPD_D_APPLIED | (d.randomise ? EG_UPD_D_RANDOMISE : 0u);
       c.d_boost = d.boost; c.d_penalty = d.penalty;
     }
+    auto saturates = [](double boost) { return boost >= 1.0 && egrule::kMinWeight * boost >= egrule::kMaxWeight; };
+    auto kills = [](double p) { return p != p || egrule::kMaxWeight * p <= egrule::kMinWeight; };
+    if (saturates(c.boost)) c.flags |= EG_UPD_BOOST_SAT;
+    if (kills(c.penalty)) c.flags |= EG_UPD_PEN_KILL;
+    if (kills(c.mild)) c.flags |= EG_UPD_MILD_KILL;
+    if (saturates(c.d_boost)) c.flags |= EG_UPD_D_BOOST_SAT;
+    if (kills(c.d_penalty)) c.flags |= EG_UPD_D_PEN_KILL;
+    if (c.boost >= 1.0 && !(c.penalty > 1.0) && !(c.mild > 1.0)) c.flags |= EG_UPD_PROPER;
+    if (c.d_boost >= 1.0 && !(c.d_penalty > 1.0)) c.flags |= EG_UPD_D_PROPER;
     b.ctl[e] = c;
     if (c.flags & (EG_UPD_RANDOMISE | EG_UPD_D_RANDOMISE)) b.state->pass_any_random = 1u;  // same value from every writer
   }
@@ -468,6 +477,10 @@ __device__ __forceinline__ void walk_tile(const EgUpdCtl* ctl, const unsigned ch
     const uint32_t random = __ballot_sync(0xFFFFFFFFu, (fl & kRandom) != 0);
     const uint32_t improved = __ballot_sync(0xFFFFFFFFu, (fl & EG_UPD_IMPROVED) != 0);
     if (!(applied | random | improved)) continue;
+    const uint32_t boost_sat = __ballot_sync(0xFFFFFFFFu, (fl & (DEFICIT ? EG_UPD_D_BOOST_SAT : EG_UPD_BOOST_SAT)) != 0);
+    const uint32_t pen_kill = __ballot_sync(0xFFFFFFFFu, (fl & (DEFICIT ? EG_UPD_D_PEN_KILL : EG_UPD_PEN_KILL)) != 0);
+    const uint32_t mild_kill = __ballot_sync(0xFFFFFFFFu, (fl & (DEFICIT ? EG_UPD_D_PEN_KILL : EG_UPD_MILD_KILL)) != 0);
+    const uint32_t proper = __ballot_sync(0xFFFFFFFFu, (fl & (DEFICIT ? EG_UPD_D_PROPER : EG_UPD_PROPER)) != 0);
 #pragma unroll 1
     for (uint32_t g = 0; g < 32; g += kGroup) {
       const uint32_t ga = (applied >> g) & 0xFFu, gr = (random >> g) & 0xFFu, gi = (improved >> g) & 0xFFu;
@@ -484,28 +497,60 @@ __device__ __forceinline__ void walk_tile(const EgUpdCtl* ctl, const unsigned ch
         mild[u] = DEFICIT ? 1.0 : ctl[j0 + u].mild;
       }
       if (!gi) {
-        // No best-strategy change inside the group (all but a handful of groups): every step is computed and then kept or
-        // dropped by a select, so the only thing a step waits for is the entry's value. Repeated multiplications beyond
-        // the first (an action the strategy holds twice, an action sampled twice) branch out only while they still change
-        // the value: MAX_WEIGHT / MIN_WEIGHT are fixed points of the boost / penalty step.
+        // No best-strategy change inside the group (all but a handful of groups). Which steps apply to this entry is settled
+        // before the multiplications start, as bit masks over the group's eight episodes: boost where the episode's contrast
+        // applied and the best strategy holds the entry, penalty where it applied and the count is non-zero, "more than once"
+        // where a second multiplication may follow. Every step is then computed and kept or dropped by ONE select on a mask
+        // bit, so the only thing a step waits for is the entry's value; the repeat handling is compiled into a second copy of
+        // the loop that a warp enters only if one of its lanes has a repeat in this group.
         const bool in_best = occ != 0;
+        uint32_t pen_mask = 0u, rep_pen = 0u;
+        double pf[kGroup];
 #pragma unroll
         for (int u = 0; u < kGroup; u++) {
-          const bool app = (ga >> u) & 1u;
-          const double wb = egrule::min_std(w * boost[u], egrule::kMaxWeight);
-          w = (app && in_best) ? wb : w;
-          if (app && occ > 1 && !(w == egrule::kMaxWeight && boost[u] >= 1.0)) w = walk_boost(w, boost[u], occ - 1);
-          int mm = m[u];
-          if (app && mm == 255) mm = walk_recount<DEFICIT>(trajs + first + j0 + u, y, key, rp, cur);  // more than the byte holds
-          const double p = (!DEFICIT && in_best) ? mild[u] : pen[u];
-          const double t = w * p;
-          const double wp = (t >= egrule::kMinWeight) ? t : egrule::kMinWeight;  // f64::max(t, MIN_WEIGHT), NaN -> MIN_WEIGHT (quirk Q9)
-          w = (app && mm != 0) ? wp : w;
-          if (app && mm > 1 && !(w == egrule::kMinWeight && !(p > 1.0))) w = walk_penalty(w, p, mm - 1);
-          if ((gr >> u) & 1u) {  // std::min(std::max(t, MIN_WEIGHT), MAX_WEIGHT) with both comparisons on t itself
+          pen_mask |= (uint32_t)(m[u] != 0) << u;
+          rep_pen |= (uint32_t)(m[u] > 1) << u;
+          pf[u] = (!DEFICIT && in_best) ? mild[u] : pen[u];
+        }
+        const uint32_t boost_mask = in_best ? ga : 0u;
+        pen_mask &= ga;
+        // a repeat can only matter when the first multiplication does not already end at the fixed point; that it does is
+        // known per episode (ctl flags) for every entry inside the clamp range
+        // (inside the range now, and every factor applied in this group keeps it there)
+        const bool in_range = w >= egrule::kMinWeight && w <= egrule::kMaxWeight && (ga & ~((proper >> g) & 0xFFu)) == 0u;
+        const uint32_t gs = (boost_sat >> g) & 0xFFu, gk = (((!DEFICIT && in_best) ? mild_kill : pen_kill) >> g) & 0xFFu;
+        rep_pen &= in_range ? (ga & ~gk) : ga;
+        const uint32_t rep_boost = occ > 1 ? (in_range ? (ga & ~gs) : ga) : 0u;
+        if (!__any_sync(0xFFFFFFFFu, (rep_boost | rep_pen) != 0u)) {
+#pragma unroll
+          for (int u = 0; u < kGroup; u++) {
+            const double tb = w * boost[u];
+            const double wb = (egrule::kMaxWeight < tb) ? egrule::kMaxWeight : tb;     // std::min(t, MAX_WEIGHT)
+            w = ((boost_mask >> u) & 1u) ? wb : w;
+            const double tp = w * pf[u];
+            const double wp = (tp >= egrule::kMinWeight) ? tp : egrule::kMinWeight;     // f64::max(t, MIN_WEIGHT), NaN -> MIN_WEIGHT (quirk Q9)
+            w = ((pen_mask >> u) & 1u) ? wp : w;
+            const double tr = w * f[u];   // std::min(std::max(t, MIN_WEIGHT), MAX_WEIGHT) with both comparisons on t itself
+            const double wr = (tr < egrule::kMinWeight) ? egrule::kMinWeight : ((egrule::kMaxWeight < tr) ? egrule::kMaxWeight : tr);
+            w = ((gr >> u) & 1u) ? wr : w;
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < kGroup; u++) {
+            const double tb = w * boost[u];
+            const double wb = (egrule::kMaxWeight < tb) ? egrule::kMaxWeight : tb;
+            w = ((boost_mask >> u) & 1u) ? wb : w;
+            // further occurrences in the best strategy: only while they still change the value (MAX_WEIGHT is a fixed point)
+            if (((rep_boost >> u) & 1u) && !(w == egrule::kMaxWeight && boost[u] >= 1.0)) w = walk_boost(w, boost[u], occ - 1);
+            int mm = m[u];
+            if (((rep_pen >> u) & 1u) && mm == 255) mm = walk_recount<DEFICIT>(trajs + first + j0 + u, y, key, rp, cur);  // more than the byte holds
+            const double tp = w * pf[u];
+            const double wp = (tp >= egrule::kMinWeight) ? tp : egrule::kMinWeight;
+            w = ((pen_mask >> u) & 1u) ? wp : w;
+            if (((rep_pen >> u) & 1u) && !(w == egrule::kMinWeight && !(pf[u] > 1.0))) w = walk_penalty(w, pf[u], mm - 1);
             const double tr = w * f[u];
-            const bool below = tr < egrule::kMinWeight, above = egrule::kMaxWeight < tr;
-            w = below ? egrule::kMinWeight : (above ? egrule::kMaxWeight : tr);
+            const double wr = (tr < egrule::kMinWeight) ? egrule::kMinWeight : ((egrule::kMaxWeight < tr) ? egrule::kMaxWeight : tr);
+            w = ((gr >> u) & 1u) ? wr : w;
           }
         }
         continue;

@@ -64,6 +64,16 @@ struct EgUpdCtl {           // per episode, what the table walk needs; 64 bytes
 #define EG_UPD_D_APPLIED 4u
 #define EG_UPD_D_RANDOMISE 8u
 #define EG_UPD_IMPROVED 16u
+// facts about the episode's factors that let the walk skip its repeat handling (valid for entries inside [MIN_WEIGHT, MAX_WEIGHT]):
+// the first boost already saturates (MIN_WEIGHT * boost >= MAX_WEIGHT, boost >= 1), the first penalty already hits the floor
+// (MAX_WEIGHT * p <= MIN_WEIGHT, or p is NaN: quirk Q9)
+#define EG_UPD_BOOST_SAT 32u
+#define EG_UPD_PEN_KILL 64u
+#define EG_UPD_MILD_KILL 128u
+#define EG_UPD_D_BOOST_SAT 256u
+#define EG_UPD_D_PEN_KILL 512u
+#define EG_UPD_PROPER 1024u     // boost >= 1 and no penalty factor above 1: the episode's steps keep an entry inside the clamp range
+#define EG_UPD_D_PROPER 2048u
 
 struct EgUpdBuffers {       // device scratch of one context, sized for EG_UPD_CHUNK episodes
   EgUpdState* state;

@@ -1,6 +1,8 @@
 """Randomised parity (GPU vs oracle): weight tables, run options and recorded trajectories the training path rarely or never
 produces — saturated/random weights, every stagnation regime, cost-only scoring, energy sales off, the heuristic count
 sampler, 37 random actions in every year (plant list and offset list overflow, maximum-length placement loops)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -100,3 +102,21 @@ def test_random_full_trajectories_hit_every_capacity(gpu_ctx, oracle_world):
         for y in full_years[:5]:
             assert rs_[y][0].tobytes() == ers_[y][0].tobytes() and rs_[y][1].tobytes() == ers_[y][1].tobytes()
     assert (res["flags"] & 1).any() and (res["flags"] & 2).any(), "the overflow paths were not exercised"
+
+
+@pytest.mark.timeout(300)
+def test_deficit_handler_ends_on_a_full_plant_list():
+    """A map whose 2025 demand needs far more capacity than 560 plants can supply: the deficit loop must leave with
+    EG_FLAG_GEN_OVERFLOW set instead of spinning on a plant list that no longer grows — in rollout and in replay mode."""
+    from eirgrid_b200 import synthetic
+    assets = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ireland_map")
+    sx, sy, spop, ex, ey, et, ec, cx, cy = synthetic.load_ireland_arrays(assets)
+    spop = np.full_like(spop, 40_000_000)  # 130 settlements x 40 M people x 1 kW = 5.2 TW
+    ctx = _lib.Context(0)
+    ctx.map_set(sx, sy, spop, ex, ey, et, ec, cx, cy, 51, 1000.0)
+    res, traj, _, _ = ctx.rollout(_lib.Weights(), 64, seed=3)
+    assert (res["flags"] & _abi.FLAG_GEN_OVERFLOW).all() and (res["n_generators"] == 560).all()
+    assert (res["power_reliability"] == 0.0).all()
+    rres, _, _ = ctx.replay(traj[:8])
+    assert (rres["flags"] & _abi.FLAG_GEN_OVERFLOW).all()
+    ctx.close()
