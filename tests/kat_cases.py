@@ -184,3 +184,87 @@ def toy_2025_metrics():
     m["total_cost"] = m["yearly_total_cost"]
     m["active_generators"] = 1
     return site, m
+
+
+# ---- (d): the same world with three carbon offsets added in 2025; years 2025 and 2026 ---------------------------------------
+FOREST_100, ACTIVE_CAPTURE_120, CARBON_CREDIT_150 = 45, 45 + 3 * 2 + 1, 45 + 3 * 3 + 2
+
+
+def toy_offsets_record():
+    """2025: Biomass by the deficit handler, then AddCarbonOffset(Forest, 100 %), (ActiveCapture, 120 %), (CarbonCredit, 150 %)"""
+    return np.atleast_1d(record({0: ([BIOMASS], [FOREST_100, ACTIVE_CAPTURE_120, CARBON_CREDIT_150])}))
+
+
+def carbon_price(year):
+    """const_funcs.rs:186-203 with constants.rs:258-267"""
+    if year < 2030:
+        return 75.0
+    if year < 2040:
+        return 75.0 + ((year - 2030) / 10.0) * (130.0 - 75.0)
+    if year <= 2050:
+        return 130.0 + ((year - 2040) / 10.0) * (300.0 - 130.0)
+    return 300.0
+
+
+def toy_offsets_metrics():
+    """YearlyMetrics of 2025 and 2026 (metrics_calculation.rs:32-175) for toy_offsets_record()"""
+    site, px, py = placement_site()
+    out = []
+    prev = None
+    pops = [20000, 10000]
+    for year in (2025, 2026):
+        m = {}
+        if year > 2025:
+            pops = [int(math.floor(p * 1.01 + 0.5)) for p in pops]                       # simulation.rs:110-113, f64::round
+        per_capita = 0.001 * math.pow(1.0 + 0.02, float(year - 2025))                     # const_funcs.rs:17-26
+        usage = 0.0
+        for p in pops:
+            usage += float(p) * per_capita                                                # simulation.rs:116-118 / settlements_loader.rs:30
+        m["total_population"] = sum(pops)
+        m["total_power_usage"] = usage * (1.0 + (float(year) - 2024.0) * 0.02)            # map_handler.rs:819-827
+        m["total_power_generation"] = 50.0 * 0.99 * 1.0
+        m["power_balance"] = m["total_power_generation"] - m["total_power_usage"]
+        inflation = (1.0 + 0.0185) ** (year - 2025)                                       # powi, const_funcs.rs:13-15
+        m["inflation_factor"] = inflation
+        # emissions: the Biomass plant; offsets in insertion order (carbon_offset.rs:210-232, completion year 2025: delays are off)
+        m["total_co2_emissions"] = 1500.0 * 1.0 * 1.0 * (1.0 - (0.99 - 0.99))
+        maturity = min(max(1.0 - math.exp(-0.1 * float(year - 2025)), 0.0), 1.0)
+        offset = 0.0
+        offset += 500.0 * 25.0 * 0.85 * maturity          # Forest, 500 ha
+        offset += 100.0 * 500.0 * 0.85 * 1.0              # ActiveCapture, 100 units
+        offset += 1000.0 * 100.0 * 0.85 * 1.0             # CarbonCredit, 1000 units
+        m["total_carbon_offset"] = offset
+        m["net_co2_emissions"] = m["total_co2_emissions"] - offset
+        credit = (-m["net_co2_emissions"]) * carbon_price(year) if m["net_co2_emissions"] < 0.0 else 0.0   # const_funcs.rs:206-219
+        m["yearly_carbon_credit_revenue"] = credit
+
+        def capital(y):  # calc_total_capital_cost(y): new plants, then offsets (map_handler.rs:951-965)
+            infl = (1.0 + 0.0185) ** (y - 2025)
+            gen = 150000000.0 * infl * math.pow(0.99, float(y - 2025)) * 1.0   # const_funcs.rs:56
+            gen = gen * 1.0                                                     # generator.rs:593
+            offs = 0.0
+            for base, mult in ((1000000.0, 1.0), (1000000000.0, 1.2), (50000000.0, 1.5)):
+                offs += (base * infl) * mult                                    # carbon_offset.rs:188-195
+            return gen, gen + offs
+        gen_cost, total_capital = capital(year)
+        m["total_capital_cost"] = total_capital
+        # 2025: plants built this year + offsets whose id "starts" in 2025 (always: quirk Q6); later: difference of the re-priced totals
+        m["yearly_capital_cost"] = total_capital if year == 2025 else total_capital - capital(year - 1)[1]
+        # opinion of the one plant
+        settlement_opinions = 0.0
+        for sx, sy in zip(TOY["sx"], TOY["sy"]):
+            settlement_opinions += 1.0 / (1.0 + math.sqrt((sx - px) ** 2 + (sy - py) ** 2) / 10000.0)
+        type_opinion = min(max(0.60 + 0.001 * float(year - 2025), 0.0), 1.0)
+        normalized = gen_cost / (1384000000.0 * inflation)
+        cost_opinion = 1.0 - normalized
+        m["average_public_opinion"] = 0.03 * (settlement_opinions / 2.0) + 0.12 * type_opinion + 0.82 * cost_opinion
+        sales = m["power_balance"] * 8.76 * 50000.0 if m["power_balance"] > 0.0 else 0.0
+        m["yearly_energy_sales_revenue"] = sales
+        m["yearly_total_cost"] = m["yearly_capital_cost"] + 0.0 + 0.0 - credit - sales
+        m["total_cost"] = m["yearly_total_cost"] if prev is None else prev["total_cost"] + m["yearly_total_cost"]
+        m["total_carbon_credit_revenue"] = credit if prev is None else prev["total_carbon_credit_revenue"] + credit
+        m["total_energy_sales_revenue"] = sales if prev is None else prev["total_energy_sales_revenue"] + sales
+        m["active_generators"] = 1
+        out.append(m)
+        prev = m
+    return site, out

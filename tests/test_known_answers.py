@@ -90,6 +90,40 @@ def test_one_plant_world_2025_hand_values_oracle():
         _check_toy_year(res, sites, yearly, "oracle fast=%s" % fast)
 
 
+def _check_offset_years(res, sites, yearly, what):
+    site, years = K.toy_offsets_metrics()
+    assert int(sites["site"][0][0]) == site
+    for yi, m in enumerate(years):
+        row = yearly["y"][0][yi]
+        for f, v in m.items():
+            if isinstance(v, int):
+                assert int(row[f]) == v, (what, 2025 + yi, f)
+            else:
+                np.testing.assert_allclose(row[f], v, rtol=RTOL, atol=1e-9 if v == 0.0 else 0, err_msg="%s: %d %s" % (what, 2025 + yi, f))
+    assert int(res["n_offsets"][0]) == 3
+
+
+def test_offsets_and_second_year_hand_values_oracle():
+    """CO2 and offset accounting (maturity curve, capture efficiency), offset cost with multipliers, carbon-credit revenue,
+    re-priced capital cost of year 2 minus year 1, population growth and per-capita demand of 2026, by hand"""
+    _, years = K.toy_offsets_metrics()
+    assert years[0]["total_carbon_offset"] == 127500.0 and years[0]["yearly_carbon_credit_revenue"] == 126000.0 * 75.0
+    assert years[1]["total_population"] == 20200 + 10100 and years[1]["total_carbon_offset"] > years[0]["total_carbon_offset"]
+    for fast in (True, False):
+        world = O.World.from_arrays(*K.toy_map_arrays(), fast=fast)
+        res, _, sites, yearly = world.replay(K.toy_offsets_record(), mode=O.FAST if fast else O.FAITHFUL)
+        _check_offset_years(res, sites, yearly, "oracle fast=%s" % fast)
+
+
+@pytest.mark.gpu
+def test_offsets_and_second_year_hand_values_kernel():
+    ctx = _lib.Context(0)
+    ctx.map_set(*K.toy_map_arrays())
+    res, sites, yearly = ctx.replay(K.toy_offsets_record())
+    _check_offset_years(res, sites, yearly, "CUDA kernel")
+    ctx.close()
+
+
 @pytest.mark.gpu
 def test_one_plant_world_2025_hand_values_kernel():
     ctx = _lib.Context(0)
