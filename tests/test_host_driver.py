@@ -135,3 +135,30 @@ def test_host_two_gpus_equal_one_gpu(host_binary, tmp_path):
     assert np.array_equal(np.ctypeslib.as_array(out[0].weights), np.ctypeslib.as_array(out[1].weights))
     assert np.array_equal(np.ctypeslib.as_array(out[0].deficit_weights), np.ctypeslib.as_array(out[1].deficit_weights))
     assert list(out[0].best_metrics) == list(out[1].best_metrics)
+
+
+def test_analyze_locations_tool_flags_and_failure_without_gpu(host_binary):
+    """host/analyze_locations.cpp mirrors aiSimulator/bin/analyze_locations.rs:7-17 (flags -m / -o / -c with the same defaults)"""
+    tool = os.path.join(os.path.dirname(host_binary), "analyze_locations")
+    assert os.path.exists(tool)
+    out = subprocess.run([tool, "--help"], capture_output=True, text=True)
+    assert out.returncode == 0
+    for flag in ("--min-suitability", "--output-file", "--cache-dir", "0.3", "location_analysis.txt", "cache"):
+        assert flag in out.stdout
+    bad = subprocess.run([tool, "--min-suitability", "abc"], capture_output=True, text=True)
+    assert bad.returncode == 2 and "invalid value" in bad.stderr
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([tool, "--assets", ASSETS], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_analyze_locations_tool_writes_both_files(host_binary, tmp_path):
+    tool = os.path.join(os.path.dirname(host_binary), "analyze_locations")
+    cache, txt = str(tmp_path / "cache"), str(tmp_path / "location_analysis.txt")
+    r = subprocess.run([tool, "--assets", ASSETS, "-c", cache, "-o", txt, "-m", "0.3"], capture_output=True, text=True)
+    assert r.returncode == 0 and "Analysis complete!" in r.stdout, r.stderr
+    d = json.load(open(os.path.join(cache, "location_analysis.json")))
+    assert len(d["locations"]) == 2601 and d["type_counts"]["OnshoreWind"] == 2601 and d["type_counts"]["OffshoreWind"] == 2421
+    assert open(txt).read().startswith("Location Analysis Results\n========================\n\nTotal suitable locations: 2601\n")
