@@ -320,6 +320,12 @@ def run_suitability(args, emit):
     edge_tests = n_coast * (19 * n_sites + 441 * water_sites) * mine_frac
     algo_bytes = n_mine * per_site * 8 + (2 * n_coast + 2 * info["n_settlements"]) * 8 + 26 * info["n_settlements"] * 12
     achieved = algo_bytes / (kernel_ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "suitability_traffic.json")
+    if os.path.exists(tp):
+        prof = json.load(open(tp))
+        if prof.get("sites_per_launch") == n_sites and world == prof.get("n_gpus", 1) and args.suitability_map == "ireland":
+            traffic = prof.get("dram_bytes_per_launch")
     line = {"metric": SUIT_METRIC, "value": value, "unit": SUIT_UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": suitability_workload_text(args, info), "sites": n_sites, "sites_on_water": water_sites,
@@ -330,7 +336,7 @@ def run_suitability(args, emit):
             "e2e": {"value": e2e, "unit": SUIT_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": n_mine * per_site * 8,
                     "what": "eg_location_analysis_sites with a HOST output buffer: kernel + device-to-host copy of this rank's scores inside the call"},
             "gpu_launches": int(launches), "clocks": clock_summary,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "eg_suitability_kernel (+ eg_suit_rows_kernel, the crossing lists)", "algorithmic_bytes_per_launch": algo_bytes,
                          "edge_tests": {"per_launch": edge_tests, "g_per_s": edge_tests / (kernel_ms / 1e3) / 1e9,
                                         "what": "ALGORITHMIC point-in-polygon edge tests (const_funcs.rs:143-158): 19 probes per site + 441 per site on "

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(128) eg_suit_rows_kernel(const EgSuitabilityPa
   bool in_map;
   const double y = slot_y(site_coord(p, j), slot, &in_map);
   double* list = rows + (size_t)j * kRowDoubles + slot * kListStride;
+  double sorted[kMaxCrossings];  // thread-local (L1-resident) while the list is built, written out once
   int c = 0;
   if (p.n_coast > 0) {
     double xj = p.cx[p.n_coast - 1], yj = p.cy[p.n_coast - 1];
@@ -97,14 +98,15 @@ __global__ void __launch_bounds__(128) eg_suit_rows_kernel(const EgSuitabilityPa
         if (c < kMaxCrossings) {  // insertion into the ascending list
           const double x = (xj - xi) * (y - yi) / (yj - yi) + xi;
           int t = c;
-          while (t > 0 && list[t] > x) { list[1 + t] = list[t]; t--; }
-          list[1 + t] = x;
+          while (t > 0 && sorted[t - 1] > x) { sorted[t] = sorted[t - 1]; t--; }
+          sorted[t] = x;
         }
         c++;
       }
       xj = xi; yj = yi;
     }
   }
+  for (int t = 0; t < min(c, kMaxCrossings); t++) list[1 + t] = sorted[t];
   list[0] = c <= kMaxCrossings ? (double)c : -1.0;   // -1: more crossings than a list holds, probes of this row test every edge
   if (slot == 0) rows[(size_t)j * kRowDoubles + kSlots * kListStride] = 0.0;  // the pad element
 }
@@ -199,26 +201,36 @@ __global__ void __launch_bounds__(128) eg_suitability_kernel(const EgSuitability
     uint32_t nearby[EG_SUIT_MAX_YEARS];
 #pragma unroll
     for (int y = 0; y < EG_SUIT_MAX_YEARS; y++) nearby[y] = 0u;
+    // (a settlement farther than every radius in play, with a metre of margin for the rounding of the square root, can
+    //  satisfy neither test: its square root is not taken)
+    const double reach = fmax(p.urban_r_max, 5000.0) + 1.0, reach2 = reach * reach;
+    bool found = false;
     for (int s = lane; s < p.n_settlements; s += 32) {
       const double dx = sx[s] - px, dy = sy[s] - py;
-      const double distance = sqrt(dx * dx + dy * dy);
-      if (distance < p.urban_r_max) {
+      const double d2 = dx * dx + dy * dy;
+      if (d2 < reach2) {
+        const double distance = sqrt(d2);
+        if (distance < p.urban_r_max) {
 #pragma unroll
-        for (int y = 0; y < EG_SUIT_MAX_YEARS; y++)
-          if (y < p.n_years && distance < __ldg(&p.urban_r[(size_t)(p.year_first + y) * p.n_settlements + s])) urban |= 1u << y;
-      }
-      if (distance <= 5000.0) {
+          for (int y = 0; y < EG_SUIT_MAX_YEARS; y++)
+            if (y < p.n_years && distance < __ldg(&p.urban_r[(size_t)(p.year_first + y) * p.n_settlements + s])) urban |= 1u << y;
+        }
+        if (distance <= 5000.0) {
+          found = true;
 #pragma unroll
-        for (int y = 0; y < EG_SUIT_MAX_YEARS; y++)
-          if (y < p.n_years) nearby[y] += __ldg(&p.pop[(size_t)(p.year_first + y) * p.n_settlements + s]);
+          for (int y = 0; y < EG_SUIT_MAX_YEARS; y++)
+            if (y < p.n_years) nearby[y] += __ldg(&p.pop[(size_t)(p.year_first + y) * p.n_settlements + s]);
+        }
       }
     }
-    urban = __reduce_or_sync(0xFFFFFFFFu, urban);
     uint32_t my_nearby = 0u;
+    if (__any_sync(0xFFFFFFFFu, found || urban != 0u)) {  // most sites have no settlement within reach: nothing to reduce
+      urban = __reduce_or_sync(0xFFFFFFFFu, urban);
 #pragma unroll
-    for (int y = 0; y < EG_SUIT_MAX_YEARS; y++) {
-      const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, nearby[y]);
-      if (lane == y) my_nearby = total;
+      for (int y = 0; y < EG_SUIT_MAX_YEARS; y++) {
+        const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, nearby[y]);
+        if (lane == y) my_nearby = total;
+      }
     }
 
     // OnshoreWind's neighbour penalty (:1329-1337) is a float sum in generator order: the distances are computed by all
@@ -230,9 +242,12 @@ __global__ void __launch_bounds__(128) eg_suitability_kernel(const EgSuitability
       bool hit = false;
       if (g < p.n_generators) {
         const double dx = __ldg(&p.gx[g]) - px, dy = __ldg(&p.gy[g]) - py;
-        const double d = sqrt(dx * dx + dy * dy);
-        hit = d < 3000.0;
-        term = 0.1 / (1.0 + d);
+        const double d2 = dx * dx + dy * dy;
+        if (d2 < 3001.0 * 3001.0) {  // d < 3000 is impossible beyond 3001 m
+          const double d = sqrt(d2);
+          hit = d < 3000.0;
+          term = 0.1 / (1.0 + d);
+        }
       }
       unsigned hits = __ballot_sync(0xFFFFFFFFu, hit);
       while (hits) {

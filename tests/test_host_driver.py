@@ -157,7 +157,8 @@ def test_analyze_locations_tool_flags_and_failure_without_gpu(host_binary):
 def test_analyze_locations_tool_writes_both_files(host_binary, tmp_path):
     tool = os.path.join(os.path.dirname(host_binary), "analyze_locations")
     cache, txt = str(tmp_path / "cache"), str(tmp_path / "location_analysis.txt")
-    r = subprocess.run([tool, "--assets", ASSETS, "-c", cache, "-o", txt, "-m", "0.3"], capture_output=True, text=True)
+    # (0.2: the shipped cache holds scores down to 0.24, so it was written with a threshold below the tool's default of 0.3)
+    r = subprocess.run([tool, "--assets", ASSETS, "-c", cache, "-o", txt, "-m", "0.2"], capture_output=True, text=True)
     assert r.returncode == 0 and "Analysis complete!" in r.stdout, r.stderr
     d = json.load(open(os.path.join(cache, "location_analysis.json")))
     assert len(d["locations"]) == 2601 and d["type_counts"]["OnshoreWind"] == 2601 and d["type_counts"]["OffshoreWind"] == 2421
