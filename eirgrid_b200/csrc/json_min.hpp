@@ -2,6 +2,7 @@
 // settlements.json, coastline_points.json (inputs of the reference's loaders) and the weights
 // checkpoints (SerializableWeights, ai/learning/serialization.rs:37-51). Host-only.
 #pragma once
+#include <charconv>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -183,10 +184,9 @@ inline std::string fmt_double(double v) {
   if (v != v || v == HUGE_VAL || v == -HUGE_VAL) return "null";
   if (v == 0.0) return std::signbit(v) ? "-0.0" : "0.0";
   char buf[40];
-  for (int prec = 0; prec <= 16; prec++) {  // %.{prec}e has prec + 1 significant digits
-    std::snprintf(buf, sizeof(buf), "%.*e", prec, v);
-    if (std::strtod(buf, nullptr) == v) break;
-  }
+  // std::to_chars without a precision: the shortest digits that round-trip (libstdc++ implements it with Ryu, like serde_json)
+  const std::to_chars_result tc = std::to_chars(buf, buf + sizeof(buf) - 1, v, std::chars_format::scientific);
+  *tc.ptr = 0;
   // buf = [-]d[.ddd]e[+-]xx
   std::string text(buf), digits, out;
   const bool negative = text[0] == '-';

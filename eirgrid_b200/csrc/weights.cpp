@@ -43,7 +43,7 @@ double score_w(const eg_weights& W, const double m[4]) { return eg_score(m, W.op
 bool contains(const std::vector<uint8_t>& v, uint8_t a) { return std::find(v.begin(), v.end(), a) != v.end(); }
 
 // ---- JSON <-> action code ---------------------------------------------------------------------------------
-void write_action(std::string& o, int code, const std::string& ind) {
+std::string render_action(int code, const std::string& ind) {
   // SerializableAction, ai/actions/serializable_action.rs:6-13 (field order of the struct)
   const char* type = "DoNothing";
   std::string gen = "null", id = "null", pct = "null", off = "null", mult = "null";
@@ -52,6 +52,7 @@ void write_action(std::string& o, int code, const std::string& ind) {
   else if (code == EG_ACT_UPGRADE) { type = "UpgradeEfficiency"; id = "\"\""; }
   else if (code == EG_ACT_ADJUST) { type = "AdjustOperation"; id = "\"\""; pct = "0"; }
   else if (code == EG_ACT_CLOSE) { type = "CloseGenerator"; id = "\"\""; }
+  std::string o;
   o += ind + "{\n";
   o += ind + "  \"action_type\": \"" + type + "\",\n";
   o += ind + "  \"generator_type\": " + gen + ",\n";
@@ -60,6 +61,22 @@ void write_action(std::string& o, int code, const std::string& ind) {
   o += ind + "  \"offset_type\": " + off + ",\n";
   o += ind + "  \"cost_multiplier\": " + mult + "\n";
   o += ind + "}";
+  return o;
+}
+
+// a checkpoint holds ~3,600 action objects out of 61 different ones at two indentations: each text is rendered once
+void write_action(std::string& o, int code, const std::string& ind) {
+  static std::string cache[2][EG_N_ACTIONS];
+  static bool ready = false;
+  static const std::string kInd[2] = {"        ", "      "};
+  if (!ready) {
+    for (int i = 0; i < 2; i++)
+      for (int c = 0; c < EG_N_ACTIONS; c++) cache[i][c] = render_action(c, kInd[i]);
+    ready = true;
+  }
+  for (int i = 0; i < 2; i++)
+    if (ind == kInd[i] && code >= 0 && code < EG_N_ACTIONS) { o += cache[i][code]; return; }
+  o += render_action(code, ind);
 }
 
 // a JSON number as the u32 the reference's struct declares (serde fails the load on anything else); a missing or null
