@@ -189,11 +189,11 @@ def run_multi_simulation(asset_dir, num_iterations, parallel=True, continue_from
             st = trainer.step()
         else:
             # Replay batches and the sequential modes run the reference's per-episode rule (it rebuilds the doubled records of
-            # replay iterations, quirk Q10). The rule is sequential in the episodes, so with several ranks every rank rolls out
-            # the SAME episode ids and applies the same update to its own copy of the weights: identical kernels on identical
-            # inputs give identical tables on every rank without an exchange (the extra GPUs add nothing in this phase).
-            advance = min(per_gpu, phase_end - completed)
+            # replay iterations, quirk Q10). The rule is sequential in the episodes: with several ranks the ROLLOUT of the batch is
+            # sharded and the records are all-gathered, then every rank applies the same in-order update to the whole batch on
+            # its own GPU (identical inputs, identical tables, no further exchange). "sequential-host" replicates everything.
             if update_mode == "sequential-host":
+                advance = min(per_gpu, phase_end - completed)
                 trainer.n = advance
                 trainer.upload_weights()
                 trainer.launch_rollout(first_episode=trainer.next_episode)
@@ -201,7 +201,8 @@ def run_multi_simulation(asset_dir, num_iterations, parallel=True, continue_from
                 st = weights.update(res, traj, replay_best=replay_best, rng_seed=rng_seed)
                 trainer.next_episode += advance
             else:
-                st = trainer.step_inorder(advance, rng_seed=rng_seed)
+                advance = min(per_gpu * world, phase_end - completed)
+                st = trainer.step_inorder_sharded(advance, rng_seed=rng_seed)
         completed += advance
         n_flagged += int(st.n_flagged)
         if st.n_flagged and rank == 0:

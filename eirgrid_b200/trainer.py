@@ -200,6 +200,38 @@ class BatchTrainer:
         self.last_stats = st
         return st
 
+    def step_inorder_sharded(self, total=None, rng_seed=0):
+        """The reference's rule on several GPUs: the batch's episodes are rolled out in shards (rank r takes its slice of the
+        ids, like step()), every rank's results and action records are all-gathered over NVLink (1,152 B per episode), and
+        every rank then applies the per-episode update to the whole batch in episode order on its own GPU
+        (eg_update_device) — the rule is sequential in the episodes, so the update itself is replicated, identical inputs
+        giving identical tables without a further exchange. With one rank this is step_inorder()."""
+        torch = _torch()
+        total = self.n_total if total is None else int(total)
+        if not (self.dist and self.world > 1):
+            return self.step_inorder(total, rng_seed=rng_seed)
+        self.set_batch(total)
+        slot = shard_of(total, 0, self.world)[1]  # the largest shard: the gather moves equal slots
+        rb, tb = _abi.RESULT_DTYPE.itemsize, _abi.TRAJ_DTYPE.itemsize
+        if getattr(self, "_gather_slot", 0) < slot:
+            self.d_all_results = torch.empty(self.world * slot * rb, dtype=torch.uint8, device=self.device)
+            self.d_all_traj = torch.empty(self.world * slot * tb, dtype=torch.uint8, device=self.device)
+            self._gather_slot = slot
+        self.upload_weights()
+        self.launch_rollout()
+        with torch.cuda.stream(self.stream):
+            self.dist.all_gather_into_tensor(self.d_all_results[:self.world * slot * rb], self.d_results[:slot * rb])
+            self.dist.all_gather_into_tensor(self.d_all_traj[:self.world * slot * tb], self.d_traj[:slot * tb])
+            if total % self.world:  # ragged: the shorter shards leave a hole at the end of their slot; close the gaps
+                res = torch.cat([self.d_all_results[r * slot * rb:(r * slot + shard_of(total, r, self.world)[1]) * rb] for r in range(self.world)])
+                traj = torch.cat([self.d_all_traj[r * slot * tb:(r * slot + shard_of(total, r, self.world)[1]) * tb] for r in range(self.world)])
+            else:
+                res, traj = self.d_all_results, self.d_all_traj
+        st = self.ctx.update_device(self.weights, total, res, traj, replay_best=bool(self.cfg.replay_best), rng_seed=rng_seed)
+        self.next_episode += total
+        self.last_stats = st
+        return st
+
     def fetch_results(self):
         """Copy this rank's last batch to the host as structured arrays (results, trajectories)."""
         self.stream.synchronize()

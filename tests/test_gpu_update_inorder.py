@@ -219,3 +219,16 @@ def test_train_batch_inorder_equals_rollout_plus_host_update(gpu_ctx):
         s1 = w1.update(res, traj, rng_seed=step)
         s2 = gpu_ctx.train_batch_inorder(w2, n, seed=8, first_episode=step * n, rng_seed=step)
         _assert_same(w1, w2, s1, s2, "step %d" % step)
+
+
+def test_inorder_rule_sharded_over_two_gpus_equals_one_gpu():
+    """BatchTrainer.step_inorder_sharded under torchrun with 2 ranks (rollouts sharded, records all-gathered over NCCL, in-order
+    update replicated): same weights as one GPU alone, bit for bit. Needs two GPUs; skipped on a single-GPU box."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(ROOT, "scripts", "inorder_sharded_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "inorder sharded ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
