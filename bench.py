@@ -440,12 +440,12 @@ def main():
             tr.launch_rollout(first_episode=first_of(W + k))
             ev[k][1].record(tr.stream)
             tr.launch_stats()
-            tr._pack_best()
             ev[k][3].record(tr.stream)
-            tr.exchange()  # the one collective of the step: all-gather of [statistics | best-episode record]
+            tr.exchange()  # the one exchange of the step: [statistics | best-episode record] of every rank onto every rank
             ev[k][2].record(tr.stream)
         barrier()
         launches = tr.ctx.kernel_launches() - launches0
+        tr.check_exchange()
         step_ms = sum(ev[k][0].elapsed_time(ev[k][2]) for k in range(K))
         rollout_ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(K)) / K
         collective_us = sum(ev[k][3].elapsed_time(ev[k][2]) for k in range(K)) / K * 1e3
@@ -602,7 +602,8 @@ def main():
                    "rollout_kernel_ms": rollout_ms,
                    "value_on_trained_table": value_trained,
                    "value_with_yearly_metrics": value_yearly,
-                   "collective": {"what": "one all-gather of [statistics int64[5156] | best-episode record 1168 B] per step, summed locally in rank order",
+                   "collective": {"what": "one exchange of [statistics int64[5156] | best-episode record 1168 B] per step onto every rank, summed locally in rank order",
+                                  "how": tr.exchange_kind,
                                   "bytes_per_rank": tr.pack_words * 8, "us_per_step": collective_us if world > 1 else 0.0},
                    "weights_sha256_16_after_e2e": weights_sha,
                    "episodes_per_step_total": n_total},

@@ -175,7 +175,51 @@ __global__ void __launch_bounds__(320) eg_stats_pack_best_kernel(const eg_result
   else if (w < 4 + kRes + kTraj) record[w] = ((const uint32_t*)(trajs + idx))[w - 4 - kRes];
 }
 
+// block b of rank r: r's buffer -> slot r of peer b's gather buffer (half `epoch & 1`), then flag r on peer b, then wait for
+// flag b on r. The two halves alternate: a rank cannot start epoch e + 2 before every peer has started e + 1, i.e. has
+// finished reading e (stream order on the peer), so a half is never overwritten while it is read.
+__global__ void __launch_bounds__(256) eg_pack_exchange_kernel(const EgExchangeParams p) {
+  constexpr int kRec = (int)(EG_BEST_RECORD_BYTES / 8), kWords = EG_STATS_WORDS + kRec;
+  constexpr int kRes = (int)sizeof(eg_result) / 8;
+  const uint32_t peer = blockIdx.x;
+  const unsigned long long raw = *p.best_index;
+  const uint32_t idx = raw < p.n ? (uint32_t)raw : (p.n ? p.n - 1 : 0);
+  long long* dst = (long long*)p.peer_buf[peer] + ((size_t)(p.epoch & 1u) * p.world + p.rank) * kWords;
+  const long long* res = (const long long*)(p.results + idx);
+  const long long* trj = (const long long*)(p.trajs + idx);
+  for (int i = threadIdx.x; i < kWords; i += blockDim.x) {
+    long long v;
+    if (i < EG_STATS_WORDS) v = p.stats[i];
+    else {
+      const int w = i - EG_STATS_WORDS;  // [score f64 | global id i64 | eg_result | eg_traj]
+      v = w == 0 ? __double_as_longlong(*p.best_score) : w == 1 ? (long long)(p.first_global + idx) : w < 2 + kRes ? res[w - 2] : trj[w - 2 - kRes];
+    }
+    dst[i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t* remote = (uint32_t*)p.peer_flag[peer] + p.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(p.epoch) : "memory");
+    const uint32_t* mine = (const uint32_t*)p.peer_flag[p.rank] + peer;
+    const long long t0 = clock64();
+    for (;;) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if ((int32_t)(v - p.epoch) >= 0) break;
+      if (clock64() - t0 > 4000000000ll) { *p.error = 1u; break; }  // ~2 s: a peer that never arrives must not hang the GPU
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t eg_launch_pack_exchange(const EgExchangeParams& p, cudaStream_t stream) {
+  static_assert(EG_BEST_RECORD_BYTES % 8 == 0 && sizeof(eg_result) % 8 == 0 && sizeof(eg_traj) % 8 == 0, "the record is copied in 64-bit words");
+  if (p.world == 0 || p.world > EG_MAX_PEERS || p.rank >= p.world) return cudaErrorInvalidValue;
+  eg_pack_exchange_kernel<<<p.world, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
 
 cudaError_t eg_launch_pack_best(const eg_result* results, const eg_traj* trajs, uint32_t n, const double* best_score,
                                 const unsigned long long* best_index, unsigned long long first_global, void* record, cudaStream_t stream) {
