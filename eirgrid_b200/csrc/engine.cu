@@ -172,7 +172,7 @@ int build_device_map(eg_ctx* c) {
   EG_CUDA(cudaStreamSynchronize(s));
   c->dmap.small = c->d_small;
   c->dmap.plant_terms = c->d_plant_terms;
-  c->dmap.near_wide = c->htab.near_wide;
+  c->dmap.near_geom = c->htab.near_geom;
   c->dmap.site_opinion = c->d_site_opinion;
   c->dmap.coast_factor = c->d_coast;
   c->dmap.order = c->d_order;

@@ -27,7 +27,7 @@
 //    maintaining the map cost more than it saved — 20 % on the shipped map, 45 % on the 10x map — and it was removed.)
 //  * Philox draws are produced 32 at a time (lane l computes draw base+l) and handed out by shuffle.
 //  * Compiled with --fmad=false: + - * / sqrt are the reference's IEEE operations, no contraction.
-//  * The kernel is bound by instruction fetch as much as by issue: it is instantiated per (REPLAY, WIDE, MODE) so that the
+//  * The kernel is bound by instruction fetch as much as by issue: it is instantiated per (REPLAY, GEOM, MODE) so that the
 //    training launch runs an image without the optional outputs, the replay-best branches and the sampler it does not use.
 #include "episode.cuh"
 #include <algorithm>
@@ -38,6 +38,10 @@ extern __shared__ __align__(16) unsigned char smem[];  // dynamic shared memory 
 namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
+#ifndef EG_EVAL_UNROLL
+#define EG_EVAL_UNROLL 2
+#endif
+constexpr int kEvalUnroll = EG_EVAL_UNROLL;  // groups of four plants per trip of the placement evaluation loop
 
 // -DEG_DEBUG_BOUNDS: index checks on the shared-memory structures; a violation sets bit 30 of eg_result.flags, which makes
 // every parity test fail (compute-sanitizer is not available on the GPU pool). Compiled out otherwise.
@@ -61,13 +65,16 @@ constexpr int kOffRows = 0;
 constexpr int kOffScratch = kOffRows + 2 * kRowBytes;           // double2[32] fold staging | double[61] + uint8[64] sorted row
 constexpr int kScratchBytes = 8 * EG_N_ACTIONS + 64;            // 552 >= 512
 constexpr int kOffSortIdx = kOffScratch + 8 * EG_N_ACTIONS;     // uint8[64] (inside the scratch area)
-constexpr int kOffVars = kOffScratch + kScratchBytes;           // double[16]  rarely used episode scalars (kV*)
-constexpr int kOffGxy = kOffVars + 8 * 16;                      // uint16[EG_MAX_NEW_GENERATORS] plant cells (gi << 8) | gj
-constexpr int kOffGat = kOffGxy + 2 * EG_MAX_NEW_GENERATORS;    // uint16[EG_MAX_NEW_GENERATORS] type(4) mult(2) build(5)
+constexpr int kOffVars = (kOffScratch + kScratchBytes + 15) & ~15;  // double[16]  rarely used episode scalars (kV*)
+constexpr int kOffGxy = kOffVars + 8 * 16;                      // uint32[EG_MAX_NEW_GENERATORS] plant words: cell (gi << 8) | gj in the low half,
+                                                                // gi*gi + gj*gj as (q & 63) << 16 | (q >> 6) << 24 in the high half (compact maps)
+constexpr int kOffGat = kOffGxy + 4 * EG_MAX_NEW_GENERATORS;    // uint16[EG_MAX_NEW_GENERATORS] type(4) mult(2) build(5)
 constexpr int kOffOffs = kOffGat + 2 * EG_MAX_NEW_GENERATORS;   // uint16[EG_MAX_OFFSETS]
 constexpr int kOffCounts = kOffOffs + 2 * EG_MAX_OFFSETS;       // uint16[26] deficit + uint16[26] additional recorded per year
 constexpr int kSliceBytes = (kOffCounts + 4 * EG_NY + 15) & ~15;  // 5.6 KB per warp
-static_assert(kOffScratch % 16 == 0 && kOffVars % 8 == 0 && kOffGxy % 8 == 0 && kOffOffs % 4 == 0 && kOffCounts % 4 == 0, "alignment");
+static_assert(kOffScratch % 16 == 0 && kOffVars % 8 == 0 && kOffGxy % 16 == 0 && EG_MAX_NEW_GENERATORS % 4 == 0 && kOffOffs % 4 == 0 && kOffCounts % 4 == 0, "alignment");
+// a plant word no site is in range of (cell (0, 0), squared norm 8191): pads the plant list to a multiple of four on compact maps
+constexpr uint32_t kPlantSentinel = (63u << 16) | (127u << 24);
 // the action record (eg_traj / eg_sites) is written straight to global memory, one slot per recorded action (lane 0), the
 // unused tail once at the end of the episode with 8-byte stores
 static_assert(offsetof(eg_traj, actions) % 8 == 0 && sizeof(eg_traj) % 8 == 0 && EG_TRAJ_CAPACITY % 8 == 0 && sizeof(eg_sites) % 8 == 0, "tail fill uses 8-byte stores");
@@ -201,8 +208,10 @@ __device__ __forceinline__ int deficit_key_action(int k) {
 // no replay-best mode, count weights present — with the plain sampler (iterations_without_improvement <= 500) or the
 // stagnation sampler (> 500) compiled in alone. EG_OPT(x) is x in the general instantiation and false in the lean ones.
 #define EG_OPT(x) (!LEAN && (x))
-template <bool REPLAY, bool WIDE, int MODE>
+// GEOM (EgDeviceMap::near_geom): 0 compact map (at most 64 sites per axis), 1 narrow (at most 128), 2 wide.
+template <bool REPLAY, int GEOM, int MODE>
 struct Warp {
+  static constexpr bool WIDE = GEOM == 2;
   static constexpr bool LEAN = MODE != 0;
   __device__ __forceinline__ bool stagnation() const { return MODE == 0 ? p.policy->iwi > 500 : MODE == 2; }
   const EgEpisodeParams& p;
@@ -231,7 +240,7 @@ struct Warp {
   __device__ Warp(const EgEpisodeParams& p_, uint32_t sb_, int lane_) : p(p_), T(p_.map.small), lane(lane_), sb(sb_) {}
 
   __device__ __forceinline__ double* VARS() const { return (double*)(smem + sb + kOffVars); }
-  __device__ __forceinline__ uint16_t* GXY() const { return (uint16_t*)(smem + sb + kOffGxy); }
+  __device__ __forceinline__ uint32_t* GXY() const { return (uint32_t*)(smem + sb + kOffGxy); }
   __device__ __forceinline__ uint16_t* GAT() const { return (uint16_t*)(smem + sb + kOffGat); }
 
   __device__ __forceinline__ double* LW(int y) const { return (double*)(smem + sb + kOffRows + (y & 1) * kRowBytes); }
@@ -286,13 +295,10 @@ struct Warp {
 #pragma unroll 1
       for (uint32_t i = 0; i < n_gens; i++) {
         const int t = gat[i] & 0xF;
-        const int c = __ldg(&T->acc_class[t]);
-        const double mw = __ldg(&T->net_mw[t]);
-        // adding +0.0 leaves the other two accumulators unchanged bit for bit
-        gen0 += c == EG_ACC_PLAIN ? mw : 0.0;
-        gen1 += c == EG_ACC_INTERMITTENT ? mw : 0.0;
-        gen2 += c == EG_ACC_STORAGE ? mw : 0.0;
-        co2 += __ldg(&T->co2[t]);
+        // (plain, intermittent, storage, CO2) of the type: adding +0.0 leaves the other accumulators unchanged bit for bit
+        const double2 s01 = __ldg((const double2*)&T->type_sums[t][0]), s23 = __ldg((const double2*)&T->type_sums[t][2]);
+        gen0 += s01.x; gen1 += s01.y; gen2 += s23.x;
+        co2 += s23.y;
       }
     }
   }
@@ -312,7 +318,7 @@ struct Warp {
       const uint32_t i = base + lane;
       if (i < n_gens) {
         const uint32_t xy = GXY()[i], at = GAT()[i];
-        const int gj = xy & 0xFF, gi = xy >> 8, t = at & 0xF, m = (at >> 4) & 0x3, b = at >> 6;
+        const int gj = xy & 0xFF, gi = (xy >> 8) & 0xFF, t = at & 0xF, m = (at >> 4) & 0x3, b = at >> 6;
         EG_CHECK(t < EG_NT && m < EG_N_MULTS && b <= y && gi < n && gj < n);
         const double2 pt = plant_terms(t, m, b, y);
         scr[lane] = make_double2(gen_opinion(gi * n + gj, t, y, pt.x), pt.y);
@@ -359,106 +365,154 @@ struct Warp {
     return s;
   }
 
-  // MetalLocationSearch::find_suitable_location (CPU branch) as a 32-wide walk down the pre-sorted site list.
+  // MetalLocationSearch::find_suitable_location (CPU branch) as a 32-wide walk down the pre-sorted site list. Returns the
+  // winning cell as (i << 8) | j (the order of these words is the scan order of the sites), -1 when no site scores above 0.
   __device__ __forceinline__ int place(int t, int y) {
     EG_CHECK(t >= 0 && t < EG_NT);
-    const int pc = __ldg(&T->pclass[t]);
-    const int rc = __ldg(&T->rclass_of_pclass[pc]);
+    // everything the walk needs to know about the type, one 8-byte read: placement class, radius class, water flag and first
+    // entry of the class in the block-shared factor table | first squared cell distance outside the penalty radius
+    const uint2 info = __ldg((const uint2*)&T->place_info[t][0]);
+    const int pc = info.x & 0xF, rc = (info.x >> 4) & 0xF;
     EG_CHECK(pc < EG_N_PCLASS && rc < EG_N_RCLASS);
-    const bool water = __ldg(&T->water_of_pclass[pc]) != 0;
+    const bool water = (info.x & 0x100u) != 0;
+    const int nf_off = (int)(info.x >> 16);
+    const int r2lim = (int)info.y;  // cell offsets with d2 < r2lim are inside the penalty radius
     const int ns = p.map.n_sites, n = p.map.grid_n;
-    const int r2lim = __ldg(&p.map.r2_limit[rc]);  // cell offsets with d2 < r2lim are inside the penalty radius
-    const size_t base = ((size_t)pc * EG_NY + y) * ns;
-    const uint16_t* __restrict__ order = p.map.order + base;
-    const double2* __restrict__ walk = (const double2*)p.map.walk + base;
+    const size_t base = ((size_t)pc * EG_NY + y) * ns + lane;
+    // this lane's entry of the current step; entries past the end of the list read as score 0, which ends the walk
+    const uint16_t* __restrict__ op = p.map.order + base;
+    const double2* __restrict__ wp = (const double2*)p.map.walk + base;
+    int left = ns - lane;  // entries from this lane's position to the end of the list
     // distance/radius by squared cell distance: block-shared copy in shared memory (narrow maps), else global
     // (the block-shared copy sits at the start of the dynamic shared memory)
     const double* __restrict__ nf = p.map.near_factor + rc * p.map.r2_stride;
-    const uint32_t nf_s = opaque((uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)__ldg(&p.map.r2_limit[EG_N_RCLASS + rc]) * 8u);
+    const uint32_t nf_base = opaque((uint32_t)__cvta_generic_to_shared(smem));
+    const uint32_t nf_s = opaque(nf_base + (uint32_t)nf_off * 8u);
     const double size_factor = __ldg(&T->size_factor);
-    const uint16_t* gxy = GXY();
+    const uint32_t* gw = GXY();
     double best_score = 0.0;
-    int best_site = -1;
-    double2 sp_next = lane < ns ? __ldg(&walk[lane]) : make_double2(0.0, 0.0);   // (static score, prefix score)
-    int packed_next = lane < ns ? (int)__ldg(&order[lane]) : 0;                  // (i << 8) | j of the candidate site
-    for (int k0 = 0; k0 < ns; k0 += 32) {
+    int best_cell = -1;
+    double2 sp_next = make_double2(0.0, 0.0);   // (static score, prefix score)
+    int packed_next = 0;                        // (i << 8) | j of the candidate site
+    if (left > 0) { sp_next = __ldg(wp); packed_next = (int)__ldg(op); }
+    for (;;) {
       const double s_static = sp_next.x, pre = sp_next.y;
       const int packed = packed_next;
       {  // entries of the next step: in flight while this step is examined
-        const int kn = k0 + 32 + lane;
+        left -= 32; wp += 32; op += 32;
         sp_next = make_double2(0.0, 0.0);
-        if (kn < ns) { sp_next = __ldg(&walk[kn]); packed_next = (int)__ldg(&order[kn]); }
+        if (left > 0) { sp_next = __ldg(wp); packed_next = (int)__ldg(op); }
       }
-      const double s_first = shfl_f64(s_static, 0);
-      // the list is sorted: nothing from here on can beat the best so far, and zero scores never win
-      if (s_first < best_score || !(s_first > 0.0)) break;
-      const bool live = s_static > 0.0 && !(s_static < best_score);
-      const int site = (packed >> 8) * n + (packed & 0xFF);
-      // every site still in the race is evaluated exactly
-      const bool cand = live;
+      // every site still in the race is evaluated exactly; zero scores never win
+      const bool cand = s_static > 0.0 && !(s_static < best_score);
+      // the list is sorted and lane 0 holds the step's highest static score: when lane 0 is out of the race, nothing from
+      // here on can beat the best so far
+      if ((__ballot_sync(kFull, cand) & 1u) == 0u) break;
 #ifdef EG_WALK_STATS
       dbg_steps++;
+      dbg_evals++;
+      dbg_cands += __popc(__ballot_sync(kFull, cand));
+      dbg_pairs += n_gens;
 #endif
-      {  // (lane 0 holds the step's highest static score, which passed the test above: at least one lane is live)
-#ifdef EG_WALK_STATS
-        dbg_evals++;
-        dbg_cands += __popc(__ballot_sync(kFull, cand));
-        dbg_pairs += n_gens;
-#endif
-        // survivors multiply their factors in plant order (== multiplication order of the reference), one site per lane
-        double sc = pre;
-        if (!WIDE) {
-          // coordinates < 128: both byte differences at once, no borrow between the bytes, then di*di + dj*dj by IDP.4A
-          const uint32_t spo = (uint32_t)packed | 0x8080u;
-          for (uint32_t g = 0; g < n_gens; g++) {
-            const uint32_t v = (spo - gxy[g]) ^ 0x8080u;
-            const int d2 = __dp4a((int)v, (int)v, 0);
-            EG_CHECK(d2 >= 0 && d2 <= 2 * 127 * 127);
-            if (cand && d2 < r2lim) sc *= lds_f64(nf_s + 8u * (uint32_t)d2);  // score *= distance / penalty_radius
-          }
-        } else {
-          const int si = packed >> 8, sj = packed & 0xFF;
-          for (uint32_t g = 0; g < n_gens; g++) {
-            const uint32_t pk = gxy[g];
-            const int dj = sj - (int)(pk & 0xFF), di = si - (int)(pk >> 8);
-            const int d2 = di * di + dj * dj;
-            if (cand && d2 < r2lim) sc *= __ldg(&nf[d2]);
-          }
+      // survivors multiply their factors in plant order (== multiplication order of the reference), one site per lane
+      double sc = pre;
+      if (GEOM == 0) {
+        // coordinates < 64: |s - g|^2 = |s|^2 + |g|^2 - 2 s.g in ONE IDP.4A per (32 sites x 1 plant): the site's bytes are
+        // (-2 sj, -2 si, 1, 64), the plant word's (gj, gi, |g|^2 & 63, |g|^2 >> 6), the accumulator |s|^2 (+ the offset of
+        // the class's factors in the block-shared table, so that the sum addresses the table directly). Four plant words per
+        // 16-byte broadcast read; the list is padded to a multiple of four with words no site is in range of.
+        const uint32_t sa = ((0x8080u - 2u * (uint32_t)packed) ^ 0x8080u) | 0x40010000u;
+        const int sq = __dp4a(packed, packed, nf_off);
+        const uint4* g4 = (const uint4*)gw;
+        const uint32_t groups = (n_gens + 3u) >> 2;
+#ifdef EG_EVAL_PREDICATED
+        const int lim = cand ? nf_off + r2lim : 0;  // squared distances are >= 0: a lane out of the race is in range of nobody
+#pragma unroll kEvalUnroll
+        for (uint32_t q = 0; q < groups; q++) {
+          const uint4 w4 = g4[q];
+          const int d0 = __dp4a((int)sa, (int)w4.x, sq), d1 = __dp4a((int)sa, (int)w4.y, sq);
+          const int d2 = __dp4a((int)sa, (int)w4.z, sq), d3 = __dp4a((int)sa, (int)w4.w, sq);
+          if (d0 < lim) sc *= lds_f64(nf_base + 8u * (uint32_t)d0);  // score *= distance / penalty_radius
+          if (d1 < lim) sc *= lds_f64(nf_base + 8u * (uint32_t)d1);
+          if (d2 < lim) sc *= lds_f64(nf_base + 8u * (uint32_t)d2);
+          if (d3 < lim) sc *= lds_f64(nf_base + 8u * (uint32_t)d3);
         }
-        if (water) sc *= __ldg(&p.map.coast_factor[site]);
-        sc *= size_factor;
-        // strict '>' in scan order: the maximum wins, equal scores keep the lower site. Scores are >= 0, so their
-        // high and low words order like the doubles: two 32-bit maximum reductions give the exact maximum.
-        const uint32_t hi = cand ? (uint32_t)__double2hiint(sc) : 0u;
-        const uint32_t mh = __reduce_max_sync(kFull, hi);
-        const uint32_t lo = (cand && hi == mh) ? (uint32_t)__double2loint(sc) : 0u;
-        const uint32_t ml = __reduce_max_sync(kFull, lo);
-        const int c_site = (int)__reduce_min_sync(kFull, (cand && hi == mh && lo == ml) ? (uint32_t)site : 0x7FFFFFFFu);
-        const double c_score = __hiloint2double((int)mh, (int)ml);
-        if (c_score > best_score || (c_score == best_score && best_site >= 0 && c_site < best_site)) { best_score = c_score; best_site = c_site; }
+#else
+        // No predicates: a plant out of range reads the 1.0 that ends the class's factors (x * 1.0 == x bit for bit), so the
+        // four lookups of a group are in flight together and only the multiplications wait for each other. (Lanes out of the
+        // race multiply along; their result is not looked at.)
+        const int lim = nf_off + r2lim;
+#pragma unroll kEvalUnroll
+        for (uint32_t q = 0; q < groups; q++) {
+          const uint4 w4 = g4[q];
+          const int d0 = min(__dp4a((int)sa, (int)w4.x, sq), lim), d1 = min(__dp4a((int)sa, (int)w4.y, sq), lim);
+          const int d2 = min(__dp4a((int)sa, (int)w4.z, sq), lim), d3 = min(__dp4a((int)sa, (int)w4.w, sq), lim);
+          EG_CHECK(d0 >= nf_off && d1 >= nf_off && d2 >= nf_off && d3 >= nf_off);
+          const double f0 = lds_f64(nf_base + 8u * (uint32_t)d0), f1 = lds_f64(nf_base + 8u * (uint32_t)d1);
+          const double f2 = lds_f64(nf_base + 8u * (uint32_t)d2), f3 = lds_f64(nf_base + 8u * (uint32_t)d3);
+          sc *= f0;  // score *= distance / penalty_radius, in plant order
+          sc *= f1;
+          sc *= f2;
+          sc *= f3;
+        }
+#endif
+      } else if (GEOM == 1) {
+        // coordinates < 128: both byte differences at once, no borrow between the bytes, then di*di + dj*dj by IDP.4A
+        const uint32_t spo = (uint32_t)packed | 0x8080u;
+        const uint16_t* gxy = (const uint16_t*)gw;  // low half of the plant words
+#pragma unroll 4
+        for (uint32_t g = 0; g < n_gens; g++) {
+          const uint32_t v = (spo - gxy[2 * g]) ^ 0x8080u;
+          const int d2 = min(__dp4a((int)v, (int)v, 0), r2lim);
+          EG_CHECK(d2 >= 0);
+          sc *= lds_f64(nf_s + 8u * (uint32_t)d2);  // score *= distance / penalty_radius (1.0 out of range)
+        }
+      } else {
+        const int si = packed >> 8, sj = packed & 0xFF;
+#pragma unroll 4
+        for (uint32_t g = 0; g < n_gens; g++) {
+          const uint32_t pk = gw[g];
+          const int dj = sj - (int)(pk & 0xFF), di = si - (int)((pk >> 8) & 0xFF);
+          const int d2 = min(di * di + dj * dj, r2lim);
+          sc *= __ldg(&nf[d2]);  // the global table holds 1.0 at r2_limit[rc] (host_tables.cpp)
+        }
       }
+      if (water) sc *= __ldg(&p.map.coast_factor[(packed >> 8) * n + (packed & 0xFF)]);
+      sc *= size_factor;
+      // strict '>' in scan order: the maximum wins, equal scores keep the lower site. Scores are >= 0, so their
+      // high and low words order like the doubles: two 32-bit maximum reductions give the exact maximum.
+      const uint32_t hi = cand ? (uint32_t)__double2hiint(sc) : 0u;
+      const uint32_t mh = __reduce_max_sync(kFull, hi);
+      const uint32_t lo = (cand && hi == mh) ? (uint32_t)__double2loint(sc) : 0u;
+      const uint32_t ml = __reduce_max_sync(kFull, lo);
+      const int c_cell = (int)__reduce_min_sync(kFull, (cand && hi == mh && lo == ml) ? (uint32_t)packed : 0x7FFFFFFFu);
+      const double c_score = __hiloint2double((int)mh, (int)ml);
+      if (c_score > best_score || (c_score == best_score && best_cell >= 0 && c_cell < best_cell)) { best_score = c_score; best_cell = c_cell; }
     }
-    return best_site;
+    return best_cell;
   }
 
   // false: the episode's plant list is full (flagged); nothing was added
-  __device__ __forceinline__ bool add_generator(int site, int t, int m, int y) {
+  __device__ __forceinline__ bool add_generator(int cell, int t, int m, int y) {
     if (n_gens >= EG_MAX_NEW_GENERATORS) { flags |= EG_FLAG_GEN_OVERFLOW; return false; }
-    const int n = p.map.grid_n;
-    const int gi = site / n, gj = site - gi * n;
-    EG_CHECK(gi >= 0 && gi < n && gj >= 0 && gj < n && n_gens < EG_MAX_NEW_GENERATORS && t < EG_NT && m < EG_N_MULTS && y < EG_NY);
-    if (lane == 0) { GXY()[n_gens] = (uint16_t)((gi << 8) | gj); GAT()[n_gens] = (uint16_t)pack_attr(t, m, y); }
+    const int gi = cell >> 8, gj = cell & 0xFF;
+    EG_CHECK(gi >= 0 && gi < p.map.grid_n && gj >= 0 && gj < p.map.grid_n && n_gens < EG_MAX_NEW_GENERATORS && t < EG_NT && m < EG_N_MULTS && y < EG_NY);
+    {
+      const uint32_t norm = (uint32_t)(gi * gi + gj * gj);  // fits (q & 63, q >> 6 <= 127) on compact maps, unused elsewhere
+      const uint32_t word = (uint32_t)cell | ((norm & 63u) << 16) | ((norm >> 6) << 24);
+      uint32_t* gw = GXY();
+      if (lane == 0) { gw[n_gens] = word; GAT()[n_gens] = (uint16_t)pack_attr(t, m, y); }
+      else if (GEOM == 0 && lane < 4 && (n_gens & 3u) == 0u) gw[n_gens + lane] = kPlantSentinel;  // pads the new group of four
+    }
     n_gens++;
     __syncwarp();
-    const int cls = __ldg(&T->acc_class[t]);
-    const double mw = __ldg(&T->net_mw[t]);
-    gen0 += cls == EG_ACC_PLAIN ? mw : 0.0;
-    gen1 += cls == EG_ACC_INTERMITTENT ? mw : 0.0;
-    gen2 += cls == EG_ACC_STORAGE ? mw : 0.0;
-    co2 += __ldg(&T->co2[t]);
+    // (plain, intermittent, storage, CO2) of the type: adding +0.0 leaves the other accumulators unchanged bit for bit
+    const double2 s01 = __ldg((const double2*)&T->type_sums[t][0]), s23 = __ldg((const double2*)&T->type_sums[t][2]);
+    gen0 += s01.x; gen1 += s01.y; gen2 += s23.x;
+    co2 += s23.y;
     if (folded) {  // keep this year's folded sums current
       const double2 pt = plant_terms(t, m, y, y);
-      op_sum += gen_opinion(site, t, y, pt.x);
+      op_sum += gen_opinion(gi * p.map.grid_n + gj, t, y, pt.x);
       gcost += pt.y;
       if (y > 0 && lane == 0) VARS()[kVGcostPrev] += gen_cost(t, m, y, y - 1);
     }
@@ -781,9 +835,12 @@ struct Warp {
         int site = -1;
         if (action < 45) {                                   // apply_action, actions.rs:42-76
           const int t = action / 3, m = action - 3 * t;
-          site = place(t, y);
-          if (site < 0) flags |= EG_FLAG_NO_SITE;
-          else if (!add_generator(site, t, m, y) && is_def) site = -1;  // plant list full: the deficit loop is left like below
+          const int cell = place(t, y);
+          if (cell < 0) flags |= EG_FLAG_NO_SITE;
+          else {
+            site = (cell >> 8) * p.map.grid_n + (cell & 0xFF);
+            if (!add_generator(cell, t, m, y) && is_def) site = -1;  // plant list full: the deficit loop is left like below
+          }
         } else if (action < 57) {                            // actions.rs:129-179
           const int a = action - 45;
           const int ot = a / 3;
@@ -933,18 +990,18 @@ struct Warp {
   }
 };
 
-template <bool REPLAY, bool WIDE, int MODE>
+template <bool REPLAY, int GEOM, int MODE>
 __global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) eg_episode_kernel(const __grid_constant__ EgEpisodeParams p, int slice_bytes, int table_bytes) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (!WIDE) {  // block-shared copy of the distance/radius factors at the start of the shared memory
-    double* nf_s = (double*)smem;  // compact: class rc holds its r2_limit[rc] entries from offset r2_limit[6 + rc]
+  if (GEOM != 2) {  // block-shared copy of the distance/radius factors at the start of the shared memory
+    double* nf_s = (double*)smem;  // compact: class rc holds its r2_limit[rc] entries from offset r2_limit[6 + rc], then a 1.0
     for (int rc = 0; rc < EG_N_RCLASS; rc++) {
       const int cnt = __ldg(&p.map.r2_limit[rc]), off = __ldg(&p.map.r2_limit[EG_N_RCLASS + rc]);
-      for (int i = threadIdx.x; i < cnt; i += blockDim.x) nf_s[off + i] = __ldg(&p.map.near_factor[rc * p.map.r2_stride + i]);
+      for (int i = threadIdx.x; i <= cnt; i += blockDim.x) nf_s[off + i] = i < cnt ? __ldg(&p.map.near_factor[rc * p.map.r2_stride + i]) : 1.0;
     }
     __syncthreads();
   }
-  Warp<REPLAY, WIDE, MODE> w(p, opaque((uint32_t)(table_bytes + warp * slice_bytes)), lane);
+  Warp<REPLAY, GEOM, MODE> w(p, opaque((uint32_t)(table_bytes + warp * slice_bytes)), lane);
   // persistent warps: every warp fetches the next unclaimed episode of the batch until none is left, so a short
   // episode never leaves its warp idle while the block's longest one finishes
   for (;;) {
@@ -956,9 +1013,9 @@ __global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) 
   }
 }
 
-template <bool REPLAY, bool WIDE, int MODE>
+template <bool REPLAY, int GEOM, int MODE>
 cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
-  const bool wide = WIDE;
+  const bool wide = GEOM == 2;
   const int slice = kSliceBytes;
   const int shared_tab = wide ? 0 : (p.nf_entries * (int)sizeof(double) + 15) & ~15;
   // as many warps per block as keep several blocks resident in the 227 KB of an SM
@@ -975,16 +1032,16 @@ cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
   Shape local;
   Shape& shape = (dev >= 0 && dev < 64) ? cache[dev] : local;
   if (shape.smem != smem_bytes || shape.resident == 0) {
-    err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, WIDE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, GEOM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
     // shared-memory carveout: room for as many blocks as the register budget allows, the rest stays L1
     const int resident_want = (int)std::min<size_t>(EG_EPISODE_MIN_BLOCKS * (EG_EPISODE_WARPS / warps), (227 * 1024) / (smem_bytes + 1024));
     const int carveout = std::min(100, (int)((resident_want * (smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
-    cudaFuncSetAttribute(eg_episode_kernel<REPLAY, WIDE, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+    cudaFuncSetAttribute(eg_episode_kernel<REPLAY, GEOM, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
     // grid = every block the device can hold at once (a multiple of the SM count), never more warps than episodes
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eg_episode_kernel<REPLAY, WIDE, MODE>, 32 * warps, smem_bytes);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eg_episode_kernel<REPLAY, GEOM, MODE>, 32 * warps, smem_bytes);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     shape.smem = smem_bytes;
@@ -994,7 +1051,7 @@ cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
   if (blocks == 0) return cudaErrorInvalidConfiguration;
   err = cudaMemsetAsync(p.next_episode, 0, sizeof(uint32_t), stream);
   if (err != cudaSuccess) return err;
-  eg_episode_kernel<REPLAY, WIDE, MODE><<<blocks, 32 * warps, smem_bytes, stream>>>(p, slice, shared_tab);
+  eg_episode_kernel<REPLAY, GEOM, MODE><<<blocks, 32 * warps, smem_bytes, stream>>>(p, slice, shared_tab);
   return cudaGetLastError();
 }
 
@@ -1004,11 +1061,12 @@ cudaError_t launch(const EgEpisodeParams& p, cudaStream_t stream) {
   // the training launch (no per-year or per-site outputs, sampling from the weights, count weights present) runs a lean
   // instantiation without the code of those options: the kernel is bound by instruction fetch, and 8 KB of code that
   // never executes still spreads the hot instructions over more cache lines (-10 % time on trained tables)
+  const int geom = p.map.near_geom;
   if (!REPLAY && !p.yearly && !p.sites && !p.replay_best && p.count_weights) {
-    if (p.stagnation) return p.map.near_wide ? launch_as<false, true, 2>(p, stream) : launch_as<false, false, 2>(p, stream);
-    return p.map.near_wide ? launch_as<false, true, 1>(p, stream) : launch_as<false, false, 1>(p, stream);
+    if (p.stagnation) return geom == 0 ? launch_as<false, 0, 2>(p, stream) : geom == 1 ? launch_as<false, 1, 2>(p, stream) : launch_as<false, 2, 2>(p, stream);
+    return geom == 0 ? launch_as<false, 0, 1>(p, stream) : geom == 1 ? launch_as<false, 1, 1>(p, stream) : launch_as<false, 2, 1>(p, stream);
   }
-  return p.map.near_wide ? launch_as<REPLAY, true, 0>(p, stream) : launch_as<REPLAY, false, 0>(p, stream);
+  return geom == 0 ? launch_as<REPLAY, 0, 0>(p, stream) : geom == 1 ? launch_as<REPLAY, 1, 0>(p, stream) : launch_as<REPLAY, 2, 0>(p, stream);
 }
 
 }  // namespace

@@ -29,7 +29,10 @@ struct EgEpisodeParams {
 #define EG_EPISODE_WARPS 4   // episodes (warps) per block for the Irish map; fewer when the per-warp slice is large
 #endif
 #ifndef EG_EPISODE_MIN_BLOCKS
-#define EG_EPISODE_MIN_BLOCKS 5  // register cap 65536 / (128 threads * 5) = 96; measured best of {4w x 4,5,6; 2w x 8,10; 6w x 3; 8w x 2,3} on B200
+// 4 blocks of 4 warps: register cap 128 (the kernels use 113-120, no spills). Round 1 ran 5 blocks (cap 96); since the placement
+// evaluation keeps four table lookups in flight per group of plants (round 2), the schedule that needs ~115 registers is worth
+// more than the fifth warp per scheduler: 3.39 against 3.55 ms per 65,536 episodes (profiles/r02_eval_loop.md).
+#define EG_EPISODE_MIN_BLOCKS 4
 #endif
 
 cudaError_t eg_launch_rollout(const EgEpisodeParams& p, cudaStream_t stream);

@@ -384,12 +384,12 @@ void eg_host_build_tables(const EgHostMap& m, EgHostTables* out) {
     int d2 = 0;
     while (std::sqrt((double)d2 * m.step * m.step) < kRadii[rc]) d2++;
     out->r2_limit[rc] = d2;
-    stride = std::max(stride, d2);
+    stride = std::max(stride, d2 + 1);  // entry r2_limit[rc] of every class stays 1.0: what a plant out of range multiplies by
   }
   out->r2_stride = stride;
   for (int rc = 0, off = 0; rc <= EG_N_RCLASS; rc++) {
     out->r2_limit[EG_N_RCLASS + rc] = off;
-    if (rc < EG_N_RCLASS) off += out->r2_limit[rc];
+    if (rc < EG_N_RCLASS) off += out->r2_limit[rc] + 1;  // the kernel's copy ends every class with a factor of 1.0 (out of range)
   }
   out->near_factor.assign((size_t)EG_N_RCLASS * stride, 1.0);
   for (int rc = 0; rc < EG_N_RCLASS; rc++)
@@ -397,8 +397,20 @@ void eg_host_build_tables(const EgHostMap& m, EgHostTables* out) {
       const double distance = std::sqrt((double)d2 * m.step * m.step);
       out->near_factor[(size_t)rc * stride + d2] = distance / kRadii[rc];
     }
-  // the packed signed-byte cell distance of the kernel needs coordinates below 128; its shared-memory copy of the factor
-  // table holds the entries inside the radii (at most a few KB on maps with cells of 750 m or more)
-  out->near_wide = (m.grid_n > 128 || out->r2_limit[2 * EG_N_RCLASS] > 2048) ? 1 : 0;
+  // the packed signed-byte cell distance of the kernel needs coordinates below 128 (its one-instruction form: below 64); its
+  // shared-memory copy of the factor table holds the entries inside the radii (at most a few KB on maps with cells of 750 m or more)
+  for (int ty = 0; ty < EG_NT; ty++) {
+    T.type_sums[ty][0] = T.type_sums[ty][1] = T.type_sums[ty][2] = 0.0;
+    T.type_sums[ty][T.acc_class[ty] == EG_ACC_PLAIN ? 0 : (T.acc_class[ty] == EG_ACC_INTERMITTENT ? 1 : 2)] = T.net_mw[ty];
+    T.type_sums[ty][3] = T.co2[ty];
+    const int pc = T.pclass[ty], rc = T.rclass_of_pclass[pc];
+    const int table_off = out->r2_limit[EG_N_RCLASS + rc];
+    T.place_info[ty][0] = (uint32_t)pc | ((uint32_t)rc << 4) | ((uint32_t)(T.water_of_pclass[pc] != 0) << 8) | ((uint32_t)(table_off & 0xFFFF) << 16);
+    T.place_info[ty][1] = (uint32_t)out->r2_limit[rc];
+  }
+  out->near_geom = (m.grid_n > 128 || out->r2_limit[2 * EG_N_RCLASS] > 2048) ? 2 : (m.grid_n > 64 ? 1 : 0);
+#ifdef EG_GEOM_NARROW  // A/B builds: the byte-difference form on compact maps too
+  if (out->near_geom == 0) out->near_geom = 1;
+#endif
   (void)kRadius;
 }

@@ -49,6 +49,12 @@ struct EgSmallTables {   // ~35 KB, read-mostly, L1/L2 resident
   uint8_t water_of_pclass[EG_N_PCLASS];
   uint8_t natural_offset[EG_N_OFFSET_TYPES];  // Forest/Wetland mature over time
   uint8_t pad[3];
+  // what a new plant of the type adds to the (plain, intermittent, storage) generation sums and to the CO2 sum: net_mw in the
+  // slot of acc_class, +0.0 in the other two, co2 (read as two 16-byte words)
+  alignas(16) double type_sums[EG_NT][4];
+  // what the placement walk needs per type, one 8-byte read: [0] = pclass | rclass << 4 | water << 8 | (first entry of the radius
+  // class in the block-shared factor table, r2_limit[6 + rclass]) << 16, [1] = r2_limit[rclass]
+  alignas(8) uint32_t place_info[EG_NT][2];
 };
 
 // per simulation-built plant and year, two doubles:
@@ -76,8 +82,10 @@ struct EgDeviceMap {      // device pointers + sizes, passed by value to the ker
   int n_sites;
   int grid_n;
   int kmax;                       // plants farther than kmax-1 cells (in x or y) are outside every radius
-  int near_wide;                  // 1: site coordinates above 127 or a factor table too large for shared memory — the kernel
-                                  // then uses plain integer cell distances and reads the factor table from global memory
+  int near_geom;                  // which form of the cell-distance arithmetic the episode kernel uses: 0 compact (at most 64 sites
+                                  // per axis: one IDP.4A per site and plant), 1 narrow (at most 128: packed byte differences), 2 wide
+                                  // (coordinates above 127 or a factor table too large for shared memory: plain integer cell
+                                  // distances, factor table read from global memory)
 };
 
 #define EG_POLICY_ROW (EG_N_ACTIONS + EG_N_DEFICIT_KEYS + EG_N_COUNT_KEYS + 1)  // 98 doubles = 784 bytes, a multiple of 16
