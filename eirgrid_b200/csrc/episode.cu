@@ -41,6 +41,10 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 #ifndef EG_EVAL_UNROLL
 #define EG_EVAL_UNROLL 2
 #endif
+#ifndef EG_YS_UNROLL
+#define EG_YS_UNROLL 1
+#endif
+constexpr int kYearStartUnroll = EG_YS_UNROLL;
 constexpr int kEvalUnroll = EG_EVAL_UNROLL;  // groups of four plants per trip of the placement evaluation loop
 
 // -DEG_DEBUG_BOUNDS: index checks on the shared-memory structures; a violation sets bit 30 of eg_result.flags, which makes
@@ -132,6 +136,13 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
   return v;
 }
 
+// c + (low half of a as s16) * (byte 0 of b) + (high half of a as s16) * (byte 1 of b), bytes unsigned
+__device__ __forceinline__ int dp2a_lo_su(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
 // keeps a value in a register: the compiler may not re-derive it from its definition inside the hot loops
 __device__ __forceinline__ uint32_t opaque(uint32_t v) {
   asm volatile("" : "+r"(v));
@@ -208,7 +219,8 @@ __device__ __forceinline__ int deficit_key_action(int k) {
 // no replay-best mode, count weights present — with the plain sampler (iterations_without_improvement <= 500) or the
 // stagnation sampler (> 500) compiled in alone. EG_OPT(x) is x in the general instantiation and false in the lean ones.
 #define EG_OPT(x) (!LEAN && (x))
-// GEOM (EgDeviceMap::near_geom): 0 compact map (at most 64 sites per axis), 1 narrow (at most 128), 2 wide.
+// GEOM (EgDeviceMap::near_geom): 0 compact map (at most 64 sites per axis), 1 medium (at most 181; blocks of 8 warps around a
+// factor table of up to 5,600 entries), 2 general (at most 256 sites per axis, factor table read from global memory).
 template <bool REPLAY, int GEOM, int MODE>
 struct Warp {
   static constexpr bool WIDE = GEOM == 2;
@@ -292,7 +304,7 @@ struct Warp {
       gen0 = __ldg(&yr.ex_gen[0]); gen1 = __ldg(&yr.ex_gen[1]); gen2 = __ldg(&yr.ex_gen[2]);
       co2 = __ldg(&yr.ex_co2);
       const uint16_t* gat = GAT();
-#pragma unroll 1
+#pragma unroll kYearStartUnroll
       for (uint32_t i = 0; i < n_gens; i++) {
         const int t = gat[i] & 0xF;
         // (plain, intermittent, storage, CO2) of the type: adding +0.0 leaves the other accumulators unchanged bit for bit
@@ -387,7 +399,6 @@ struct Warp {
     // (the block-shared copy sits at the start of the dynamic shared memory)
     const double* __restrict__ nf = p.map.near_factor + rc * p.map.r2_stride;
     const uint32_t nf_base = opaque((uint32_t)__cvta_generic_to_shared(smem));
-    const uint32_t nf_s = opaque(nf_base + (uint32_t)nf_off * 8u);
     const double size_factor = __ldg(&T->size_factor);
     const uint32_t* gw = GXY();
     double best_score = 0.0;
@@ -425,22 +436,10 @@ struct Warp {
         const int sq = __dp4a(packed, packed, nf_off);
         const uint4* g4 = (const uint4*)gw;
         const uint32_t groups = (n_gens + 3u) >> 2;
-#ifdef EG_EVAL_PREDICATED
-        const int lim = cand ? nf_off + r2lim : 0;  // squared distances are >= 0: a lane out of the race is in range of nobody
-#pragma unroll kEvalUnroll
-        for (uint32_t q = 0; q < groups; q++) {
-          const uint4 w4 = g4[q];
-          const int d0 = __dp4a((int)sa, (int)w4.x, sq), d1 = __dp4a((int)sa, (int)w4.y, sq);
-          const int d2 = __dp4a((int)sa, (int)w4.z, sq), d3 = __dp4a((int)sa, (int)w4.w, sq);
-          if (d0 < lim) sc *= lds_f64(nf_base + 8u * (uint32_t)d0);  // score *= distance / penalty_radius
-          if (d1 < lim) sc *= lds_f64(nf_base + 8u * (uint32_t)d1);
-          if (d2 < lim) sc *= lds_f64(nf_base + 8u * (uint32_t)d2);
-          if (d3 < lim) sc *= lds_f64(nf_base + 8u * (uint32_t)d3);
-        }
-#else
         // No predicates: a plant out of range reads the 1.0 that ends the class's factors (x * 1.0 == x bit for bit), so the
         // four lookups of a group are in flight together and only the multiplications wait for each other. (Lanes out of the
-        // race multiply along; their result is not looked at.)
+        // race multiply along; their result is not looked at.) Measured alternatives, all with identical outputs
+        // (profiles/r02_eval_loop.md): predicated lookups, a two-stage software pipeline, unrolling by 1, 3 and 4.
         const int lim = nf_off + r2lim;
 #pragma unroll kEvalUnroll
         for (uint32_t q = 0; q < groups; q++) {
@@ -455,17 +454,28 @@ struct Warp {
           sc *= f2;
           sc *= f3;
         }
-#endif
       } else if (GEOM == 1) {
-        // coordinates < 128: both byte differences at once, no borrow between the bytes, then di*di + dj*dj by IDP.4A
-        const uint32_t spo = (uint32_t)packed | 0x8080u;
-        const uint16_t* gxy = (const uint16_t*)gw;  // low half of the plant words
-#pragma unroll 4
-        for (uint32_t g = 0; g < n_gens; g++) {
-          const uint32_t v = (spo - gxy[2 * g]) ^ 0x8080u;
-          const int d2 = min(__dp4a((int)v, (int)v, 0), r2lim);
-          EG_CHECK(d2 >= 0);
-          sc *= lds_f64(nf_s + 8u * (uint32_t)d2);  // score *= distance / penalty_radius (1.0 out of range)
+        // up to 181 sites per axis (|g|^2 fits 16 bits): the plant word is cell | |g|^2 << 16, and
+        // |s - g|^2 = (|s|^2 - 2 s.g) + |g|^2 is one IDP.2A (16-bit (-2 sj, -2 si) times the word's two low bytes) and one add
+        // of the word's high half; same groups of four, same unpredicated lookups as on compact maps
+        const int si = packed >> 8, sj = packed & 0xFF;
+        const uint32_t sa = ((uint32_t)(-2 * sj) & 0xFFFFu) | ((uint32_t)(-2 * si) << 16);
+        const int sq = si * si + sj * sj + nf_off;
+        const uint4* g4 = (const uint4*)gw;
+        const uint32_t groups = (n_gens + 3u) >> 2;
+        const int lim = nf_off + r2lim;
+#pragma unroll kEvalUnroll
+        for (uint32_t q = 0; q < groups; q++) {
+          const uint4 w4 = g4[q];
+          const int d0 = min(dp2a_lo_su(sa, w4.x, sq) + (int)(w4.x >> 16), lim), d1 = min(dp2a_lo_su(sa, w4.y, sq) + (int)(w4.y >> 16), lim);
+          const int d2 = min(dp2a_lo_su(sa, w4.z, sq) + (int)(w4.z >> 16), lim), d3 = min(dp2a_lo_su(sa, w4.w, sq) + (int)(w4.w >> 16), lim);
+          EG_CHECK(d0 >= nf_off && d1 >= nf_off && d2 >= nf_off && d3 >= nf_off);
+          const double f0 = lds_f64(nf_base + 8u * (uint32_t)d0), f1 = lds_f64(nf_base + 8u * (uint32_t)d1);
+          const double f2 = lds_f64(nf_base + 8u * (uint32_t)d2), f3 = lds_f64(nf_base + 8u * (uint32_t)d3);
+          sc *= f0;  // score *= distance / penalty_radius, in plant order
+          sc *= f1;
+          sc *= f2;
+          sc *= f3;
         }
       } else {
         const int si = packed >> 8, sj = packed & 0xFF;
@@ -498,11 +508,12 @@ struct Warp {
     const int gi = cell >> 8, gj = cell & 0xFF;
     EG_CHECK(gi >= 0 && gi < p.map.grid_n && gj >= 0 && gj < p.map.grid_n && n_gens < EG_MAX_NEW_GENERATORS && t < EG_NT && m < EG_N_MULTS && y < EG_NY);
     {
-      const uint32_t norm = (uint32_t)(gi * gi + gj * gj);  // fits (q & 63, q >> 6 <= 127) on compact maps, unused elsewhere
-      const uint32_t word = (uint32_t)cell | ((norm & 63u) << 16) | ((norm >> 6) << 24);
+      // |g|^2 next to the cell: as (q & 63, q >> 6 <= 127) on compact maps, as 16 bits on maps of up to 181 sites per axis
+      const uint32_t norm = (uint32_t)(gi * gi + gj * gj);
+      const uint32_t word = (uint32_t)cell | (GEOM == 0 ? ((norm & 63u) << 16) | ((norm >> 6) << 24) : (GEOM == 1 ? norm << 16 : 0u));
       uint32_t* gw = GXY();
       if (lane == 0) { gw[n_gens] = word; GAT()[n_gens] = (uint16_t)pack_attr(t, m, y); }
-      else if (GEOM == 0 && lane < 4 && (n_gens & 3u) == 0u) gw[n_gens + lane] = kPlantSentinel;  // pads the new group of four
+      else if (GEOM != 2 && lane < 4 && (n_gens & 3u) == 0u) gw[n_gens + lane] = GEOM == 0 ? kPlantSentinel : 0xFFFF0000u;  // pads the new group of four
     }
     n_gens++;
     __syncwarp();
@@ -990,8 +1001,11 @@ struct Warp {
   }
 };
 
+// blocks of 4 warps x 4 per SM, or (medium maps: one larger factor table per block) 8 warps x 2: 16 warps per SM, register cap 128
+template <int GEOM> struct Shape { static constexpr int kWarps = GEOM == 1 ? 2 * EG_EPISODE_WARPS : EG_EPISODE_WARPS, kMinBlocks = GEOM == 1 ? EG_EPISODE_MIN_BLOCKS / 2 : EG_EPISODE_MIN_BLOCKS; };
+
 template <bool REPLAY, int GEOM, int MODE>
-__global__ void __launch_bounds__(32 * EG_EPISODE_WARPS, EG_EPISODE_MIN_BLOCKS) eg_episode_kernel(const __grid_constant__ EgEpisodeParams p, int slice_bytes, int table_bytes) {
+__global__ void __launch_bounds__(32 * Shape<GEOM>::kWarps, Shape<GEOM>::kMinBlocks) eg_episode_kernel(const __grid_constant__ EgEpisodeParams p, int slice_bytes, int table_bytes) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (GEOM != 2) {  // block-shared copy of the distance/radius factors at the start of the shared memory
     double* nf_s = (double*)smem;  // compact: class rc holds its r2_limit[rc] entries from offset r2_limit[6 + rc], then a 1.0
@@ -1019,23 +1033,23 @@ cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
   const int slice = kSliceBytes;
   const int shared_tab = wide ? 0 : (p.nf_entries * (int)sizeof(double) + 15) & ~15;
   // as many warps per block as keep several blocks resident in the 227 KB of an SM
-  int warps = EG_EPISODE_WARPS;
-  while (warps > 1 && warps * slice + shared_tab > 100 * 1024) warps >>= 1;
+  int warps = Shape<GEOM>::kWarps;
+  while (warps > 1 && (size_t)Shape<GEOM>::kMinBlocks * (warps * slice + shared_tab + 1024) > 227 * 1024) warps >>= 1;
   const size_t smem_bytes = (size_t)warps * slice + shared_tab;
   if (smem_bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
   // function attributes and the occupancy query are per (device, shared-memory size): done once, then cached
-  struct Shape { size_t smem = 0; int resident = 0; };
-  static thread_local Shape cache[64];
+  struct Cached { size_t smem = 0; int resident = 0; };
+  static thread_local Cached cache[64];
   int dev = 0;
   cudaError_t err = cudaGetDevice(&dev);
   if (err != cudaSuccess) return err;
-  Shape local;
-  Shape& shape = (dev >= 0 && dev < 64) ? cache[dev] : local;
+  Cached local;
+  Cached& shape = (dev >= 0 && dev < 64) ? cache[dev] : local;
   if (shape.smem != smem_bytes || shape.resident == 0) {
     err = cudaFuncSetAttribute(eg_episode_kernel<REPLAY, GEOM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
     // shared-memory carveout: room for as many blocks as the register budget allows, the rest stays L1
-    const int resident_want = (int)std::min<size_t>(EG_EPISODE_MIN_BLOCKS * (EG_EPISODE_WARPS / warps), (227 * 1024) / (smem_bytes + 1024));
+    const int resident_want = (int)std::min<size_t>(Shape<GEOM>::kMinBlocks * (Shape<GEOM>::kWarps / warps), (227 * 1024) / (smem_bytes + 1024));
     const int carveout = std::min(100, (int)((resident_want * (smem_bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
     cudaFuncSetAttribute(eg_episode_kernel<REPLAY, GEOM, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
     // grid = every block the device can hold at once (a multiple of the SM count), never more warps than episodes

@@ -397,8 +397,9 @@ void eg_host_build_tables(const EgHostMap& m, EgHostTables* out) {
       const double distance = std::sqrt((double)d2 * m.step * m.step);
       out->near_factor[(size_t)rc * stride + d2] = distance / kRadii[rc];
     }
-  // the packed signed-byte cell distance of the kernel needs coordinates below 128 (its one-instruction form: below 64); its
-  // shared-memory copy of the factor table holds the entries inside the radii (at most a few KB on maps with cells of 750 m or more)
+  // the kernel's one-instruction cell distance needs coordinates below 64, its two-instruction form |g|^2 < 65536 (181 sites per
+  // axis); both read the factors from a block-shared copy of the table (entries inside the radii: a few KB on maps with cells of
+  // 750 m or more, 27 KB on the 10x grid)
   for (int ty = 0; ty < EG_NT; ty++) {
     T.type_sums[ty][0] = T.type_sums[ty][1] = T.type_sums[ty][2] = 0.0;
     T.type_sums[ty][T.acc_class[ty] == EG_ACC_PLAIN ? 0 : (T.acc_class[ty] == EG_ACC_INTERMITTENT ? 1 : 2)] = T.net_mw[ty];
@@ -408,9 +409,12 @@ void eg_host_build_tables(const EgHostMap& m, EgHostTables* out) {
     T.place_info[ty][0] = (uint32_t)pc | ((uint32_t)rc << 4) | ((uint32_t)(T.water_of_pclass[pc] != 0) << 8) | ((uint32_t)(table_off & 0xFFFF) << 16);
     T.place_info[ty][1] = (uint32_t)out->r2_limit[rc];
   }
-  out->near_geom = (m.grid_n > 128 || out->r2_limit[2 * EG_N_RCLASS] > 2048) ? 2 : (m.grid_n > 64 ? 1 : 0);
-#ifdef EG_GEOM_NARROW  // A/B builds: the byte-difference form on compact maps too
-  if (out->near_geom == 0) out->near_geom = 1;
+  {
+    const int entries = out->r2_limit[2 * EG_N_RCLASS];
+    out->near_geom = (m.grid_n <= 64 && entries <= 2048) ? 0 : ((m.grid_n <= 181 && entries <= 5600) ? 1 : 2);
+  }
+#ifdef EG_GEOM_GENERAL  // A/B builds: every map through the general form
+  out->near_geom = 2;
 #endif
   (void)kRadius;
 }

@@ -83,9 +83,9 @@ struct EgDeviceMap {      // device pointers + sizes, passed by value to the ker
   int grid_n;
   int kmax;                       // plants farther than kmax-1 cells (in x or y) are outside every radius
   int near_geom;                  // which form of the cell-distance arithmetic the episode kernel uses: 0 compact (at most 64 sites
-                                  // per axis: one IDP.4A per site and plant), 1 narrow (at most 128: packed byte differences), 2 wide
-                                  // (coordinates above 127 or a factor table too large for shared memory: plain integer cell
-                                  // distances, factor table read from global memory)
+                                  // per axis: one IDP.4A per site and plant), 1 medium (at most 181: IDP.2A + add; both read the
+                                  // factors from a block-shared copy of the table), 2 general (coordinates up to 255 or a factor
+                                  // table too large for shared memory: plain integer cell distances, table in global memory)
 };
 
 #define EG_POLICY_ROW (EG_N_ACTIONS + EG_N_DEFICIT_KEYS + EG_N_COUNT_KEYS + 1)  // 98 doubles = 784 bytes, a multiple of 16

@@ -68,14 +68,14 @@ def main():
     cubin = [f for f in os.listdir(tmp) if f.startswith("episode")][0]
     sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
     # pick the function whose mangled name matches the kernel's template arguments
-    m_args = re.search(r"eg_episode_kernel<\(bool\)(\d), \(bool\)(\d), \(int\)(\d)>|eg_episode_kernel<(\d), (\d), (\d)>", kname)
+    m_args = re.search(r"eg_episode_kernel<\(bool\)(\d), \(int\)(\d), \(int\)(\d)>|eg_episode_kernel<(\d), (\d), (\d)>", kname)
     a_ = [g for g in m_args.groups() if g is not None] if m_args else ["0", "0", "1"]
     want_replay, want_wide = a_[0] == "1", a_[1] == "1"
     fn_ok, line, m = False, None, {}
     for l in sass.split("\n"):
         s = l.strip()
         if s.startswith(".text."):
-            fn_ok = ("eg_episode_kernelILb%dELb%dELi%sEE" % (want_replay, want_wide, a_[2])) in s
+            fn_ok = ("eg_episode_kernelILb%dELi%sELi%sEE" % (want_replay, a_[1], a_[2])) in s
         mm = re.match(r'//## File "(.*)", line (\d+)', s)
         if mm:
             line = int(mm.group(2)) if mm.group(1).endswith("episode.cu") else -1

@@ -28,7 +28,7 @@ cnt, byfn, on, line = collections.Counter(), collections.Counter(), False, None
 for l in dis.split("\n"):
     s = l.strip()
     if s.startswith(".text."):
-        on = ("eg_episode_kernelILb0ELb0ELi%sEE" % MODE) in s
+        on = ("eg_episode_kernelILb0ELi0ELi%sEE" % MODE) in s
     m = re.match(r'//## File "([^"]+)", line (\d+)', s)
     if m:
         line = (os.path.basename(m.group(1)), int(m.group(2)))

@@ -83,28 +83,35 @@ def _compare(m, n, seed):
 
 @pytest.mark.gpu
 def test_coarse_grid_narrow_map():
-    # 2.5 km cells: radii 3..12 km reach 1..4 cells, uint8 nearest-plant map, other row stride and stamp pattern
+    # 2.5 km cells: radii 3..12 km reach 1..4 cells; compact form of the cell distance (one IDP.4A), 21 sites per axis
     _compare(_subset_map(60, 20, 21, 2500, seed=7), 256, seed=11)
 
 
 @pytest.mark.gpu
 def test_odd_grid_narrow_map():
-    # 47 x 47 sites of 1086 m: row stride padding (48), column alignment classes, 11-cell stamp radius
+    # 47 x 47 sites of 1086 m: compact form, plant lists of every length modulo four (sentinel padding), 11-cell radius
     _compare(_subset_map(130, 59, 47, 1086, seed=8), 256, seed=12)
 
 
 @pytest.mark.gpu
 def test_fine_grid_wide_map():
-    # 500 m cells: 12 km = 24 cells, squared cell distances up to 575 -> quantised map (shift 2)
+    # 500 m cells, 101 sites per axis: 12 km = 24 cells, 1,308 table entries -> medium form (IDP.2A + add, blocks of 8 warps)
     _compare(_subset_map(40, 12, 101, 500, seed=9), 96, seed=13)
 
 
 @pytest.mark.gpu
 def test_more_than_128_sites_per_axis():
-    # coordinates above 127 cannot use the packed signed-byte distance: wide path even though cells are 1 km
+    # 151 sites of 331 m: medium form with coordinates above 127 (unsigned bytes) and squared norms up to 45,000 (16 bits)
     sx, sy, spop, ex, ey, et, ec, cx, cy = synthetic.load_ireland_arrays(ASSETS)
-    # stretch the map by 3: 150 km box would be clamped, so shrink the cell instead: 151 sites of 331 m
     _compare((sx, sy, spop, ex, ey, et, ec, cx, cy, 151, 331.0), 48, seed=14)
+
+
+@pytest.mark.gpu
+def test_more_than_181_sites_per_axis():
+    # 191 sites of 262 m: squared norms no longer fit 16 bits -> general form (integer cell distances, factor table in global
+    # memory, 1.0 at the end of every class)
+    sx, sy, spop, ex, ey, et, ec, cx, cy = synthetic.load_ireland_arrays(ASSETS)
+    _compare((sx, sy, spop, ex, ey, et, ec, cx, cy, 191, 262.0), 32, seed=16)
 
 
 @pytest.mark.gpu
