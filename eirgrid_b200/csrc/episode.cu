@@ -45,6 +45,19 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 #define EG_YS_UNROLL 1
 #endif
 constexpr int kYearStartUnroll = EG_YS_UNROLL;
+#ifndef EG_FOLD_UNROLL
+#define EG_FOLD_UNROLL 2
+#endif
+#ifndef EG_SCAN_UNROLL
+#define EG_SCAN_UNROLL 4
+#endif
+#ifndef EG_TABLE_COPIES
+#define EG_TABLE_COPIES 1
+#endif
+// compact maps: copies of the block-shared factor table, interleaved entry by entry; with 16 copies lane l reads copy l & 15, every
+// lane of a half-warp its own pair of banks, and the lookups of the evaluation loop cannot collide (they are random otherwise)
+constexpr int kTableCopies = EG_TABLE_COPIES;
+constexpr int kFoldUnroll = EG_FOLD_UNROLL, kScanUnroll = EG_SCAN_UNROLL;  // year folds; sequential sampling scans
 constexpr int kEvalUnroll = EG_EVAL_UNROLL;  // groups of four plants per trip of the placement evaluation loop
 
 // -DEG_DEBUG_BOUNDS: index checks on the shared-memory structures; a violation sets bit 30 of eg_result.flags, which makes
@@ -337,7 +350,7 @@ struct Warp {
       }
       __syncwarp();
       const int cnt = min(32u, n_gens - base);
-#pragma unroll 2
+#pragma unroll kFoldUnroll
       for (int j = 0; j < cnt; j++) {
         const double2 v = scr[j];
         op_sum += v.x;
@@ -357,7 +370,7 @@ struct Warp {
       }
       __syncwarp();
       const int cnt = min(32u, n_offs - base);
-#pragma unroll 2
+#pragma unroll kFoldUnroll
       for (int j = 0; j < cnt; j++) {
         const double2 v = scr[j];
         off_amount += v.x;
@@ -441,14 +454,16 @@ struct Warp {
         // race multiply along; their result is not looked at.) Measured alternatives, all with identical outputs
         // (profiles/r02_eval_loop.md): predicated lookups, a two-stage software pipeline, unrolling by 1, 3 and 4.
         const int lim = nf_off + r2lim;
+        constexpr uint32_t kStride = 8u * kTableCopies;
+        const uint32_t nf_lane = nf_base + 8u * ((uint32_t)lane & (kTableCopies - 1));
 #pragma unroll kEvalUnroll
         for (uint32_t q = 0; q < groups; q++) {
           const uint4 w4 = g4[q];
           const int d0 = min(__dp4a((int)sa, (int)w4.x, sq), lim), d1 = min(__dp4a((int)sa, (int)w4.y, sq), lim);
           const int d2 = min(__dp4a((int)sa, (int)w4.z, sq), lim), d3 = min(__dp4a((int)sa, (int)w4.w, sq), lim);
           EG_CHECK(d0 >= nf_off && d1 >= nf_off && d2 >= nf_off && d3 >= nf_off);
-          const double f0 = lds_f64(nf_base + 8u * (uint32_t)d0), f1 = lds_f64(nf_base + 8u * (uint32_t)d1);
-          const double f2 = lds_f64(nf_base + 8u * (uint32_t)d2), f3 = lds_f64(nf_base + 8u * (uint32_t)d3);
+          const double f0 = lds_f64(nf_lane + kStride * (uint32_t)d0), f1 = lds_f64(nf_lane + kStride * (uint32_t)d1);
+          const double f2 = lds_f64(nf_lane + kStride * (uint32_t)d2), f3 = lds_f64(nf_lane + kStride * (uint32_t)d3);
           sc *= f0;  // score *= distance / penalty_radius, in plant order
           sc *= f1;
           sc *= f2;
@@ -625,14 +640,14 @@ struct Warp {
     double total;
     if (dw_dirty) {
       total = 0.0;
-      #pragma unroll 4
+      #pragma unroll kScanUnroll
       for (int k = 0; k < 14; k++) total += ldw[k];
     } else {
       total = __ldg(&p.policy->dw_total[y]);  // same left-to-right sum, done once per snapshot on the host
     }
     if (total <= 0.0) return kGasPeaker100;
     double rv = f64() * total;
-    #pragma unroll 4
+    #pragma unroll kScanUnroll
     for (int k = 0; k < 14; k++) {
       rv -= ldw[k];
       if (rv <= 0.0) return deficit_key_action(k);
@@ -648,7 +663,7 @@ struct Warp {
       const double* lcw = LCW(y);
       if (total <= 0.0) return 0;
       double rc = random_val * total;
-      #pragma unroll 4
+      #pragma unroll kScanUnroll
       for (int c = 0; c < EG_N_COUNT_KEYS; c++) {
         rc -= lcw[c];
         if (rc <= 0.0) return min((uint32_t)c, max_possible);
@@ -674,7 +689,7 @@ struct Warp {
     if (rows_dirty) {
       if (!total_valid) {
         double t = 0.0;
-        #pragma unroll 4
+        #pragma unroll kScanUnroll
         for (int k = 0; k < EG_N_ACTIONS; k++) t += lw[k];
         if (lane == 0) VARS()[kVLwTotal] = t;
         total_valid = true;
@@ -694,14 +709,14 @@ struct Warp {
         sort_local(sb, sb + kOffRows + (uint32_t)(y & 1) * kRowBytes, lane, p.policy->stagnation_power);
         sorted_valid = true;
         double t = 0.0;  // left-to-right sum of the scaled row, once per edit of the row
-        #pragma unroll 4
+        #pragma unroll kScanUnroll
         for (int k = 0; k < EG_N_ACTIONS; k++) t += scl[k];
         if (lane == 0) VARS()[kVScaledTotal] = t;
         __syncwarp();
       }
       const double total_scaled = rows_dirty ? VARS()[kVScaledTotal] : __ldg(&p.policy->scaled_total[y]);
       double rv = f64() * total_scaled;
-      #pragma unroll 4
+      #pragma unroll kScanUnroll
       for (int k = 0; k < EG_N_ACTIONS; k++) {
         rv -= scl[k];
         if (rv <= 0.0) return (smem + sb + kOffSortIdx)[k];
@@ -737,7 +752,7 @@ struct Warp {
       }
     }
 #endif
-    #pragma unroll 4
+    #pragma unroll kScanUnroll
     for (int k = 0; k < EG_N_ACTIONS; k++) {
       rv -= lw[k];
       if (rv <= 0.0) return k;
@@ -1002,7 +1017,10 @@ struct Warp {
 };
 
 // blocks of 4 warps x 4 per SM, or (medium maps: one larger factor table per block) 8 warps x 2: 16 warps per SM, register cap 128
-template <int GEOM> struct Shape { static constexpr int kWarps = GEOM == 1 ? 2 * EG_EPISODE_WARPS : EG_EPISODE_WARPS, kMinBlocks = GEOM == 1 ? EG_EPISODE_MIN_BLOCKS / 2 : EG_EPISODE_MIN_BLOCKS; };
+template <int GEOM> struct Shape {
+  static constexpr bool kLarge = GEOM == 1 || (GEOM == 0 && kTableCopies > 1);  // one large table per block: fewer, larger blocks
+  static constexpr int kWarps = kLarge ? 2 * EG_EPISODE_WARPS : EG_EPISODE_WARPS, kMinBlocks = kLarge ? EG_EPISODE_MIN_BLOCKS / 2 : EG_EPISODE_MIN_BLOCKS;
+};
 
 template <bool REPLAY, int GEOM, int MODE>
 __global__ void __launch_bounds__(32 * Shape<GEOM>::kWarps, Shape<GEOM>::kMinBlocks) eg_episode_kernel(const __grid_constant__ EgEpisodeParams p, int slice_bytes, int table_bytes) {
@@ -1011,7 +1029,11 @@ __global__ void __launch_bounds__(32 * Shape<GEOM>::kWarps, Shape<GEOM>::kMinBlo
     double* nf_s = (double*)smem;  // compact: class rc holds its r2_limit[rc] entries from offset r2_limit[6 + rc], then a 1.0
     for (int rc = 0; rc < EG_N_RCLASS; rc++) {
       const int cnt = __ldg(&p.map.r2_limit[rc]), off = __ldg(&p.map.r2_limit[EG_N_RCLASS + rc]);
-      for (int i = threadIdx.x; i <= cnt; i += blockDim.x) nf_s[off + i] = i < cnt ? __ldg(&p.map.near_factor[rc * p.map.r2_stride + i]) : 1.0;
+      const int copies = GEOM == 0 ? kTableCopies : 1;
+      for (int i = threadIdx.x; i < (cnt + 1) * copies; i += blockDim.x) {
+        const int e = i / copies;
+        nf_s[(off + e) * copies + (i - e * copies)] = e < cnt ? __ldg(&p.map.near_factor[rc * p.map.r2_stride + e]) : 1.0;
+      }
     }
     __syncthreads();
   }
@@ -1031,7 +1053,7 @@ template <bool REPLAY, int GEOM, int MODE>
 cudaError_t launch_as(const EgEpisodeParams& p, cudaStream_t stream) {
   const bool wide = GEOM == 2;
   const int slice = kSliceBytes;
-  const int shared_tab = wide ? 0 : (p.nf_entries * (int)sizeof(double) + 15) & ~15;
+  const int shared_tab = wide ? 0 : (p.nf_entries * (int)sizeof(double) * (GEOM == 0 ? kTableCopies : 1) + 15) & ~15;
   // as many warps per block as keep several blocks resident in the 227 KB of an SM
   int warps = Shape<GEOM>::kWarps;
   while (warps > 1 && (size_t)Shape<GEOM>::kMinBlocks * (warps * slice + shared_tab + 1024) > 227 * 1024) warps >>= 1;

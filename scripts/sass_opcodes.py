@@ -11,7 +11,7 @@ import re
 import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-WATCH = ["LDGSTS", "UBLKCP", "SYNCS", "REDUX", "IDP", "DFMA", "DMUL", "DADD", "DSETP", "MUFU", "SHFL", "VOTE", "LDS", "STS", "LDG", "STG", "ATOM", "RED",
+WATCH = ["LDGSTS", "UBLKCP", "SYNCS", "REDUX", "CREDUX", "IDP", "DFMA", "DMUL", "DADD", "DSETP", "MUFU", "SHFL", "VOTE", "LDS", "STS", "LDG", "STG", "ATOM", "RED",
          "BAR", "CALL", "FFMA", "HMMA", "UTMALDG", "LDGDEPBAR", "DEPBAR", "MATCH", "WARPSYNC", "ELECT"]
 
 
@@ -37,7 +37,7 @@ def main():
             if m and func:
                 hist[func][m.group(1)] += 1
                 full = m.group(1) + m.group(2)
-                if m.group(1) in ("IDP", "REDUX", "SYNCS", "UBLKCP", "LDGSTS", "MUFU"):
+                if m.group(1) in ("IDP", "REDUX", "CREDUX", "SYNCS", "UBLKCP", "LDGSTS", "MUFU"):
                     hist[func]["  " + full] += 1
         for func, h in hist.items():
             total = sum(v for k, v in h.items() if not k.startswith("  "))
@@ -53,7 +53,7 @@ def main():
             sub = ", ".join("%s %d" % (k.strip(), v) for k, v in sorted(h.items()) if k.startswith("  "))
             if sub:
                 print("   forms: " + sub)
-            print("   absent: " + ", ".join(k for k in ("DFMA", "FFMA", "HMMA", "UBLKCP", "LDGSTS", "REDUX", "IDP") if not h.get(k, 0)))
+            print("   absent: " + ", ".join(k for k in ("DFMA", "FFMA", "HMMA", "UBLKCP", "LDGSTS", "REDUX", "IDP") if not h.get(k, 0) and not (k == "REDUX" and h.get("CREDUX", 0))))  # CREDUX: the reduction into a uniform register
 
 
 if __name__ == "__main__":
