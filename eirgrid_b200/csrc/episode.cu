@@ -58,6 +58,9 @@ constexpr int kYearStartUnroll = EG_YS_UNROLL;
 // lane of a half-warp its own pair of banks, and the lookups of the evaluation loop cannot collide (they are random otherwise)
 constexpr int kTableCopies = EG_TABLE_COPIES;
 constexpr int kFoldUnroll = EG_FOLD_UNROLL, kScanUnroll = EG_SCAN_UNROLL;  // year folds; sequential sampling scans
+#ifndef EG_EVAL_UNROLL_STAGNATION
+#define EG_EVAL_UNROLL_STAGNATION 1  // the stagnation-sampler instantiation is the larger one: no unrolling there (+2 %)
+#endif
 constexpr int kEvalUnroll = EG_EVAL_UNROLL;  // groups of four plants per trip of the placement evaluation loop
 
 // -DEG_DEBUG_BOUNDS: index checks on the shared-memory structures; a violation sets bit 30 of eg_result.flags, which makes
@@ -82,8 +85,8 @@ constexpr int kOffRows = 0;
 constexpr int kOffScratch = kOffRows + 2 * kRowBytes;           // double2[32] fold staging | double[61] + uint8[64] sorted row
 constexpr int kScratchBytes = 8 * EG_N_ACTIONS + 64;            // 552 >= 512
 constexpr int kOffSortIdx = kOffScratch + 8 * EG_N_ACTIONS;     // uint8[64] (inside the scratch area)
-constexpr int kOffVars = (kOffScratch + kScratchBytes + 15) & ~15;  // double[16]  rarely used episode scalars (kV*)
-constexpr int kOffGxy = kOffVars + 8 * 16;                      // uint32[EG_MAX_NEW_GENERATORS] plant words: cell (gi << 8) | gj in the low half,
+constexpr int kOffVars = (kOffScratch + kScratchBytes + 15) & ~15;  // double[32]  rarely used episode scalars (kV*)
+constexpr int kOffGxy = kOffVars + 8 * 32;                      // uint32[EG_MAX_NEW_GENERATORS] plant words: cell (gi << 8) | gj in the low half,
                                                                 // gi*gi + gj*gj as (q & 63) << 16 | (q >> 6) << 24 in the high half (compact maps)
 constexpr int kOffGat = kOffGxy + 4 * EG_MAX_NEW_GENERATORS;    // uint16[EG_MAX_NEW_GENERATORS] type(4) mult(2) build(5)
 constexpr int kOffOffs = kOffGat + 2 * EG_MAX_NEW_GENERATORS;   // uint16[EG_MAX_OFFSETS]
@@ -97,7 +100,7 @@ constexpr uint32_t kPlantSentinel = (63u << 16) | (127u << 24);
 static_assert(offsetof(eg_traj, actions) % 8 == 0 && sizeof(eg_traj) % 8 == 0 && EG_TRAJ_CAPACITY % 8 == 0 && sizeof(eg_sites) % 8 == 0, "tail fill uses 8-byte stores");
 
 // slots of the per-warp scalar area: values every lane agrees on that are touched a few times per year
-enum { kVTotalCost = 0, kVTotalCredit, kVTotalSales, kVGcostPrev, kVOcostPrev, kVLwTotal, kVInitNet, kVInitOpinion, kVInitBalance, kVInitCost, kVScaledTotal };
+enum { kVTotalCost = 0, kVTotalCredit, kVTotalSales, kVGcostPrev, kVOcostPrev, kVLwTotal, kVInitNet, kVInitOpinion, kVInitBalance, kVInitCost, kVScaledTotal, kVStash /* 13 slots */ };
 
 // ---- Philox4x32-10, counter = (episode lo, episode hi, draw, stream 0), key = seed ------------------------
 __device__ __noinline__ unsigned long long philox_u64(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2) {
@@ -380,6 +383,30 @@ struct Warp {
     }
   }
 
+#ifndef EG_NO_STASH
+  // the episode's running sums and the deficit handler's current state wait in shared memory while the placement walk runs, so the
+  // walk has their 26 registers
+  __device__ __forceinline__ void stash(const State& cur, double remaining) {
+    if (lane == 0) {
+      double* v = VARS() + kVStash;
+      v[0] = gen0; v[1] = gen1; v[2] = gen2; v[3] = co2; v[4] = op_sum; v[5] = gcost; v[6] = ocost; v[7] = off_amount;
+      v[8] = cur.net; v[9] = cur.opinion; v[10] = cur.balance; v[11] = cur.cost; v[12] = remaining;
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ double lds_v(uint32_t addr) const {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void unstash(State& cur, double& remaining) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem) + sb + kOffVars + 8u * kVStash;
+    gen0 = lds_v(a); gen1 = lds_v(a + 8); gen2 = lds_v(a + 16); co2 = lds_v(a + 24); op_sum = lds_v(a + 32); gcost = lds_v(a + 40);
+    ocost = lds_v(a + 48); off_amount = lds_v(a + 56);
+    cur.net = lds_v(a + 64); cur.opinion = lds_v(a + 72); cur.balance = lds_v(a + 80); cur.cost = lds_v(a + 88); remaining = lds_v(a + 96);
+    __syncwarp();  // every lane has its copy before lane 0 may write the slots again
+  }
+#endif
   __device__ __forceinline__ State state(int y) const {  // simulation.rs:122-135
     State s;
     s.net = co2 - off_amount;
@@ -454,9 +481,10 @@ struct Warp {
         // race multiply along; their result is not looked at.) Measured alternatives, all with identical outputs
         // (profiles/r02_eval_loop.md): predicated lookups, a two-stage software pipeline, unrolling by 1, 3 and 4.
         const int lim = nf_off + r2lim;
+        constexpr int kUnroll = EG_EVAL_UNROLL_STAGNATION > 0 && MODE == 2 ? EG_EVAL_UNROLL_STAGNATION : kEvalUnroll;
         constexpr uint32_t kStride = 8u * kTableCopies;
         const uint32_t nf_lane = nf_base + 8u * ((uint32_t)lane & (kTableCopies - 1));
-#pragma unroll kEvalUnroll
+#pragma unroll kUnroll
         for (uint32_t q = 0; q < groups; q++) {
           const uint4 w4 = g4[q];
           const int d0 = min(__dp4a((int)sa, (int)w4.x, sq), lim), d1 = min(__dp4a((int)sa, (int)w4.y, sq), lim);
@@ -861,7 +889,13 @@ struct Warp {
         int site = -1;
         if (action < 45) {                                   // apply_action, actions.rs:42-76
           const int t = action / 3, m = action - 3 * t;
+#ifndef EG_NO_STASH
+          stash(cur, remaining);
           const int cell = place(t, y);
+          unstash(cur, remaining);
+#else
+          const int cell = place(t, y);
+#endif
           if (cell < 0) flags |= EG_FLAG_NO_SITE;
           else {
             site = (cell >> 8) * p.map.grid_n + (cell & 0xFF);
@@ -1016,10 +1050,13 @@ struct Warp {
   }
 };
 
-// blocks of 4 warps x 4 per SM, or (medium maps: one larger factor table per block) 8 warps x 2: 16 warps per SM, register cap 128
+// blocks of 4 warps x 5 per SM, or (medium maps: one larger factor table per block) 10 warps x 2: 20 warps per SM, register cap 96
 template <int GEOM> struct Shape {
   static constexpr bool kLarge = GEOM == 1 || (GEOM == 0 && kTableCopies > 1);  // one large table per block: fewer, larger blocks
-  static constexpr int kWarps = kLarge ? 2 * EG_EPISODE_WARPS : EG_EPISODE_WARPS, kMinBlocks = kLarge ? EG_EPISODE_MIN_BLOCKS / 2 : EG_EPISODE_MIN_BLOCKS;
+#ifndef EG_LARGE_WARPS
+#define EG_LARGE_WARPS (EG_EPISODE_WARPS * EG_EPISODE_MIN_BLOCKS / 2)
+#endif
+  static constexpr int kWarps = kLarge ? EG_LARGE_WARPS : EG_EPISODE_WARPS, kMinBlocks = kLarge ? 2 : EG_EPISODE_MIN_BLOCKS;
 };
 
 template <bool REPLAY, int GEOM, int MODE>
