@@ -618,7 +618,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clock_summary,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "eg_episode_kernel<REPLAY=false, WIDE, MODE=1> (rollout, lean training instantiation)",
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "eg_episode_kernel<REPLAY=false, GEOM, MODE=1> (rollout, lean training instantiation)",
                      "algorithmic_bytes_per_launch": algo_bytes, "issue": issue,
                      "note": "the path moves ~1.2 KB per episode and is bound by warp-instruction issue/latency, not HBM: "
                              "see roofline.issue, DESIGN.md §4.1 and profiles/"},
