@@ -159,6 +159,28 @@ __device__ __forceinline__ int dp2a_lo_su(uint32_t a, uint32_t b, int c) {
   return d;
 }
 
+// walk-list entries are read once per placement step and never again: they stream past the L1 (`LDG.E.NA`, no allocation), which
+// keeps it for the tables that are re-read (type, year and plant terms, site opinions, policy constants): +1 % / +1.8 % (initial /
+// trained table, profiles/r02_eval_loop.md)
+__device__ __forceinline__ double2 ldg_stream(const double2* p) {
+#ifndef EG_WALK_ALLOCATE
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ int ldg_stream(const uint16_t* p) {
+#ifndef EG_WALK_ALLOCATE
+  unsigned short v;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return (int)v;
+#else
+  return (int)__ldg(p);
+#endif
+}
+
 // keeps a value in a register: the compiler may not re-derive it from its definition inside the hot loops
 __device__ __forceinline__ uint32_t opaque(uint32_t v) {
   asm volatile("" : "+r"(v));
@@ -445,14 +467,14 @@ struct Warp {
     int best_cell = -1;
     double2 sp_next = make_double2(0.0, 0.0);   // (static score, prefix score)
     int packed_next = 0;                        // (i << 8) | j of the candidate site
-    if (left > 0) { sp_next = __ldg(wp); packed_next = (int)__ldg(op); }
+    if (left > 0) { sp_next = ldg_stream(wp); packed_next = ldg_stream(op); }
     for (;;) {
       const double s_static = sp_next.x, pre = sp_next.y;
       const int packed = packed_next;
       {  // entries of the next step: in flight while this step is examined
         left -= 32; wp += 32; op += 32;
         sp_next = make_double2(0.0, 0.0);
-        if (left > 0) { sp_next = __ldg(wp); packed_next = (int)__ldg(op); }
+        if (left > 0) { sp_next = ldg_stream(wp); packed_next = ldg_stream(op); }
       }
       // every site still in the race is evaluated exactly; zero scores never win
       const bool cand = s_static > 0.0 && !(s_static < best_score);
