@@ -22,9 +22,10 @@
 //    by static score (the score when no simulation-built plant is in range). A plant in range can only lower a site's
 //    score (all factors < 1, rounding is monotone), so the walk stops once static scores fall below the best exact
 //    score found. Every site still in the race multiplies the factors of the plants in its range in plant order, one
-//    site per lane. (Round 1's earlier versions kept a per-site map of the distance to the nearest new plant to prune
-//    sites by an upper bound before evaluating them; once the evaluation loop was down to ~9 instructions per plant,
-//    maintaining the map cost more than it saved — 20 % on the shipped map, 45 % on the 10x map — and it was removed.)
+//    site per lane: the squared cell distance is ONE dot-product instruction per (site, plant) (|s|^2 + |g|^2 - 2 s.g from
+//    packed bytes), plant words are read four at a time, and a plant out of range multiplies by a 1.0 stored after the
+//    class's factors, so there is no range test and four lookups are in flight (Warp::place). While the walk runs, the
+//    episode's running sums wait in shared memory (Warp::stash): 94 registers, 20 warps per SM.
 //  * Philox draws are produced 32 at a time (lane l computes draw base+l) and handed out by shuffle.
 //  * Compiled with --fmad=false: + - * / sqrt are the reference's IEEE operations, no contraction.
 //  * The kernel is bound by instruction fetch as much as by issue: it is instantiated per (REPLAY, GEOM, MODE) so that the
@@ -38,30 +39,31 @@ extern __shared__ __align__(16) unsigned char smem[];  // dynamic shared memory 
 namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
+
+// Tuning switches of the A/B builds (scripts/build_variants.sh "name:-DEG_...=v"; every setting below is the measured optimum,
+// profiles/r02_eval_loop.md has the table). Outputs do not depend on any of them.
 #ifndef EG_EVAL_UNROLL
-#define EG_EVAL_UNROLL 2
+#define EG_EVAL_UNROLL 2             // groups of four plants per trip of the placement evaluation loop
+#endif
+#ifndef EG_EVAL_UNROLL_STAGNATION
+#define EG_EVAL_UNROLL_STAGNATION 1  // the same in the stagnation-sampler instantiation, the larger one (0: as EG_EVAL_UNROLL)
 #endif
 #ifndef EG_YS_UNROLL
-#define EG_YS_UNROLL 1
+#define EG_YS_UNROLL 1               // year_start's re-sum over the plants
 #endif
-constexpr int kYearStartUnroll = EG_YS_UNROLL;
 #ifndef EG_FOLD_UNROLL
-#define EG_FOLD_UNROLL 2
+#define EG_FOLD_UNROLL 2             // year folds
 #endif
 #ifndef EG_SCAN_UNROLL
-#define EG_SCAN_UNROLL 4
+#define EG_SCAN_UNROLL 4             // sequential sampling scans
 #endif
 #ifndef EG_TABLE_COPIES
-#define EG_TABLE_COPIES 1
-#endif
-// compact maps: copies of the block-shared factor table, interleaved entry by entry; with 16 copies lane l reads copy l & 15, every
-// lane of a half-warp its own pair of banks, and the lookups of the evaluation loop cannot collide (they are random otherwise)
+#define EG_TABLE_COPIES 1            // compact maps: copies of the block-shared factor table, interleaved entry by entry; with 16, lane l
+#endif                               // reads copy l & 15 — no bank conflicts, but 40 KB less L1 per block and 3-6 % slower
+// further: -DEG_NO_STASH (episode state stays in registers across the placement walk), -DEG_WALK_ALLOCATE (walk loads allocate in
+// L1), -DEG_EPISODE_WARPS / -DEG_EPISODE_MIN_BLOCKS / -DEG_LARGE_WARPS (block shapes), -DEG_SCAN_SEQUENTIAL, -DEG_ROWS_SYNC
+constexpr int kEvalUnroll = EG_EVAL_UNROLL, kYearStartUnroll = EG_YS_UNROLL, kFoldUnroll = EG_FOLD_UNROLL, kScanUnroll = EG_SCAN_UNROLL;
 constexpr int kTableCopies = EG_TABLE_COPIES;
-constexpr int kFoldUnroll = EG_FOLD_UNROLL, kScanUnroll = EG_SCAN_UNROLL;  // year folds; sequential sampling scans
-#ifndef EG_EVAL_UNROLL_STAGNATION
-#define EG_EVAL_UNROLL_STAGNATION 1  // the stagnation-sampler instantiation is the larger one: no unrolling there (+2 %)
-#endif
-constexpr int kEvalUnroll = EG_EVAL_UNROLL;  // groups of four plants per trip of the placement evaluation loop
 
 // -DEG_DEBUG_BOUNDS: index checks on the shared-memory structures; a violation sets bit 30 of eg_result.flags, which makes
 // every parity test fail (compute-sanitizer is not available on the GPU pool). Compiled out otherwise.
