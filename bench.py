@@ -585,6 +585,10 @@ def main():
             if T._lib.lib().eg_microbench_fp64(local, ctypes.byref(peak64)) == 0:
                 issue["fp64_peak_tflops_no_fma"] = peak64.value
                 issue["fp64_pipe_active_pct"] = prof.get("fp64_pipe_pct")
+            # the second resource the kernel runs close to (ncu, same capture): the L1 / shared-memory data pipe
+            issue["l1_data_pipe_busy_pct_ncu"] = prof.get("l1_data_pipe_pct")
+            issue["issue_slots_busy_pct_ncu"] = prof.get("issue_active_pct")
+            issue["resident_warps_per_sm_ncu"] = prof.get("resident_warps_per_sm")
         except Exception:
             traffic, issue = None, None
     line = {

@@ -26,6 +26,11 @@ d = {
     "registers_per_thread": get("launch__registers_per_thread"),
     "l2_hit_pct": get("lts__t_sector_hit_rate.pct"), "l1_hit_pct": get("l1tex__t_sector_hit_rate.pct"),
     "fp64_pipe_pct": get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+    # the L1 / shared-memory data pipe (shared-memory and global wavefronts): the second resource the kernel runs close to
+    "l1_data_pipe_pct": get("l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"),
+    "shared_wavefronts": get("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
+    "shared_bank_conflicts": get("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
+    "resident_warps_per_sm": get("sm__warps_active.avg.per_cycle_active"),
 }
 json.dump(d, open(out, "w"), indent=1)
 print(json.dumps(d))
