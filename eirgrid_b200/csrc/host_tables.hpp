@@ -24,7 +24,7 @@ struct EgHostTables {
   int r2_limit[2 * EG_N_RCLASS + 1] = {0};  // limits, compact-table offsets, compact-table size
   int r2_stride = 0;
   int kmax = 0;
-  int near_geom = 0;                 // EgDeviceMap::near_geom (0 compact, 1 narrow, 2 wide)
+  int near_geom = 0;                 // EgDeviceMap::near_geom (0 compact, 1 medium, 2 general)
   std::vector<int> ex_online_year;   // first year in which each pre-existing plant is Operational (quirk Q1); 0 = never
 };
 
